@@ -1,0 +1,600 @@
+"""Host-side engine of the CLIP-HBA forward / live-sub-graph backward on libhba (sm_100a).
+
+The engine owns nothing numerical: it stages the frozen weights once as bf16 (hi[/lo]) GEMM
+operands, owns the HBM workspaces, and sequences C-ABI calls on the current CUDA stream.
+
+What is computed (equal to the reference graph reached through CLIPHBA.forward, NEW:287-304, up to
+fp32 re-association):
+  * vision tower: conv1-as-GEMM, cls/pos, ln_pre, L residual attention blocks, ln_post, proj;
+    the LAST block is evaluated for the CLS query row only (its other rows feed nothing);
+  * text tower: embedding, L_t causal blocks; after the last attention only the EOT rows are kept
+    (everything after it is row-wise);
+  * cosine logits  exp(logit_scale) * <img, txt>.
+Backward covers exactly the sub-graph that reaches trainable parameters in the reference setup
+(NEW:484-544: `out_proj` of the last <= 2 vision blocks and of the last text block): it returns
+dL/dW for those `out_proj.weight` tensors; the DoRA chain rule on top is hba.dora (fused) or plain
+autograd when the reference's own DoRALayer is used.
+
+Precision modes (hba.set_precision):
+  "bf16": bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 residual stream / LN / softmax
+  "fp32": every GEMM runs three bf16 passes over hi/lo split operands (~2^-16 relative error),
+          attention in exact fp32 — the parity mode (1e-3 relative vs the fp32 reference)
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+from .ops import Operand, HBA_ACT_NONE, HBA_ACT_QUICKGELU, HBA_ACT_QUICKGELU_GRAD
+
+_PRECISION = os.environ.get("HBA_PRECISION", "bf16")
+LN_EPS = 1e-5
+
+
+def set_precision(mode: str):
+    global _PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _roundup(v, m):
+    return (v + m - 1) // m * m
+
+
+class _Block:
+    """Staged operands of one residual attention block."""
+    __slots__ = ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_in", "b_in", "w_out", "b_out", "w_fc",
+                 "b_fc", "w_proj", "b_proj", "w_in_t", "w_fc_t", "w_proj_t", "adapter")
+
+
+class _Tower:
+    __slots__ = ("blocks", "d", "heads", "T", "causal")
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self.precision = None
+        self._bufs = {}
+        self._stamp = None
+        self.cache_text = True
+        self._text_cache = None
+        self._gen = 0
+        self.launches = 0  # kernels launched by the last run_forward / run_backward (our own count)
+
+    # ---------------------------------------------------------------- staging
+    @property
+    def split(self):
+        return self.precision == "fp32"
+
+    def _param_stamp(self):
+        return sum(p._version for p in self.model.parameters()) + 7919 * sum(
+            b._version for b in self.model.buffers())
+
+    def _operand(self, W, K_pad=None, transpose=False):
+        W = W.detach()
+        if W.dtype != torch.float32:
+            W = W.float()
+        W = W.contiguous()
+        rows, cols = W.shape
+        if transpose:
+            op = Operand.empty(cols, rows if K_pad is None else K_pad, self.split, W.device,
+                               zero=K_pad is not None)
+        else:
+            op = Operand.empty(rows, cols if K_pad is None else K_pad, self.split, W.device,
+                               zero=K_pad is not None)
+        ops.split_bf16(W, op, transpose=transpose)
+        return op
+
+    def _stage_tower(self, resblocks, T, causal, n_live):
+        tw = _Tower()
+        tw.blocks, tw.T, tw.causal = [], T, causal
+        L = len(resblocks)
+        for i, blk in enumerate(resblocks):
+            b = _Block()
+            attn = blk.attn
+            b.ln1_w, b.ln1_b = blk.ln_1.weight.detach(), blk.ln_1.bias.detach()
+            b.ln2_w, b.ln2_b = blk.ln_2.weight.detach(), blk.ln_2.bias.detach()
+            b.w_in, b.b_in = self._operand(attn.in_proj_weight), attn.in_proj_bias.detach()
+            op = attn.out_proj
+            b.adapter = not isinstance(op, torch.nn.Linear)
+            if b.adapter:
+                b.w_out, b.b_out = None, None  # supplied per call (the adapter's .weight / .bias)
+            else:
+                if op.weight.requires_grad:
+                    raise RuntimeError("libhba: a plain out_proj.weight requires grad; only adapter "
+                                       "modules (DoRA) on out_proj are trainable on this path")
+                b.w_out, b.b_out = self._operand(op.weight), op.bias.detach()
+            b.w_fc, b.b_fc = self._operand(blk.mlp.c_fc.weight), blk.mlp.c_fc.bias.detach()
+            b.w_proj, b.b_proj = self._operand(blk.mlp.c_proj.weight), blk.mlp.c_proj.bias.detach()
+            live = i >= L - n_live
+            b.w_in_t = self._operand(attn.in_proj_weight, transpose=True) if live else None
+            b.w_fc_t = self._operand(blk.mlp.c_fc.weight, transpose=True) if live else None
+            b.w_proj_t = self._operand(blk.mlp.c_proj.weight, transpose=True) if live else None
+            tw.blocks.append(b)
+        tw.d = resblocks[0].attn.embed_dim
+        tw.heads = resblocks[0].attn.num_heads
+        if tw.d // tw.heads != 64:
+            raise RuntimeError("libhba: head_dim must be 64")
+        return tw
+
+    def prepare(self, device):
+        """(Re)stages every frozen weight on `device` in the current precision mode."""
+        m = self.model
+        self.device, self.precision = device, _PRECISION
+        for p in list(m.parameters()) + list(m.buffers()):
+            if p.device != device:
+                raise RuntimeError("libhba: move the model to the CUDA device before calling it")
+        v = m.visual
+        self.P = v.conv1.weight.shape[-1]
+        self.res = v.input_resolution
+        self.grid = self.res // self.P
+        self.vis = self._stage_tower(v.transformer.resblocks, self.grid ** 2 + 1, False, 2)
+        d = self.vis.d
+        self.kp = _roundup(3 * self.P * self.P, 64)
+        self.w_conv = self._operand(v.conv1.weight.detach().reshape(d, -1), K_pad=self.kp)
+        self.cls, self.pos = v.class_embedding.detach(), v.positional_embedding.detach()
+        self._pos_cache = {}
+        self.ln_pre = (v.ln_pre.weight.detach(), v.ln_pre.bias.detach())
+        self.ln_post = (v.ln_post.weight.detach(), v.ln_post.bias.detach())
+        self.proj_t = self._operand(v.proj, transpose=True)   # [E, d]: B operand of x @ proj
+        self.proj_n = self._operand(v.proj)                   # [d, E]: B operand of g @ proj^T
+        self.txt = self._stage_tower(m.transformer.resblocks, m.context_length, True, 1)
+        self.tok_table = m.token_embedding.weight.detach()
+        self.tpos = m.positional_embedding.detach()
+        self.ln_final = (m.ln_final.weight.detach(), m.ln_final.bias.detach())
+        self.tproj_t = self._operand(m.text_projection, transpose=True)
+        self.tproj_n = self._operand(m.text_projection)
+        self.E = m.text_projection.shape[1]
+        self.logit_scale = m.logit_scale.detach().reshape(1)
+        self._bufs.clear()
+        self._text_cache = None
+        self._stamp = self._param_stamp()
+
+    def ensure(self, device):
+        if (self.device != device or self.precision != _PRECISION
+                or self._stamp != self._param_stamp()):
+            self.prepare(device)
+
+    # ---------------------------------------------------------------- workspaces
+    def _buf(self, name, shape, dtype=torch.float32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _opbuf(self, name, rows, K, zero=False):
+        width = 2 * K if self.split else K
+        return Operand(self._buf(name, (rows, width), torch.bfloat16, zero=zero), rows, K,
+                       K if self.split else 0)
+
+    def _positional(self, grid_now):
+        if grid_now == self.grid:
+            return self.pos
+        if grid_now not in self._pos_cache:
+            # CLIP-HBA `pos_embedding=True`: bicubic resize of the patch part of the table
+            # (one-off weight preparation, identity at the native 224^2 resolution)
+            g = self.grid
+            patch = self.pos[1:].reshape(1, g, g, -1).permute(0, 3, 1, 2)
+            patch = torch.nn.functional.interpolate(patch, size=(grid_now, grid_now), mode="bicubic",
+                                                    align_corners=False)
+            patch = patch.permute(0, 2, 3, 1).reshape(grid_now * grid_now, -1)
+            self._pos_cache[grid_now] = torch.cat([self.pos[:1], patch], 0).contiguous()
+        return self._pos_cache[grid_now]
+
+    # ---------------------------------------------------------------- building blocks
+    def _qkv_buffer(self, tag, M, d):
+        return self._buf(tag + ".qkv", (M, 3 * d), torch.float32 if self.split else torch.bfloat16)
+
+    def _gemm_qkv(self, h, w_in, b_in, qkv, M):
+        if self.split:
+            ops.gemm(h, w_in, M, bias=b_in, out_f32=qkv)
+        else:
+            ops.gemm(h, w_in, M, bias=b_in, out=Operand(qkv, M, qkv.shape[1], 0))
+        self.launches += 1
+
+    def _adapter_operands(self, W):
+        """bf16 operands of an adapter weight W [out, in]: (w [out,in], wt [in,out])."""
+        cached = getattr(W, "_hba_ops", None)
+        if cached is not None and cached[2] == self.precision:
+            return cached[0], cached[1]
+        Wd = W.detach()
+        out_f, in_f = Wd.shape
+        w = Operand.empty(out_f, in_f, self.split, Wd.device)
+        wt = Operand.empty(in_f, out_f, self.split, Wd.device)
+        if Wd.t().is_contiguous():
+            base = Wd.t()
+            ops.split_bf16(base, w, transpose=True)
+            ops.split_bf16(base, wt)
+        else:
+            base = Wd.contiguous()
+            ops.split_bf16(base, w)
+            ops.split_bf16(base, wt, transpose=True)
+        self.launches += 2
+        return w, wt
+
+    def _block_full(self, tw, blk, tag, x_in, x_mid, x_out, B, w_out, b_out, keep=None):
+        """One full residual attention block on all M = B*T rows (x_* are fp32 [M, d])."""
+        T, d, H = tw.T, tw.d, tw.heads
+        M = B * T
+        h = self._opbuf(tag + ".h", M, d)
+        ops.layernorm_fwd(x_in, M, d, blk.ln1_w, blk.ln1_b, LN_EPS, y=h)
+        qkv = self._qkv_buffer(tag, M, d)
+        self._gemm_qkv(h, blk.w_in, blk.b_in, qkv, M)
+        a = self._opbuf(tag + ".a", M, d)
+        ops.attention_fwd(qkv, B, T, H, causal=tw.causal, out=a,
+                          out_f32=keep.get("a_f32") if keep else None)
+        ops.gemm(a, w_out, M, bias=b_out, residual=x_in, out_f32=x_mid)
+        ops.layernorm_fwd(x_mid, M, d, blk.ln2_w, blk.ln2_b, LN_EPS, y=h)
+        hid = self._opbuf(tag + ".hid", M, 4 * d)
+        ops.gemm(h, blk.w_fc, M, bias=blk.b_fc, act=HBA_ACT_QUICKGELU, out=hid,
+                 pre_out=keep.get("h_pre") if keep else None)
+        ops.gemm(hid, blk.w_proj, M, bias=blk.b_proj, residual=x_mid, out_f32=x_out)
+        self.launches += 6
+
+    def _rows_tail(self, tw, blk, tag, a_rows, x_res, R, w_out, b_out, keep):
+        """out_proj + MLP of a block on R selected rows (CLS rows / EOT rows).
+        a_rows: Operand [R, d] (attention output rows); x_res: fp32 view [R, *] of the block input
+        rows (row stride arbitrary).  Returns x_out [R, d] fp32."""
+        d = tw.d
+        x_mid = keep["x_mid"] if keep else self._buf(tag + ".xmid", (R, d))
+        ops.gemm(a_rows, w_out, R, bias=b_out, residual=x_res, out_f32=x_mid)
+        h = self._opbuf(tag + ".h2", max(R, 128), d)
+        ops.layernorm_fwd(x_mid, R, d, blk.ln2_w, blk.ln2_b, LN_EPS, y=h)
+        hid = self._opbuf(tag + ".hid2", max(R, 128), 4 * d)
+        ops.gemm(h, blk.w_fc, R, bias=blk.b_fc, act=HBA_ACT_QUICKGELU, out=hid,
+                 pre_out=keep["h_pre"] if keep else None)
+        x_out = keep["x_out"] if keep else self._buf(tag + ".xout", (R, d))
+        ops.gemm(hid, blk.w_proj, R, bias=blk.b_proj, residual=x_mid, out_f32=x_out)
+        self.launches += 4
+        return x_out
+
+    # ---------------------------------------------------------------- forward
+    def _keep(self, name, shape, dtype=torch.float32):
+        return self._buf("keep." + name, shape, dtype)
+
+    def vision_trunk(self, images, upto):
+        """conv1 + cls/pos + ln_pre + blocks [0, upto) on all rows. Returns x fp32 [B*T, d]."""
+        B = images.shape[0]
+        if images.shape[2] % self.P or images.shape[3] % self.P or images.shape[2] != images.shape[3]:
+            raise RuntimeError("libhba: image side must be a multiple of the patch size and square")
+        grid = images.shape[2] // self.P
+        tw = self.vis
+        if grid != self.grid:
+            if not self._pos_flag:
+                raise RuntimeError("libhba: image resolution differs from the model's and "
+                                   "pos_embedding=False")
+            tw = _Tower()
+            tw.blocks, tw.d, tw.heads, tw.causal = self.vis.blocks, self.vis.d, self.vis.heads, False
+            tw.T = grid * grid + 1
+        npatch, d, T = grid * grid, tw.d, tw.T
+        M = B * T
+        images = images.contiguous().float()
+        patches = self._opbuf("v.patches", max(B * npatch, 128), self.kp, zero=True)
+        ops.im2col_patches(images, self.P, patches)
+        conv = self._buf("v.conv", (B * npatch, d))
+        ops.gemm(patches, self.w_conv, B * npatch, out_f32=conv)
+        x = self._buf("v.x", (M, d))
+        ops.assemble_tokens_ln(conv, B, npatch, d, self.cls, self._positional(grid), self.ln_pre[0],
+                               self.ln_pre[1], LN_EPS, x)
+        self.launches += 3
+        for i in range(upto):
+            blk = tw.blocks[i]
+            if blk.adapter:
+                raise RuntimeError("libhba: adapters are supported on the last two vision blocks only")
+            self._block_full(tw, blk, "v", x, x, x, B, blk.w_out, blk.b_out)
+        return x, tw
+
+    def vision_head(self, x, tw, B, adapters, need_grad):
+        """Blocks L-2 (full) and L-1 (CLS row only) + ln_post + proj.  `adapters` maps block index
+        -> (W, bias) for adapter blocks.  Returns (img_feat [B,E] fp32, saved dict)."""
+        L = len(tw.blocks)
+        T, d, H = tw.T, tw.d, tw.heads
+        M = B * T
+        saved = {"B": B, "T": T, "tw": tw}
+        # ---- block P = L-2, all rows
+        if L >= 2:
+            blkP = tw.blocks[L - 2]
+            keepP = None
+            if blkP.adapter:
+                Wp, bp = adapters[L - 2]
+                wP, _ = self._adapter_operands(Wp)
+                trainP = need_grad and Wp.requires_grad
+                saved["trainP"] = trainP
+                if trainP:
+                    keepP = {"a_f32": self._keep("aP", (M, d)),
+                             "h_pre": self._keep("hpreP", (M, 4 * d),
+                                                 torch.float32 if self.split else torch.bfloat16)}
+                    saved["keepP"] = keepP
+                bP = bp.detach()
+            else:
+                wP, bP = blkP.w_out, blkP.b_out
+                saved["trainP"] = False
+            x_mid = self._keep("xmidP", (M, d)) if keepP else x
+            x_out = self._keep("xoutP", (M, d)) if need_grad else x
+            self._block_full(tw, blkP, "v", x, x_mid, x_out, B, wP, bP, keep=keepP)
+            if keepP:
+                keepP["x_mid"] = x_mid
+            x = x_out
+        # ---- block Z = L-1, CLS query rows only
+        blkZ = tw.blocks[L - 1]
+        if blkZ.adapter:
+            Wz, bz = adapters[L - 1]
+            wZ, wtZ = self._adapter_operands(Wz)
+            bZ = bz.detach()
+            trainZ = need_grad and Wz.requires_grad
+        else:
+            wZ, wtZ, bZ, trainZ = blkZ.w_out, None, blkZ.b_out, False
+        keepZ = None
+        if need_grad:
+            keepZ = {"x_mid": self._keep("xmidZ", (B, d)), "x_out": self._keep("xoutZ", (B, d)),
+                     "h_pre": self._keep("hpreZ", (B, 4 * d),
+                                         torch.float32 if self.split else torch.bfloat16),
+                     "a_f32": self._keep("aZ", (B, d)), "x_in": x, "wtZ": wtZ}
+        h = self._opbuf("v.h", M, d)
+        ops.layernorm_fwd(x, M, d, blkZ.ln1_w, blkZ.ln1_b, LN_EPS, y=h)
+        qkv = self._keep("qkvZ", (M, 3 * d), torch.float32 if self.split else torch.bfloat16) \
+            if need_grad else self._qkv_buffer("v", M, d)
+        self._gemm_qkv(h, blkZ.w_in, blkZ.b_in, qkv, M)
+        a_cls = self._opbuf("v.acls", max(B, 128), d)
+        ops.attention_fwd(qkv, B, T, H, first_row_only=True, out=a_cls,
+                          out_f32=keepZ["a_f32"] if keepZ else None)
+        x_cls = x.view(B, T * d)[:, :d]  # CLS rows of the block input, row stride T*d
+        x_out = self._rows_tail(tw, blkZ, "v", a_cls, x_cls, B, wZ, bZ, keepZ)
+        hp = self._opbuf("v.lnpost", max(B, 128), d)
+        ops.layernorm_fwd(x_out, B, d, self.ln_post[0], self.ln_post[1], LN_EPS, y=hp)
+        feat = self._keep("imgfeat", (B, self.E))
+        ops.gemm(hp, self.proj_t, B, out_f32=feat)
+        self.launches += 4
+        saved.update(trainZ=trainZ, keepZ=keepZ, qkvZ=qkv)
+        return feat, saved
+
+    def text_features(self, tokens, adapters, need_grad):
+        """Text tower -> txt_feat [S, E]; the trunk up to the last attention is cached per token
+        tensor (the prompts never change, NEW:282)."""
+        tw = self.txt
+        S, T = tokens.shape
+        d, H, L = tw.d, tw.heads, len(tw.blocks)
+        M = S * T
+        key = (tokens.data_ptr(), tokens._version, S, T)
+        cache = self._text_cache if (self.cache_text and self._text_cache
+                                     and self._text_cache["key"] == key) else None
+        if cache is None:
+            x = self._buf("t.x", (M, d))
+            ops.embed_tokens(tokens, self.tok_table, self.tpos, x)
+            self.launches += 1
+            for i in range(L - 1):
+                blk = tw.blocks[i]
+                if blk.adapter:
+                    raise RuntimeError("libhba: adapters are supported on the last text block only")
+                self._block_full(tw, blk, "t", x, x, x, S, blk.w_out, blk.b_out)
+            blkZ = tw.blocks[L - 1]
+            h = self._opbuf("t.h", M, d)
+            ops.layernorm_fwd(x, M, d, blkZ.ln1_w, blkZ.ln1_b, LN_EPS, y=h)
+            qkv = self._qkv_buffer("t", M, d)
+            self._gemm_qkv(h, blkZ.w_in, blkZ.b_in, qkv, M)
+            a_all = self._buf("t.a_f32", (M, d))
+            ops.attention_fwd(qkv, S, T, H, causal=True, out_f32=a_all)
+            eot = (tokens.argmax(dim=-1) + torch.arange(S, device=tokens.device) * T).contiguous()
+            a_eot = torch.empty(S, d, device=self.device)
+            x_eot = torch.empty(S, d, device=self.device)
+            ops.gather_rows(a_all, eot, d, a_eot)
+            ops.gather_rows(x, eot, d, x_eot)
+            a_op = Operand.empty(max(S, 128), d, self.split, self.device, zero=True)
+            ops.split_bf16(a_eot, a_op)
+            self.launches += 6
+            cache = {"key": key, "a_eot": a_eot, "x_eot": x_eot, "a_op": a_op}
+            if self.cache_text:
+                self._text_cache = cache
+        blkZ = tw.blocks[L - 1]
+        if blkZ.adapter:
+            Wz, bz = adapters[L - 1]
+            wZ, _ = self._adapter_operands(Wz)
+            bZ = bz.detach()
+            trainZ = need_grad and Wz.requires_grad
+        else:
+            wZ, bZ, trainZ = blkZ.w_out, blkZ.b_out, False
+        keepZ = None
+        if need_grad:
+            keepZ = {"x_mid": self._keep("t.xmidZ", (S, d)), "x_out": self._keep("t.xoutZ", (S, d)),
+                     "h_pre": self._keep("t.hpreZ", (S, 4 * d),
+                                         torch.float32 if self.split else torch.bfloat16),
+                     "a_f32": cache["a_eot"]}
+        x_out = self._rows_tail(tw, blkZ, "t", cache["a_op"], cache["x_eot"], S, wZ, bZ, keepZ)
+        hp = self._opbuf("t.lnfinal", max(S, 128), d)
+        ops.layernorm_fwd(x_out, S, d, self.ln_final[0], self.ln_final[1], LN_EPS, y=hp)
+        feat = self._keep("txtfeat", (S, self.E))
+        ops.gemm(hp, self.tproj_t, S, out_f32=feat)
+        self.launches += 2
+        return feat, {"S": S, "trainZ": trainZ, "keepZ": keepZ}
+
+    def run_forward(self, images, tokens, pos_embedding, v_adapters, t_adapters, need_grad):
+        """-> (pred [B, S] fp32 (fresh tensor), saved state for run_backward)."""
+        self.ensure(images.device)
+        self.launches = 0
+        self._pos_flag = bool(pos_embedding)
+        tokens = tokens.reshape(-1, tokens.shape[-1])
+        if tokens.dtype != torch.int64:
+            tokens = tokens.long()
+        tokens = tokens if tokens.is_contiguous() else tokens.contiguous()
+        B = images.shape[0]
+        L = len(self.vis.blocks)
+        x, tw = self.vision_trunk(images, max(L - 2, 0))
+        img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad)
+        txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
+        pred = torch.empty(B, txt_feat.shape[0], device=self.device)
+        ops.cos_head_fwd(img_feat, txt_feat, self.logit_scale, pred)
+        self.launches += 1
+        self._gen += 1
+        return pred, {"v": sv, "t": st, "img_feat": img_feat, "txt_feat": txt_feat, "gen": self._gen}
+
+    # ---------------------------------------------------------------- backward
+    def _grad_operand(self, name, g, rows, cols, transpose=False, k_pad=None):
+        """fp32 gradient [rows, cols] -> bf16 operand ([rows, cols] or, transposed, [cols, k_pad])."""
+        if transpose:
+            op = self._opbuf(name, cols, k_pad, zero=True)
+            ops.split_bf16(g[:rows], op, transpose=True)
+        else:
+            op = self._opbuf(name, max(rows, 128), cols)
+            ops.split_bf16(g[:rows], op)
+        self.launches += 1
+        return op
+
+    def _mlp_rows_bwd(self, blk, tag, dxo, R, d, h_pre, x_mid):
+        """dxo [R, d] holds dL/dx_out; on return it holds dL/dx_mid (MLP + LN2 + residual)."""
+        g1 = self._grad_operand(tag + ".g1", dxo, R, d)
+        gh = self._opbuf(tag + ".gh", max(R, 128), 4 * d)
+        ops.gemm(g1, blk.w_proj_t, R, act=HBA_ACT_QUICKGELU_GRAD, aux=h_pre, out=gh)
+        d_ln2 = self._buf(tag + ".dln2", (R, d))
+        ops.gemm(gh, blk.w_fc_t, R, out_f32=d_ln2)
+        ops.layernorm_bwd(d_ln2, x_mid, R, d, blk.ln2_w, LN_EPS, dxo, accumulate=True)
+        self.launches += 3
+
+    def _dw(self, tag, dY, a_f32, R, d_out, d_in):
+        """dW[out, in] = sum_r dY[r, out] a[r, in] as a GEMM with K = rows (zero padded to 64)."""
+        kp = _roundup(R, 64)
+        # the buffers are keyed by R: their zero K-padding [R, kp) must never hold stale rows
+        A = self._grad_operand(f"{tag}.dyT{R}", dY, R, d_out, transpose=True, k_pad=kp)
+        Bo = self._grad_operand(f"{tag}.aT{R}", a_f32, R, d_in, transpose=True, k_pad=kp)
+        dW = torch.empty(d_out, d_in, device=self.device)
+        ops.gemm(A, Bo, d_out, out_f32=dW)
+        self.launches += 1
+        return dW
+
+    def run_backward(self, saved, d_pred):
+        """-> dict {('v', block_index) | ('t', block_index): dL/dW [out, in] fp32}."""
+        if saved["gen"] != self._gen:
+            raise RuntimeError("libhba: backward called after a newer forward pass overwrote the "
+                               "saved activations (call backward before the next forward)")
+        self.launches = 0
+        grads = {}
+        img_feat, txt_feat = saved["img_feat"], saved["txt_feat"]
+        B, S, E = img_feat.shape[0], txt_feat.shape[0], self.E
+        d_img = self._buf("b.dimg", (B, E))
+        d_txt = self._buf("b.dtxt", (S, E))
+        ops.cos_head_bwd(img_feat, txt_feat, self.logit_scale, d_img, d_txt,
+                         d_pred=d_pred.contiguous().float())
+        self.launches += 1
+        # ------------------------------------------------ text: last block, EOT rows
+        st = saved["t"]
+        if st["trainZ"]:
+            tw = self.txt
+            d, L = tw.d, len(tw.blocks)
+            blk, kz = tw.blocks[L - 1], st["keepZ"]
+            g = self._grad_operand("tb.g0", d_txt, S, E)
+            d_lnf = self._buf("tb.dlnf", (S, d))
+            ops.gemm(g, self.tproj_n, S, out_f32=d_lnf)
+            dxo = self._buf("tb.dxo", (S, d))
+            ops.layernorm_bwd(d_lnf, kz["x_out"], S, d, self.ln_final[0], LN_EPS, dxo)
+            self.launches += 2
+            self._mlp_rows_bwd(blk, "tb", dxo, S, d, kz["h_pre"], kz["x_mid"])
+            grads[("t", L - 1)] = self._dw("tb", dxo, kz["a_f32"], S, d, d)
+        # ------------------------------------------------ vision
+        sv = saved["v"]
+        tw = sv["tw"]
+        L, d, T, H = len(tw.blocks), tw.d, sv["T"], tw.heads
+        M = B * T
+        if sv["trainZ"] or sv.get("trainP"):
+            blkZ, kz = tw.blocks[L - 1], sv["keepZ"]
+            g = self._grad_operand("vb.g0", d_img, B, E)
+            d_lnp = self._buf("vb.dlnp", (B, d))
+            ops.gemm(g, self.proj_n, B, out_f32=d_lnp)
+            dxo = self._buf("vb.dxo", (B, d))
+            ops.layernorm_bwd(d_lnp, kz["x_out"], B, d, self.ln_post[0], LN_EPS, dxo)
+            self.launches += 2
+            self._mlp_rows_bwd(blkZ, "vb", dxo, B, d, kz["h_pre"], kz["x_mid"])  # dxo = dY_Z
+            if sv["trainZ"]:
+                grads[("v", L - 1)] = self._dw("vb", dxo, kz["a_f32"], B, d, d)
+            if sv.get("trainP"):
+                blkP, kp = tw.blocks[L - 2], sv["keepP"]
+                wtZ = kz["wtZ"] if kz["wtZ"] is not None else self._frozen_wt(blkZ)
+                g2 = self._grad_operand("vb.g2", dxo, B, d)
+                d_a = self._buf("vb.da", (B, d))
+                ops.gemm(g2, wtZ, B, out_f32=d_a)
+                d_qkv = self._buf("vb.dqkv", (M, 3 * d))
+                ops.attention_bwd_row0(sv["qkvZ"], B, T, H, d_a, d_qkv)
+                gq = self._grad_operand("vb.gq", d_qkv, M, 3 * d)
+                d_ln1 = self._buf("vb.dln1", (M, d))
+                ops.gemm(gq, blkZ.w_in_t, M, out_f32=d_ln1)
+                dx = self._buf("vb.dx", (M, d))
+                ops.layernorm_bwd(d_ln1, kz["x_in"], M, d, blkZ.ln1_w, LN_EPS, dx)
+                ops.add_rows(dx, dxo, B, d, dst_row_step=T)  # residual path of the CLS rows
+                self.launches += 5
+                self._mlp_rows_bwd(blkP, "vbP", dx, M, d, kp["h_pre"], kp["x_mid"])  # dx = dY_P
+                grads[("v", L - 2)] = self._dw("vbP", dx, kp["a_f32"], M, d, d)
+        return grads
+
+    def _frozen_wt(self, blk):
+        raise RuntimeError("libhba: backward through a frozen out_proj of the last block is not "
+                           "staged (adapter expected on the last vision block)")
+
+
+def get_engine(model) -> Engine:
+    eng = model.__dict__.get("_hba_engine")
+    if eng is None:
+        eng = Engine(model)
+        model.__dict__["_hba_engine"] = eng
+    return eng
+
+
+class _ClipForward(torch.autograd.Function):
+    """preds = CLIP(image, tokens); differentiable w.r.t. the adapter `out_proj.weight` tensors."""
+
+    @staticmethod
+    def forward(ctx, engine, images, tokens, pos_embedding, keys, *tensors):
+        n = len(keys)
+        weights, biases = tensors[:n], tensors[n:]
+        v_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "v"}
+        t_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "t"}
+        need_grad = any(ctx.needs_input_grad[5:5 + n])
+        if any(ctx.needs_input_grad[5 + n:]):
+            raise RuntimeError("libhba: adapter biases are frozen on this path (NEW:535-536)")
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("libhba: gradients w.r.t. the input images are not supported")
+        pred, saved = engine.run_forward(images, tokens, pos_embedding, v_ad, t_ad, need_grad)
+        ctx.engine, ctx.saved, ctx.keys = engine, saved, keys
+        return pred
+
+    @staticmethod
+    def backward(ctx, d_pred):
+        grads = ctx.engine.run_backward(ctx.saved, d_pred)
+        out = []
+        for i, k in enumerate(ctx.keys):
+            g = grads.get(k)
+            if ctx.needs_input_grad[5 + i] and g is None:
+                raise RuntimeError(f"libhba: no gradient path staged for adapter {k}")
+            out.append(g if ctx.needs_input_grad[5 + i] else None)
+        return (None, None, None, None, None, *out, *([None] * len(ctx.keys)))
+
+
+def clip_forward(model, image, text, pos_embedding=False):
+    """Entry point used by the plug-in CLIP module's ``forward`` (src/models/CLIPs/clip_hba/clip.py)."""
+    if not image.is_cuda:
+        raise RuntimeError("libhba has no CPU path: move the model and the images to a CUDA device "
+                           "(sm_100a)")
+    eng = get_engine(model)
+    keys, weights, biases = [], [], []
+    for side, blocks in (("v", model.visual.transformer.resblocks), ("t", model.transformer.resblocks)):
+        for i, blk in enumerate(blocks):
+            op = blk.attn.out_proj
+            if not isinstance(op, torch.nn.Linear):
+                keys.append((side, i))
+                weights.append(op.weight)   # DoRALayer.weight property: merged W [out, in]
+                biases.append(op.bias)
+    if torch.is_grad_enabled() and any(w.requires_grad for w in weights):
+        return _ClipForward.apply(eng, image, text, pos_embedding, tuple(keys), *weights, *biases)
+    with torch.no_grad():
+        v_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "v"}
+        t_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "t"}
+        pred, _ = eng.run_forward(image, text, pos_embedding, v_ad, t_ad, False)
+    return pred

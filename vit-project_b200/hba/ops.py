@@ -1,0 +1,240 @@
+"""Torch-tensor front ends of the libhba C-ABI (device memory + stream plumbing only).
+
+Every function takes CUDA tensors, passes raw pointers / leading dimensions / the current stream to
+the C-ABI and raises ``RuntimeError`` on failure.  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (HBA_ACT_GELU_ERF, HBA_ACT_GELU_ERF_GRAD, HBA_ACT_NONE, HBA_ACT_QUICKGELU,
+                   HBA_ACT_QUICKGELU_GRAD, HBA_DT_BF16, HBA_DT_F32, GemmParams, check)
+
+__all__ = ["gemm", "split_bf16", "layernorm_fwd", "layernorm_bwd", "im2col_patches",
+           "assemble_tokens_ln", "embed_tokens", "gather_rows", "attention_fwd",
+           "attention_bwd_row0", "dora_merge_fwd", "dora_merge_bwd", "cos_head_fwd", "cos_head_bwd",
+           "adamw_multi", "sgd_multi", "rdm_f64", "rank_avg_f64", "pearson_f64", "softmax_ce",
+           "add_rows", "nonfinite_flag", "Operand"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "libhba operates on CUDA tensors only (no CPU fallback)"
+    return C.c_void_p(t.data_ptr())
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return HBA_DT_F32
+    if t.dtype == torch.bfloat16:
+        return HBA_DT_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+class Operand:
+    """A bf16 GEMM operand [rows, K] with an optional lo part (fp32 mode): ``buf`` is
+    [rows, ld] bf16 with hi at columns [0, K) and, when ``lo_off > 0``, lo at [lo_off, lo_off+K)."""
+    __slots__ = ("buf", "rows", "K", "lo_off")
+
+    def __init__(self, buf, rows, K, lo_off):
+        self.buf, self.rows, self.K, self.lo_off = buf, rows, K, lo_off
+
+    @property
+    def ld(self):
+        return self.buf.stride(0)
+
+    @staticmethod
+    def empty(rows, K, split, device, zero=False):
+        width = 2 * K if split else K
+        f = torch.zeros if zero else torch.empty
+        return Operand(f(rows, width, dtype=torch.bfloat16, device=device), rows, K, K if split else 0)
+
+    def narrow_rows(self, start, n):
+        return Operand(self.buf.narrow(0, start, n), n, self.K, self.lo_off)
+
+
+def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_ACT_NONE, aux=None,
+         pre_out=None, out_f32=None, out: Operand = None, transpose_out=False, alpha=1.0,
+         max_ctas=0):
+    """C[M,N] = epilogue(A . B^T) on the tcgen05 tensor pipe (hba_gemm_bf16)."""
+    M = a.rows if M is None else M
+    N, K = b.rows, b.K
+    assert a.K == K, (a.K, K)
+    split = a.lo_off > 0 and b.lo_off > 0
+    p = GemmParams()
+    p.A, p.B = a.buf.data_ptr(), b.buf.data_ptr()
+    p.M, p.N, p.K = M, N, K
+    p.lda, p.ldb = a.ld, b.ld
+    p.nsplit = 3 if split else 1
+    p.a_lo_off, p.b_lo_off = (a.lo_off, b.lo_off) if split else (0, 0)
+    p.alpha = alpha
+    p.bias = bias.data_ptr() if bias is not None else None
+    if residual is not None:
+        p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
+    p.act = act
+    if aux is not None:
+        p.aux, p.ld_aux, p.aux_dtype = aux.data_ptr(), aux.stride(0), _dt(aux)
+    if pre_out is not None:
+        p.pre_out, p.ld_pre, p.pre_dtype = pre_out.data_ptr(), pre_out.stride(0), _dt(pre_out)
+    if out_f32 is not None:
+        p.out_f32, p.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out is not None:
+        p.out_bf16, p.ld_bf16, p.out_lo_off = out.buf.data_ptr(), out.ld, out.lo_off
+    p.transpose_out = 1 if transpose_out else 0
+    p.max_ctas = max_ctas
+    check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16")
+
+
+def split_bf16(x, out: Operand, transpose=False):
+    """fp32 [rows, cols] -> bf16 hi(/lo) operand; ``transpose`` writes out[c, r]."""
+    rows, cols = x.shape
+    check(_lib.load().hba_split_bf16(_p(x), rows, cols, x.stride(0), _p(out.buf), out.ld, out.lo_off,
+                                     1 if transpose else 0, _stream()), "hba_split_bf16")
+    return out
+
+
+def layernorm_fwd(x, rows, cols, gamma, beta, eps, *, row_step=1, y_f32=None, y: Operand = None):
+    check(_lib.load().hba_layernorm_fwd(
+        _p(x), rows, cols, x.stride(0), row_step, _p(gamma), _p(beta), eps,
+        _p(y_f32), y_f32.stride(0) if y_f32 is not None else 0,
+        _p(y.buf) if y is not None else None, y.ld if y is not None else 0,
+        y.lo_off if y is not None else 0, _stream()), "hba_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, rows, cols, gamma, eps, dx, *, row_step=1, accumulate=False):
+    check(_lib.load().hba_layernorm_bwd(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), row_step,
+                                        _p(gamma), eps, _p(dx), dx.stride(0), 1 if accumulate else 0,
+                                        _stream()), "hba_layernorm_bwd")
+
+
+def im2col_patches(image, P, out: Operand):
+    B, Cc, H, W = image.shape
+    assert Cc == 3 and image.is_contiguous() and image.dtype == torch.float32
+    check(_lib.load().hba_im2col_patches(_p(image), B, H, W, P, _p(out.buf), out.ld, out.lo_off,
+                                         _stream()), "hba_im2col_patches")
+
+
+def assemble_tokens_ln(conv, B, n_patches, width, cls, pos, gamma, beta, eps, x_out):
+    check(_lib.load().hba_assemble_tokens_ln(_p(conv), B, n_patches, width, _p(cls), _p(pos), _p(gamma),
+                                             _p(beta), eps, _p(x_out), _stream()),
+          "hba_assemble_tokens_ln")
+
+
+def embed_tokens(tokens, table, pos, x_out):
+    S, T = tokens.shape
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous()
+    check(_lib.load().hba_embed_tokens(_p(tokens), S, T, table.shape[1], _p(table), _p(pos), _p(x_out),
+                                       _stream()), "hba_embed_tokens")
+
+
+def gather_rows(src, idx, cols, out):
+    check(_lib.load().hba_gather_rows(_p(src), src.stride(0), _p(idx), idx.numel(), cols, _p(out),
+                                      out.stride(0), _stream()), "hba_gather_rows")
+
+
+def attention_fwd(qkv, B, T, H, *, causal=False, first_row_only=False, out: Operand = None,
+                  out_f32=None):
+    check(_lib.load().hba_attention_fwd(
+        _p(qkv), _dt(qkv), qkv.stride(0), B, T, H, 1 if causal else 0, 1 if first_row_only else 0,
+        _p(out.buf) if out is not None else None, out.ld if out is not None else 0,
+        out.lo_off if out is not None else 0, _p(out_f32),
+        out_f32.stride(0) if out_f32 is not None else 0, _stream()), "hba_attention_fwd")
+
+
+def attention_bwd_row0(qkv, B, T, H, d_out, d_qkv):
+    check(_lib.load().hba_attention_bwd_row0(_p(qkv), _dt(qkv), qkv.stride(0), B, T, H, _p(d_out),
+                                             d_out.stride(0), _p(d_qkv), d_qkv.stride(0), _stream()),
+          "hba_attention_bwd_row0")
+
+
+def dora_merge_fwd(D, A, Bm, m, scale, eps, *, w_t_f32=None, w: Operand = None, wt: Operand = None,
+                   norm_out=None):
+    in_f, out_f = D.shape
+    r = A.shape[0]
+    check(_lib.load().hba_dora_merge_fwd(
+        _p(D), _p(A), _p(Bm), _p(m), in_f, out_f, r, scale, eps, _p(w_t_f32),
+        _p(w.buf) if w is not None else None, w.ld if w is not None else 0,
+        w.lo_off if w is not None else 0,
+        _p(wt.buf) if wt is not None else None, wt.ld if wt is not None else 0,
+        wt.lo_off if wt is not None else 0, _p(norm_out), _stream()), "hba_dora_merge_fwd")
+
+
+def dora_merge_bwd(G, D, A, Bm, m, scale, eps, dm, dA, dB, workspace):
+    in_f, out_f = D.shape
+    check(_lib.load().hba_dora_merge_bwd(_p(G), G.stride(0), _p(D), _p(A), _p(Bm), _p(m), in_f, out_f,
+                                         A.shape[0], scale, eps, _p(dm), _p(dA), _p(dB), _p(workspace),
+                                         _stream()), "hba_dora_merge_bwd")
+
+
+def cos_head_fwd(img, txt, logit_scale, pred, target=None, loss=None):
+    B, E = img.shape
+    check(_lib.load().hba_cos_head_fwd(_p(img), _p(txt), B, txt.shape[0], E, _p(logit_scale), _p(pred),
+                                       _p(target), _p(loss), _stream()), "hba_cos_head_fwd")
+
+
+def cos_head_bwd(img, txt, logit_scale, d_img, d_txt, *, d_pred=None, pred=None, target=None):
+    B, E = img.shape
+    check(_lib.load().hba_cos_head_bwd(_p(img), _p(txt), B, txt.shape[0], E, _p(logit_scale),
+                                       _p(d_pred), _p(pred), _p(target), _p(d_img), _p(d_txt),
+                                       _stream()), "hba_cos_head_bwd")
+
+
+def adamw_multi(ptr_table, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step, skip_flag=None):
+    check(_lib.load().hba_adamw_multi(_p(ptr_table), _p(sizes), n, total, lr, beta1, beta2, eps,
+                                      weight_decay, step, _p(skip_flag), _stream()), "hba_adamw_multi")
+
+
+def sgd_multi(ptr_table, sizes, n, total, lr, momentum, weight_decay, first_step, skip_flag=None):
+    check(_lib.load().hba_sgd_multi(_p(ptr_table), _p(sizes), n, total, lr, momentum, weight_decay,
+                                    1 if first_step else 0, _p(skip_flag), _stream()), "hba_sgd_multi")
+
+
+def rdm_f64(E, rdm=None, tri=None):
+    N, Dm = E.shape
+    assert E.dtype == torch.float32 and E.is_contiguous()
+    check(_lib.load().hba_rdm_f64(_p(E), N, Dm, _p(rdm), _p(tri), _stream()), "hba_rdm_f64")
+
+
+def rank_workspace_bytes(n):
+    return int(_lib.load().hba_rank_workspace_bytes(n))
+
+
+def rank_avg_f64(x, ranks, workspace=None):
+    n = x.numel()
+    assert x.dtype == torch.float64 and ranks.dtype == torch.float64
+    need = rank_workspace_bytes(n)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    check(_lib.load().hba_rank_avg_f64(_p(x), n, _p(ranks), _p(workspace), workspace.numel(), _stream()),
+          "hba_rank_avg_f64")
+
+
+def pearson_f64(a, b, rho_out, workspace):
+    check(_lib.load().hba_pearson_f64(_p(a), _p(b), a.numel(), _p(rho_out), _p(workspace), _stream()),
+          "hba_pearson_f64")
+
+
+def softmax_ce(logits, labels, loss, d_logits, correct, workspace):
+    B, Cc = logits.shape
+    check(_lib.load().hba_softmax_ce_fwd_bwd(_p(logits), logits.stride(0), _p(labels), B, Cc, _p(loss),
+                                             _p(d_logits),
+                                             d_logits.stride(0) if d_logits is not None else 0,
+                                             _p(correct), _p(workspace), _stream()),
+          "hba_softmax_ce_fwd_bwd")
+
+
+def add_rows(dst, src, rows, cols, dst_row_step=1):
+    check(_lib.load().hba_add_rows(_p(dst), dst.stride(0), dst_row_step, _p(src), src.stride(0), rows,
+                                   cols, _stream()), "hba_add_rows")
+
+
+def nonfinite_flag(x, flag):
+    check(_lib.load().hba_nonfinite_flag(_p(x), x.numel(), _p(flag), _stream()), "hba_nonfinite_flag")

@@ -1,0 +1,227 @@
+"""Plug-in seam: the module the reference imports as ``src.models.CLIPs.clip_hba.clip``
+(NEW:21 / BASE:21).  The reference uses exactly four attributes of it (NEW:251-265, 282):
+``_MODELS[name]``, ``_download(url, root)``, ``build_model(state_dict)`` and ``tokenize(str)``.
+
+``build_model`` returns an ``nn.Module`` tree with the parameter names and module paths of the
+published CLIP checkpoints (``visual.transformer.resblocks[i].attn.out_proj`` ... — the paths the
+reference patches with DoRA, NEW:496-513, and saves, NEW:665-669), whose forward
+``clip_model(image, tokens[66,77], pos_embedding) -> [B,66]`` (NEW:298) runs on the libhba sm_100a
+kernels.  The modules hold parameters only; there is no PyTorch/CPU forward path.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+import os
+import warnings
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from hba import engine as _engine
+
+__all__ = ["_MODELS", "_download", "build_model", "tokenize", "available_models", "CLIP"]
+
+SOT_TOKEN, EOT_TOKEN, VOCAB_SIZE, CONTEXT_LENGTH = 49406, 49407, 49408, 77
+
+_MODELS = {
+    "ViT-L/14": "https://openaipublic.azureedge.net/clip/models/b8cca3fd41ae0c99ba7e8951adf17d267cdb84cd88be6f7c2e0eca1737a03836/ViT-L-14.pt",
+    "ViT-B/16": "https://openaipublic.azureedge.net/clip/models/5806e77cd80f8b59890b7e101eabd078d9fb84e6937f9e85e4ecb61988df416f/ViT-B-16.pt",
+    # structure-identical miniature used by the test-suite (3 vision / 2 text blocks)
+    "ViT-tiny/14": "synthetic://ViT-tiny-14.pt",
+}
+
+_ARCH = {
+    "ViT-L-14.pt": dict(embed_dim=768, image_resolution=224, vision_layers=24, vision_width=1024,
+                        vision_patch_size=14, context_length=77, vocab_size=VOCAB_SIZE,
+                        transformer_width=768, transformer_heads=12, transformer_layers=12),
+    "ViT-B-16.pt": dict(embed_dim=512, image_resolution=224, vision_layers=12, vision_width=768,
+                        vision_patch_size=16, context_length=77, vocab_size=VOCAB_SIZE,
+                        transformer_width=512, transformer_heads=8, transformer_layers=12),
+    "ViT-tiny-14.pt": dict(embed_dim=128, image_resolution=224, vision_layers=3, vision_width=256,
+                           vision_patch_size=14, context_length=77, vocab_size=VOCAB_SIZE,
+                           transformer_width=128, transformer_heads=2, transformer_layers=2),
+}
+
+
+def available_models():
+    return list(_MODELS.keys())
+
+
+def _no_torch_path(name):
+    raise NotImplementedError(
+        f"{name}: this CLIP build computes only through CLIP.forward / encode_image / encode_text on "
+        "the libhba sm_100a kernels; sub-modules hold parameters and have no PyTorch forward")
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):
+        _no_torch_path("QuickGELU")
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d_model, n_head, causal):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(d_model, d_model * 4)),
+                                              ("gelu", QuickGELU()),
+                                              ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = nn.LayerNorm(d_model)
+        self.causal = causal
+
+    def forward(self, x):
+        _no_torch_path("ResidualAttentionBlock")
+
+
+class Transformer(nn.Module):
+    def __init__(self, width, layers, heads, causal=False):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads, causal)
+                                         for _ in range(layers)])
+
+    def forward(self, x):
+        _no_torch_path("Transformer")
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.input_resolution, self.output_dim = input_resolution, output_dim
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(
+            scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+    def forward(self, x, pos_embedding=False):
+        _no_torch_path("VisionTransformer")
+
+
+class CLIP(nn.Module):
+    def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size,
+                 context_length, vocab_size, transformer_width, transformer_heads, transformer_layers):
+        super().__init__()
+        self.context_length, self.vocab_size = context_length, vocab_size
+        self.visual = VisionTransformer(image_resolution, vision_patch_size, vision_width,
+                                        vision_layers, vision_width // 64, embed_dim)
+        self.transformer = Transformer(transformer_width, transformer_layers, transformer_heads,
+                                       causal=True)
+        self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+        self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width))
+        self.ln_final = nn.LayerNorm(transformer_width)
+        self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
+        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+        self._init_weights()
+
+    def _init_weights(self):
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        w, n = self.transformer.width, self.transformer.layers
+        proj_std, attn_std, fc_std = (w ** -0.5) * ((2 * n) ** -0.5), w ** -0.5, (2 * w) ** -0.5
+        for blk in self.transformer.resblocks:
+            nn.init.normal_(blk.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(blk.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(blk.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(blk.mlp.c_proj.weight, std=proj_std)
+        nn.init.normal_(self.text_projection, std=w ** -0.5)
+
+    @property
+    def dtype(self):
+        return self.visual.conv1.weight.dtype
+
+    def forward(self, image, text, pos_embedding=False):
+        """[B,3,H,W] images x [S,77] (or [S,1,77]) token ids -> [B,S] logits
+        exp(logit_scale) * cos(image_features, text_features)."""
+        return _engine.clip_forward(self, image, text, pos_embedding)
+
+    def hba_engine(self):
+        return _engine.get_engine(self)
+
+
+def _arch_from_state_dict(sd):
+    vw = sd["visual.conv1.weight"].shape[0]
+    vl = len({k.split(".")[3] for k in sd if k.startswith("visual.transformer.resblocks.")})
+    ps = sd["visual.conv1.weight"].shape[-1]
+    grid = round((sd["visual.positional_embedding"].shape[0] - 1) ** 0.5)
+    tw = sd["ln_final.weight"].shape[0]
+    tl = len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")})
+    return dict(embed_dim=sd["text_projection"].shape[1], image_resolution=ps * grid,
+                vision_layers=vl, vision_width=vw, vision_patch_size=ps,
+                context_length=sd["positional_embedding"].shape[0],
+                vocab_size=sd["token_embedding.weight"].shape[0], transformer_width=tw,
+                transformer_heads=tw // 64, transformer_layers=tl)
+
+
+def build_model(state_dict):
+    if "visual.proj" not in state_dict:
+        raise NotImplementedError("libhba covers the ViT CLIP variants only (ResNet towers are out "
+                                  "of scope: the reference drivers use ViT-L/14)")
+    model = CLIP(**_arch_from_state_dict(state_dict))
+    sd = {k: v for k, v in state_dict.items()
+          if k not in ("input_resolution", "context_length", "vocab_size")}
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+def synthetic_state_dict(fname, seed=1):
+    """Seeded random-init weights of a published architecture (offline stand-in for a checkpoint);
+    ``logit_scale`` = ln 100, the value the pretrained checkpoints saturate at."""
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        model = CLIP(**_ARCH[fname])
+        with torch.no_grad():
+            model.logit_scale.fill_(math.log(100.0))
+            for n, p in model.named_parameters():
+                if n.endswith("bias"):
+                    p.normal_(0.0, 0.02)
+        return OrderedDict((k, v.detach().clone()) for k, v in model.state_dict().items())
+    finally:
+        torch.set_rng_state(state)
+
+
+def _download(url, root):
+    """Returns the local checkpoint path.  A cached file wins; real URLs are fetched only when
+    HBA_ALLOW_DOWNLOAD=1; otherwise (offline) a seeded synthetic checkpoint of the same
+    architecture is materialised, with a warning."""
+    os.makedirs(root, exist_ok=True)
+    fname = os.path.basename(url)
+    target = os.path.join(root, fname)
+    if os.path.exists(target):
+        return target
+    if not url.startswith("synthetic://") and os.environ.get("HBA_ALLOW_DOWNLOAD") == "1":
+        import urllib.request
+        urllib.request.urlretrieve(url, target)
+        return target
+    if not url.startswith("synthetic://"):
+        warnings.warn(f"{fname}: no cached checkpoint under {root} and downloads are disabled; "
+                      "using seeded random-init weights of the same architecture", RuntimeWarning)
+        target = os.path.join(root, "synthetic-" + fname)
+        if os.path.exists(target):
+            return target
+    torch.save(synthetic_state_dict(fname), target)
+    return target
+
+
+def tokenize(texts, context_length=CONTEXT_LENGTH):
+    """str | list[str] -> int64 [n, context_length]: [SOT, word ids ..., EOT, 0-pad].
+    With the BPE vocabulary unavailable offline, each lower-cased whitespace/punctuation token maps to
+    a stable pseudo-id (sha256); EOT stays the row maximum, which is all the model relies on
+    (``text.argmax(-1)``).  A str yields [1,77] like the published tokenizer, so the reference's
+    ``torch.stack([clip.tokenize(c) ...])`` (NEW:282) gives [66,1,77]."""
+    rows = []
+    for t in ([texts] if isinstance(texts, str) else list(texts)):
+        ids = [SOT_TOKEN]
+        for w in t.lower().replace(",", " , ").replace(";", " ; ").split()[: context_length - 2]:
+            h = int.from_bytes(hashlib.sha256(w.encode()).digest()[:4], "little")
+            ids.append(1 + h % (SOT_TOKEN - 1))
+        ids.append(EOT_TOKEN)
+        rows.append(ids + [0] * (context_length - len(ids)))
+    return torch.tensor(rows, dtype=torch.long)
