@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — CLIP-HBA-Behavior training throughput (images/s) on N B200s.
+
+Workload (BASELINE.json configs[0], the configuration `metric` is quoted on): ViT-L/14 CLIP +
+DoRA (rank 32) on the last 2 vision blocks and the last text block, batch 32 synthetic 224^2 images
+-> random 66-D targets, MSE, AdamW(lr 3e-4).  One "step" = one full training step exactly as the
+reference does it per batch (NEW:985-1003): the whole vision trunk AND the text tower are recomputed
+every step (no activation cache inside the timed region), forward + live-sub-graph backward + DoRA
+backward + optimiser step.  N > 1 runs N independent replicas (one sweep condition per GPU — the
+path shards as independent runs): weak scaling, no data-path collective.
+
+  value : images/s with inputs resident in HBM (device-timed, max over ranks)
+  e2e   : same metric through the public API (functions.*: CLIPHBA + DoRALayer + FusedAdamW) with
+          pinned HOST images/targets copied in and the loss read back every step
+  roofline : the tcgen05 GEMM kernel, algorithmic FLOPs / CUDA-event time of its launches, measured
+          live in the timed region, against MEASURED_PEAKS.json bf16_tflops_sustained
+  cpu_baseline : the oracle port (oracle/clip_ref.py + oracle/dora_ref.py, PyTorch fp32 on the host
+          cores) on a bounded sample of the same workload
+
+`--impl reference` times that CPU implementation as the reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "vit-project_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "CLIP-HBA train imgs/s"
+UNIT = "images/s"
+N_CLASSES = 66
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--backbone", default="ViT-L/14")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-images", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n):
+    return {"workload": f"CLIP-HBA-Behavior {args.backbone} + DoRA r32 (last 2 vision + 1 text out_proj), "
+                        f"batch {args.batch}/GPU, 224x224 synthetic images -> random 66-D targets, MSE, "
+                        "AdamW lr 3e-4; full trunk + text tower recomputed every step (no activation cache)",
+            "global_batch": args.batch * n, "parallelism": f"{n} independent replicas (one condition per GPU)",
+            "l2": "per-step working set (>= 1.3 GB of activations and 0.8 GB of weights) exceeds the "
+                  "126 MB L2; no explicit flush",
+            "precision_mode": args.precision}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def build_cpu_reference(backbone, rank=32):
+    import torch
+    from oracle import clip_ref, dora_ref
+    from functions.spose_dimensions import classnames66
+    sd = clip_ref.synthetic_state_dict(backbone, seed=1)
+    tokens = torch.stack([clip_ref.tokenize(c) for c in classnames66])
+    model = dora_ref.CLIPHBARef(clip_ref.build_model(sd), tokens)
+    torch.manual_seed(123)
+    dora_ref.apply_dora_ref(model, 2, 1, r=rank)
+    dora_ref.switch_dora_ref(model)
+    return model
+
+
+def cpu_step_fn(model, n_images):
+    import torch
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(n_images, 3, 224, 224, generator=g)
+    targets = torch.randn(n_images, N_CLASSES, generator=g) * 9.5 + 5.75
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4)
+    crit = torch.nn.MSELoss()
+
+    def step():
+        opt.zero_grad()
+        loss = crit(model(images), targets)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def run_reference(args):
+    """The reference's CPU path (restated: oracle port) on all host cores; one step = a bounded
+    sample of `cpu_sample_images` images of the same workload."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(build_cpu_reference(args.backbone), args.cpu_sample_images)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.cpu_sample_images * args.steps / dt
+    sample = (f"{args.cpu_sample_images} images per step (fwd + bwd + AdamW, text tower recomputed each "
+              f"step), {args.steps} steps, PyTorch fp32, {torch.get_num_threads()} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def build_gpu_model(args, device):
+    """The public API a user of the reference calls: CLIPHBA + apply_dora_to_ViT + switch_dora_layers
+    (NEW:1133-1152) from the drop-in functions module, AdamW via its make_optimizer."""
+    import torch
+    import functions._pipeline_core as core
+    from functions.spose_dimensions import classnames66
+    os.environ.setdefault("HBA_SYNTHETIC_OK", "1")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = core.CLIPHBA(classnames66, backbone_name=args.backbone, pos_embedding=True)
+    torch.manual_seed(123)
+    core.apply_dora_to_ViT(model, n_vision_layers=2, n_transformer_layers=1, r=32)
+    core.switch_dora_layers(model, freeze_all=True, dora_state=True)
+    model.to(device)
+    model.train()
+    opt = core.make_optimizer(model, 3e-4)
+    return model, opt
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import hba
+    from hba import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    hba.set_precision(args.precision)
+    model, opt = build_gpu_model(args, device)
+    eng = model.clip_model.hba_engine()
+    eng.cache_text = False  # the reference recomputes the text tower every step (NEW:298)
+    crit = torch.nn.MSELoss()
+    B = args.batch
+    g = torch.Generator().manual_seed(rank)
+    host_images = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    host_targets = (torch.randn(B, N_CLASSES, generator=g) * 9.5 + 5.75).pin_memory()
+    dev_images, dev_targets = host_images.to(device), host_targets.to(device)
+
+    def step_resident():
+        opt.zero_grad()
+        loss = crit(model(dev_images), dev_targets)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        images = host_images.to(device, non_blocking=True)
+        targets = host_targets.to(device, non_blocking=True)
+        opt.zero_grad()
+        loss = crit(model(images), targets)
+        loss.backward()
+        opt.step()
+        return float(loss)  # device -> host read of the step's result
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile_gemm=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile_gemm:
+            ops.GEMM_PROFILE = []
+        c0 = ops.COUNTERS["launches"]
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+        launches = ops.COUNTERS["launches"] - c0
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, profile_gemm=True)
+    clocks = sampler.stop()
+    loss_val = float(step_resident())
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    flops = sum(2.0 * M * N * K for (M, N, K, ns, a, b) in prof)
+    gemm_ms = sum(a.elapsed_time(b) for (M, N, K, ns, a, b) in prof)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    else:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    achieved = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32 mode)", "data": "synthetic",
+        "config": workload_config(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": host_images.numel() * 4 + host_targets.numel() * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "gemm_launches_per_step": len(prof) / args.steps,
+                     "gemm_flops_per_step": flops / args.steps,
+                     "gemm_ms_per_step": gemm_ms / args.steps,
+                     "gemm_share_of_step": gemm_ms / ms},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n = args.cpu_sample_images
+        step = cpu_step_fn(build_cpu_reference(args.backbone), n)
+        step()  # warm-up (allocations, thread pool)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            step()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(),
+                               "kind": "port",
+                               "sample": f"{reps} training steps of {n} images (same model, fwd+bwd+AdamW, "
+                                         "text tower recomputed), oracle port in PyTorch fp32"}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

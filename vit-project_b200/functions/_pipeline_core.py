@@ -1,0 +1,500 @@
+"""Shared implementation behind the two drop-in pipeline modules
+
+    functions/new_cvpr_train_behavior_things_pipeline.py        (reference NEW, 1226 lines)
+    functions/cvpr_train_behavior_things_pipeline_baseline.py   (reference BASE, 823 lines)
+
+Same public names, argument meaning, on-disk formats (CSV schema NEW:795 / BASE:636, DoRA checkpoint
+keys NEW:665-683, random-state checkpoint NEW:709-727) and control flow semantics as the reference;
+the arithmetic runs on libhba (sm_100a): the CLIP towers and DoRA merge through the plug-in ``clip``
+module + ``hba.DoRALayer``, AdamW through ``hba.optim.FusedAdamW``, the RSA tail through ``hba.rsa``.
+
+Host-synchronisation changes w.r.t. the reference (results unchanged): the per-step ``loss.item()``
+calls (NEW:999/1003) and NaN checks (NEW:989-998) are evaluated on the device — the running loss is
+a device scalar read once per epoch and a bad batch raises a device flag that makes the fused
+optimiser skip the update, which is what the reference's ``continue`` achieves.
+"""
+from __future__ import annotations
+
+import csv
+import logging
+import os
+import random
+import sys
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn as nn
+from PIL import Image
+from torch.utils.data import DataLoader, Dataset
+from torchvision import transforms
+from tqdm import tqdm
+
+from hba import DoRALayer, ops, rsa
+from hba.optim import FusedAdamW
+from src.models.CLIPs.clip_hba import clip
+
+THINGS_MEAN = [0.52997664, 0.48070561, 0.41943838]
+THINGS_STD = [0.27608301, 0.26593025, 0.28238822]
+
+NEW_HEADERS = ["epoch", "train_loss", "test_loss", "behavioral_rsa_rho", "behavioral_rsa_p_value",
+               "used_random_targets", "used_shuffled_targets", "used_uniform_images", "used_image_noise"]
+BASE_HEADERS = NEW_HEADERS[:5]
+
+
+# ------------------------------------------------------------------------------- seeding / logging
+def seed_everything(seed):
+    """NEW:35-48."""
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
+def setup_logger(log_file_path):
+    """File + stdout logger with the reference's line format (NEW:51-85)."""
+    logger = logging.getLogger("training_logger")
+    logger.setLevel(logging.INFO)
+    logger.handlers = []
+    fmt = logging.Formatter("%(asctime)s - %(levelname)s - %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
+    os.makedirs(os.path.dirname(log_file_path) or ".", exist_ok=True)
+    for handler in (logging.FileHandler(log_file_path, mode="w"), logging.StreamHandler(sys.stdout)):
+        handler.setLevel(logging.INFO)
+        handler.setFormatter(fmt)
+        logger.addHandler(handler)
+    return logger
+
+
+def _log_fn(logger):
+    return logger.info if logger else print
+
+
+# ------------------------------------------------------------------------------- data
+def _things_transform():
+    return transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                               transforms.Normalize(mean=THINGS_MEAN, std=THINGS_STD)])
+
+
+class ThingsDataset(Dataset):
+    """(image_name, image[3,224,224], targets[66]) rows of the SPoSE csv (NEW:180-204)."""
+
+    def __init__(self, csv_file, img_dir):
+        self.img_dir = img_dir
+        self.transform = _things_transform()
+        self.annotations = pd.read_csv(csv_file, index_col=0)
+
+    def __len__(self):
+        return len(self.annotations)
+
+    def _image(self, index):
+        name = self.annotations.iloc[index, 0]
+        return name, self.transform(Image.open(os.path.join(self.img_dir, name)).convert("RGB"))
+
+    def __getitem__(self, index):
+        name, image = self._image(index)
+        targets = torch.tensor(self.annotations.iloc[index, 1:].values.astype("float32"))
+        return name, image, targets
+
+
+class ThingsInferenceDataset(ThingsDataset):
+    """(image_name, image) rows of the 48-image inference csv; carries the path of the human RDM
+    (NEW:225-248)."""
+
+    def __init__(self, inference_csv_file, img_dir, RDM48_triplet_dir):
+        super().__init__(inference_csv_file, img_dir)
+        self.RDM48_triplet_dir = RDM48_triplet_dir
+
+    def __getitem__(self, index):
+        return self._image(index)
+
+
+class SubsetWithIndices(Dataset):
+    """NEW:164-177."""
+
+    def __init__(self, dataset, indices):
+        self.dataset, self.indices = dataset, indices
+
+    def __getitem__(self, idx):
+        return self.dataset[self.indices[idx]]
+
+    def __len__(self):
+        return len(self.indices)
+
+
+def load_dataset_split_indices(split_indices_path, logger=None):
+    """NEW:137-161."""
+    log = _log_fn(logger)
+    if not os.path.exists(split_indices_path):
+        log(f"Split indices file not found: {split_indices_path}")
+        return None
+    info = torch.load(split_indices_path)
+    log(f"Loaded dataset split indices from: {split_indices_path}")
+    log(f"  Train samples: {len(info['train_indices'])}")
+    log(f"  Test samples: {len(info['test_indices'])}")
+    log(f"  Random seed used: {info['random_seed']}")
+    return info
+
+
+def replace_with_gaussian_noise(image, mean, std):
+    """NEW:207-221 (global torch RNG of the image's device)."""
+    return torch.randn(tuple(image.size()), device=image.device) * std + mean
+
+
+# ------------------------------------------------------------------------------- model
+def load_clip_to_cpu(backbone_name):
+    """NEW:251-265 through the plug-in clip module."""
+    path = clip._download(clip._MODELS[backbone_name], os.path.expanduser("~/.cache/clip"))
+    try:
+        jit = torch.jit.load(path, map_location="cpu").eval()
+        state_dict = jit.state_dict()
+    except RuntimeError:
+        state_dict = torch.load(path, map_location="cpu")
+    return clip.build_model(state_dict)
+
+
+class CLIPHBA(nn.Module):
+    """NEW:268-304: frozen CLIP scored against the fixed class prompts -> [B, n_prompts] fp32."""
+
+    def __init__(self, classnames, backbone_name="RN50", pos_embedding=False):
+        super().__init__()
+        self.num_clip = len(classnames)
+        self.clip_model = load_clip_to_cpu(backbone_name)
+        self.clip_model.float()
+        self.pos_embedding = pos_embedding
+        for p in self.clip_model.parameters():
+            p.requires_grad = False
+        self.tokenized_prompts = torch.stack([clip.tokenize(c) for c in classnames])
+        self._cached_tokenized_prompts = None
+        self._cached_device = None
+
+    def forward(self, image):
+        if self.clip_model.training:
+            self.clip_model.eval()  # dropout never active on this path (NEW:288-289)
+        if self._cached_tokenized_prompts is None or self._cached_device != image.device:
+            self._cached_tokenized_prompts = self.tokenized_prompts.to(image.device)
+            self._cached_device = image.device
+        return self.clip_model(image, self._cached_tokenized_prompts, self.pos_embedding).float()
+
+
+def _unwrap(model):
+    return model.module if isinstance(model, nn.DataParallel) else model
+
+
+def apply_dora_to_ViT(model, n_vision_layers=1, n_transformer_layers=1, r=8, dora_dropout=0.1, seed=123):
+    """NEW:484-513: DoRA on attn.out_proj of the last vision blocks, then of the last text blocks
+    (that order fixes how the global RNG is consumed)."""
+    cm = _unwrap(model).clip_model
+    for tower, n in ((cm.visual.transformer, n_vision_layers), (cm.transformer, n_transformer_layers)):
+        for idx in range(-n, 0):
+            blk = tower.resblocks[idx]
+            blk.attn.out_proj = DoRALayer(blk.attn.out_proj, r=r, dora_dropout=dora_dropout)
+
+
+def switch_dora_layers(model, freeze_all=True, dora_state=True):
+    """NEW:516-544."""
+    for p in model.parameters():
+        p.requires_grad = not freeze_all
+    if freeze_all:
+        for mod in _unwrap(model).modules():
+            if isinstance(mod, DoRALayer):
+                for p in (mod.m, mod.delta_D_A, mod.delta_D_B):
+                    p.requires_grad = dora_state
+                if mod.bias is not None:
+                    mod.bias.requires_grad = False
+
+
+def count_trainable_parameters(model):
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def dora_module_paths(model, vision_layers, transformer_layers):
+    cm = _unwrap(model).clip_model
+    nv, nt = len(cm.visual.transformer.resblocks), len(cm.transformer.resblocks)
+    return ([f"clip_model.visual.transformer.resblocks.{nv - vision_layers + i}.attn.out_proj"
+             for i in range(vision_layers)] +
+            [f"clip_model.transformer.resblocks.{nt - transformer_layers + i}.attn.out_proj"
+             for i in range(transformer_layers)])
+
+
+def _dora_state(model, paths):
+    out = {}
+    root = _unwrap(model)
+    for path in paths:
+        mod = root
+        for attr in path.split("."):
+            mod = getattr(mod, attr)
+        for name in ("m", "delta_D_A", "delta_D_B"):
+            out[f"{path}.{name}"] = getattr(mod, name).detach().cpu()
+    return out
+
+
+def find_dora_paths(model):
+    return [n for n, m in _unwrap(model).named_modules() if isinstance(m, DoRALayer)]
+
+
+# ------------------------------------------------------------------------------- checkpoints
+def save_dora_parameters(model, dora_parameters_path, epoch, logger=None):
+    """NEW:657-693: one dict {<module path>.{m,delta_D_A,delta_D_B}: cpu tensor} per epoch.  The
+    reference hard-codes blocks 22/23/11 of ViT-L/14; the adapters are located here, which yields
+    the same keys for that model."""
+    os.makedirs(dora_parameters_path, exist_ok=True)
+    torch.save(_dora_state(model, find_dora_paths(model)),
+               os.path.join(dora_parameters_path, f"epoch{epoch + 1}_dora_params.pth"))
+
+
+def save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=None):
+    """NEW:696-728."""
+    ckpt = {"epoch": epoch, "optimizer_state_dict": optimizer.state_dict(),
+            "torch_rng_state": torch.get_rng_state(), "numpy_rng_state": np.random.get_state(),
+            "python_rng_state": random.getstate(),
+            "dataloader_generator_state": dataloader_generator.get_state()}
+    if torch.cuda.is_available():
+        ckpt["cuda_rng_state"] = torch.cuda.get_rng_state()
+        ckpt["cuda_rng_state_all"] = torch.cuda.get_rng_state_all()
+    os.makedirs(random_state_path, exist_ok=True)
+    path = os.path.join(random_state_path, f"epoch{epoch + 1}_random_states.pth")
+    torch.save(ckpt, path)
+    _log_fn(logger)(f"Random states saved: {path}")
+
+
+def load_random_states(random_state_path, epoch, optimizer=None, dataloader_generator=None, logger=None):
+    """NEW:88-134."""
+    log = _log_fn(logger)
+    path = os.path.join(random_state_path, f"epoch{epoch}_random_states.pth")
+    if not os.path.exists(path):
+        log(f"Warning: Random state checkpoint not found: {path}")
+        return False
+    ckpt = torch.load(path, weights_only=False)
+    torch.set_rng_state(ckpt["torch_rng_state"])
+    np.random.set_state(ckpt["numpy_rng_state"])
+    random.setstate(ckpt["python_rng_state"])
+    if torch.cuda.is_available() and "cuda_rng_state" in ckpt:
+        torch.cuda.set_rng_state(ckpt["cuda_rng_state"])
+        if "cuda_rng_state_all" in ckpt:
+            states = ckpt["cuda_rng_state_all"]
+            if len(states) == torch.cuda.device_count():
+                torch.cuda.set_rng_state_all(states)
+    if optimizer is not None and "optimizer_state_dict" in ckpt:
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        log(f"Restored optimizer state from epoch {epoch}")
+    if dataloader_generator is not None and "dataloader_generator_state" in ckpt:
+        dataloader_generator.set_state(ckpt["dataloader_generator_state"])
+        log(f"Restored DataLoader generator state from epoch {epoch}")
+    log(f"Random states loaded from: {path}")
+    return True
+
+
+# ------------------------------------------------------------------------------- evaluation
+def evaluate_model(model, data_loader, device, criterion):
+    """NEW:584-602: sample-weighted mean loss; accumulated on the device, one read at the end."""
+    model.eval()
+    total = torch.zeros((), device=device, dtype=torch.float64)
+    with torch.no_grad():
+        for _, images, targets in tqdm(data_loader, total=len(data_loader), desc="Evaluating",
+                                       file=sys.stderr):
+            images = images.to(device, non_blocking=True)
+            targets = targets.to(device, non_blocking=True)
+            total += criterion(model(images), targets).double() * images.size(0)
+    return float(total) / len(data_loader.dataset)
+
+
+_RSA_CACHE = {}
+
+
+def _reference_rdm(path):
+    import scipy.io
+    return scipy.io.loadmat(path)["RDM48_triplet"]
+
+
+def behavioral_RSA(model, inference_loader, device, logger=None):
+    """NEW:605-654 -> (rho, p_value, model_rdm).  The embeddings stay in HBM; RDM, average-tie
+    ranking and Pearson-on-ranks run in hba.rsa."""
+    model.eval()
+    log = _log_fn(logger)
+    names, chunks = [], []
+    with torch.no_grad():
+        for image_name, image in inference_loader:
+            chunks.append(model(image.to(device, non_blocking=True)))
+            names.extend(image_name)
+    emb = torch.cat(chunks, 0)
+    log(f"First 10 image names: {names[:5]}")
+    log(f"Embedding matrix shape: {tuple(emb.shape)}\n")
+    key = (inference_loader.dataset.RDM48_triplet_dir, str(emb.device))
+    if key not in _RSA_CACHE:
+        _RSA_CACHE[key] = rsa.RSAEvaluator(_reference_rdm(key[0]), emb.device)
+    return _RSA_CACHE[key](emb)
+
+
+# ------------------------------------------------------------------------------- perturbations
+def shuffle_targets(targets, perturb_seed=None, generator=None):
+    """NEW:731-779: permute the batch dimension of `targets` (torch.randperm on its device)."""
+    saved = None
+    if generator is None and perturb_seed is not None:
+        saved = (torch.get_rng_state(), np.random.get_state(), random.getstate())
+        torch.manual_seed(perturb_seed)
+        np.random.seed(perturb_seed)
+        random.seed(perturb_seed)
+    n = targets.shape[0]
+    perm = (torch.randperm(n, device=targets.device, generator=generator) if generator is not None
+            else torch.randperm(n, device=targets.device))
+    shuffled = targets.clone()[perm]
+    if saved is not None:
+        torch.set_rng_state(saved[0])
+        np.random.set_state(saved[1])
+        random.setstate(saved[2])
+    return shuffled
+
+
+PERTURB_FLAGS = {"random_target": "used_random_targets", "label_shuffle": "used_shuffled_targets",
+                 "uniform_images": "used_uniform_images", "image_noise": "used_image_noise"}
+
+
+class Perturbation:
+    """The four perturbation types of NEW:843-982 with their exact RNG discipline: per-batch seed
+    perturb_seed + training_run*1000 + batch_idx (independent of the epoch)."""
+
+    def __init__(self, kind, training_run, length, seed, distribution, mean, std):
+        self.kind, self.training_run, self.length = kind, training_run, length
+        self.seed, self.distribution, self.mean, self.std = seed, distribution, mean, std
+        self.first = training_run - 1           # 0-indexed first perturbed epoch (NEW:844)
+        self.last = self.first + length - 1
+
+    def active(self, epoch):
+        return self.kind in PERTURB_FLAGS and self.first <= epoch <= self.last
+
+    def in_window(self, epoch):
+        return self.first <= epoch <= self.last
+
+    def flags(self, epoch):
+        f = dict.fromkeys(PERTURB_FLAGS.values(), False)
+        if self.active(epoch):
+            f[PERTURB_FLAGS[self.kind]] = True
+        return f
+
+    def apply(self, images, targets, batch_idx, device):
+        s = self.seed + self.training_run * 1000 + batch_idx
+        if self.kind == "image_noise":
+            torch.manual_seed(s)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed_all(s)
+            for i in range(len(images)):
+                images[i] = replace_with_gaussian_noise(images[i], self.mean, self.std)
+        elif self.kind == "uniform_images":
+            images = torch.ones_like(images) * 0.5
+        elif self.kind == "random_target":
+            gen = torch.Generator(device=device)
+            gen.manual_seed(s)
+            noise = torch.randn(targets.shape, device=device, dtype=torch.float32, generator=gen)
+            targets = noise * self.std + self.mean if self.distribution == "target" else noise
+        elif self.kind == "label_shuffle":
+            gen = torch.Generator(device=device)
+            gen.manual_seed(s)
+            targets = shuffle_targets(targets, generator=gen)
+        return images, targets
+
+
+# ------------------------------------------------------------------------------- training epoch
+class _BadBatchFlag:
+    """Device-side NaN/Inf guard (reference: NEW:932-935, 989-998)."""
+
+    def __init__(self, device):
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        self.total = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def check(self, *tensors):
+        self.step.zero_()
+        for t in tensors:
+            ops.nonfinite_flag(t.detach().reshape(-1).float().contiguous(), self.step)
+        self.total += self.step
+        return self.step
+
+
+def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs, perturb=None,
+                    log=print):
+    """One pass over train_loader (NEW:873-1004 / BASE:644-659): returns the sample-weighted mean
+    loss, read from the device once."""
+    total = torch.zeros((), device=device, dtype=torch.float64)
+    guard = _BadBatchFlag(device)
+    fused = isinstance(optimizer, FusedAdamW)
+    active = perturb is not None and perturb.active(epoch)
+    bar = tqdm(enumerate(train_loader), total=len(train_loader), desc=f"Epoch {epoch + 1}/{epochs}",
+               file=sys.stderr)
+    for batch_idx, (_, images, targets) in bar:
+        images = images.to(device, non_blocking=True)
+        targets = targets.to(device, non_blocking=True)
+        if active:
+            images, targets = perturb.apply(images, targets, batch_idx, device)
+        optimizer.zero_grad()
+        predictions = model(images)
+        loss = criterion(predictions, targets)
+        bad = guard.check(predictions, loss.reshape(1), targets)
+        loss.backward()
+        if fused:
+            optimizer.step(skip_flag=bad)
+        elif int(bad) == 0:
+            optimizer.step()
+        total += torch.where(bad[0] == 0, loss.detach().double(), torch.zeros_like(total)) * images.size(0)
+    n_bad = int(guard.total)
+    if n_bad:
+        log(f"ERROR: NaN/Inf detected in {n_bad} batch(es) of epoch {epoch + 1}; they were skipped")
+    return float(total) / len(train_loader.dataset)
+
+
+def select_device(cuda_flag):
+    """config['cuda'] (NEW:1137-1144): -1 / 0 / 1 -> CUDA device; anything else asked for the CPU in
+    the reference, which this build does not have."""
+    if cuda_flag == -1:
+        return torch.device("cuda")
+    if cuda_flag in (0, 1):
+        return torch.device(f"cuda:{cuda_flag}")
+    raise RuntimeError("config['cuda'] selects the CPU, but the libhba pipeline has no CPU path; "
+                       "use 0, 1 or -1")
+
+
+def make_optimizer(model, lr):
+    """AdamW(model.parameters(), lr) (NEW:1181) with the fused multi-tensor step."""
+    return FusedAdamW(model.parameters(), lr=lr)
+
+
+def open_logger(config):
+    log_dir = os.path.dirname(config["checkpoint_path"])
+    stamp = datetime.now().strftime("%Y%m%d_%H%M%S")
+    log_file = os.path.join(log_dir, f"training_log_{stamp}.txt")
+    logger = setup_logger(log_file)
+    logger.info("=" * 80)
+    logger.info("Starting Training Run")
+    logger.info(f"Log file: {log_file}")
+    logger.info("=" * 80)
+    return logger
+
+
+def build_model(config, device, logger):
+    from functions.spose_dimensions import classnames66
+    pos_embedding = config["backbone"] != "RN50"
+    logger.info(f"pos_embedding is {pos_embedding}")
+    model = CLIPHBA(classnames=classnames66, backbone_name=config["backbone"], pos_embedding=pos_embedding)
+    apply_dora_to_ViT(model, n_vision_layers=config["vision_layers"],
+                      n_transformer_layers=config["transformer_layers"], r=config["rank"],
+                      dora_dropout=0.1)
+    switch_dora_layers(model, freeze_all=True, dora_state=True)
+    return model
+
+
+def describe_run(model, config, logger):
+    logger.info("\nModel Configuration:")
+    logger.info("-------------------")
+    for k, v in config.items():
+        logger.info(f"{k}: {v}")
+    logger.info("\nUpdating layers:")
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            logger.info(name)
+    logger.info(f"\nNumber of trainable parameters: {count_trainable_parameters(model)}\n")
+
+
+def append_csv_row(path, row):
+    with open(path, "a", newline="") as f:
+        csv.writer(f).writerow(row)

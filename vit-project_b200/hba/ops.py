@@ -11,7 +11,21 @@ import torch
 
 from . import _lib
 from ._lib import (HBA_ACT_GELU_ERF, HBA_ACT_GELU_ERF_GRAD, HBA_ACT_NONE, HBA_ACT_QUICKGELU,
-                   HBA_ACT_QUICKGELU_GRAD, HBA_DT_BF16, HBA_DT_F32, GemmParams, check)
+                   HBA_ACT_QUICKGELU_GRAD, HBA_DT_BF16, HBA_DT_F32, GemmParams)
+from ._lib import check as _check
+
+# Our own count of kernels launched through the C-ABI (bench.py reports it as `gpu_launches`).
+COUNTERS = {"launches": 0, "calls": 0}
+_KERNELS_PER_CALL = {"hba_dora_merge_bwd": 2, "hba_pearson_f64": 3, "hba_softmax_ce_fwd_bwd": 2}
+# When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and
+# (M, N, K, nsplit, start_event, end_event) is appended (bench.py's live roofline measurement).
+GEMM_PROFILE = None
+
+
+def check(rc, what, kernels=None):
+    _check(rc, what)
+    COUNTERS["calls"] += 1
+    COUNTERS["launches"] += kernels if kernels is not None else _KERNELS_PER_CALL.get(what, 1)
 
 __all__ = ["gemm", "split_bf16", "layernorm_fwd", "layernorm_bwd", "im2col_patches",
            "assemble_tokens_ln", "embed_tokens", "gather_rows", "attention_fwd",
@@ -90,6 +104,13 @@ def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_AC
         p.out_bf16, p.ld_bf16, p.out_lo_off = out.buf.data_ptr(), out.ld, out.lo_off
     p.transpose_out = 1 if transpose_out else 0
     p.max_ctas = max_ctas
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16")
+        e1.record()
+        GEMM_PROFILE.append((M, N, K, p.nsplit, e0, e1))
+        return
     check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16")
 
 
@@ -177,7 +198,8 @@ def dora_merge_bwd(G, D, A, Bm, m, scale, eps, dm, dA, dB, workspace):
 def cos_head_fwd(img, txt, logit_scale, pred, target=None, loss=None):
     B, E = img.shape
     check(_lib.load().hba_cos_head_fwd(_p(img), _p(txt), B, txt.shape[0], E, _p(logit_scale), _p(pred),
-                                       _p(target), _p(loss), _stream()), "hba_cos_head_fwd")
+                                       _p(target), _p(loss), _stream()), "hba_cos_head_fwd",
+          2 if loss is not None else 1)
 
 
 def cos_head_bwd(img, txt, logit_scale, d_img, d_txt, *, d_pred=None, pred=None, target=None):
@@ -214,7 +236,7 @@ def rank_avg_f64(x, ranks, workspace=None):
     if workspace is None:
         workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
     check(_lib.load().hba_rank_avg_f64(_p(x), n, _p(ranks), _p(workspace), workspace.numel(), _stream()),
-          "hba_rank_avg_f64")
+          "hba_rank_avg_f64", 1 if n <= 2048 else 26)
 
 
 def pearson_f64(a, b, rho_out, workspace):
