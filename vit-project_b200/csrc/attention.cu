@@ -4,6 +4,8 @@
 //
 // This file holds the exact-fp32 CUDA-core path (used by the fp32 parity mode and for the CLS-row
 // pruned forward/backward of the last vision block); the bf16 tensor-core path is attention_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hba {
@@ -284,6 +286,10 @@ __global__ void __launch_bounds__(128)
   gbase[lane + 32] = 0.125f * dq_hi;
 }
 
+int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
+                        __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of,
+                        cudaStream_t stream);
+
 template <typename T>
 static int attention_fwd_dispatch(const T* qkv, int64_t ld_qkv, int B, int Tn, int H, int causal,
                                   int first_row_only, __nv_bfloat16* out, int64_t ld_out,
@@ -330,6 +336,10 @@ extern "C" int hba_attention_fwd(const void* qkv, int32_t qkv_dtype, int64_t ld_
     return attention_fwd_dispatch<float>(static_cast<const float*>(qkv), ld_qkv, B, T, H, causal,
                                          first_row_only, static_cast<__nv_bfloat16*>(out), ld_out,
                                          lo_off, out_f32, ld_of, s);
+  if (qkv_dtype == HBA_DT_BF16 && !first_row_only && lo_off == 0 && T <= 264 && ld_qkv % 8 == 0 &&
+      (!out || ld_out % 8 == 0) && (!out_f32 || ld_of % 4 == 0) && getenv("HBA_ATTN_SIMT") == nullptr)
+    return attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, causal,
+                               static_cast<__nv_bfloat16*>(out), ld_out, out_f32, ld_of, s);
   if (qkv_dtype == HBA_DT_BF16)
     return attention_fwd_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B,
                                                  T, H, causal, first_row_only,

@@ -17,7 +17,8 @@ namespace hba {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -47,9 +48,13 @@ struct GemmArgs {
   int transpose_out;
 };
 
-__device__ __forceinline__ float quickgelu(float v) { return v / (1.0f + expf(-1.702f * v)); }
+// x * sigmoid(1.702 x) on the SFU fast paths (ex2.approx + rcp.approx, ~2 ulp): the epilogue of the
+// c_fc GEMM evaluates this 33.7 M times per layer and must stay under the main loop's time
+__device__ __forceinline__ float quickgelu(float v) {
+  return __fdividef(v, 1.0f + __expf(-1.702f * v));
+}
 __device__ __forceinline__ float quickgelu_grad(float a) {
-  const float s = 1.0f / (1.0f + expf(-1.702f * a));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * a));
   return s * (1.0f + 1.702f * a * (1.0f - s));
 }
 __device__ __forceinline__ float gelu_erf(float v) {
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -303,6 +308,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32;
         tmem_ld_32x32b_x32(taddr, r);
