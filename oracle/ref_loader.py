@@ -53,6 +53,9 @@ def load_reference(clip_module=None):
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
     if clip_module is None:
         from oracle import clip_ref as clip_module
+    # the stubs below live in sys.modules only while the reference is imported (the product ships
+    # its own `src.models...` plug-in package under the same names)
+    saved_src = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "src" or k.startswith("src.")}
     for name in ("src", "src.models", "src.models.CLIPs", "src.models.CLIPs.clip_hba"):
         if name not in sys.modules or not getattr(sys.modules[name], "__hba_stub__", False):
             m = types.ModuleType(name)
@@ -69,13 +72,22 @@ def load_reference(clip_module=None):
     # the reference must win the name "functions" while it is being imported
     saved = {k: sys.modules.pop(k) for k in list(sys.modules)
              if k == "functions" or k.startswith("functions.")}
+    # a regular package named `functions` anywhere on sys.path (the product's drop-in package) would
+    # shadow the reference's namespace package: hide such entries while the reference is imported
+    hidden = [p for p in sys.path if os.path.exists(os.path.join(p or ".", "functions", "__init__.py"))]
+    for p in hidden:
+        sys.path.remove(p)
     sys.path.insert(0, tr)
     try:
         new = importlib.import_module("functions.new_cvpr_train_behavior_things_pipeline")
         base = importlib.import_module("functions.cvpr_train_behavior_things_pipeline_baseline")
     finally:
         sys.path.remove(tr)
+        sys.path[:0] = hidden
         for k in [k for k in sys.modules if k == "functions" or k.startswith("functions.")]:
             sys.modules["_reference_" + k] = sys.modules.pop(k)
         sys.modules.update(saved)
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved_src)
     return new, base

@@ -1,0 +1,122 @@
+"""CPU tests of the host-side logic of the drop-in pipeline modules (functions/*): perturbation
+windows, target shuffling (vs the reference golden), CSV bootstrap / resume, checkpoint formats,
+reference public surface."""
+import csv
+import inspect
+import os
+
+import numpy as np
+import torch
+
+import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
+import functions.new_cvpr_train_behavior_things_pipeline as NEW
+from functions import _pipeline_core as core
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_public_surface_matches_reference_names_and_signatures():
+    for name in ("seed_everything", "setup_logger", "load_random_states", "load_dataset_split_indices",
+                 "SubsetWithIndices", "ThingsDataset", "replace_with_gaussian_noise",
+                 "ThingsInferenceDataset", "load_clip_to_cpu", "CLIPHBA", "DoRALayer", "apply_dora_to_ViT",
+                 "switch_dora_layers", "count_trainable_parameters", "evaluate_model", "behavioral_RSA",
+                 "save_dora_parameters", "save_random_states", "shuffle_targets", "train_model",
+                 "run_behavioral_training", "classnames66"):
+        assert hasattr(NEW, name), name
+    for name in ("seed_everything", "setup_logger", "ThingsDataset", "ThingsInferenceDataset", "CLIPHBA",
+                 "DoRALayer", "apply_dora_to_ViT", "switch_dora_layers", "evaluate_model", "behavioral_RSA",
+                 "save_random_states", "train_model", "run_behavioral_training"):
+        assert hasattr(BASE, name), name
+    sig = list(inspect.signature(NEW.train_model).parameters)
+    assert sig == ["model", "train_loader", "test_loader", "inference_loader", "device", "optimizer",
+                   "criterion", "epochs", "training_res_path", "training_run", "perturb_length",
+                   "perturb_seed", "mean", "std", "perturb_distribution", "perturb_type", "logger",
+                   "early_stopping_patience", "checkpoint_path", "dora_parameters_path",
+                   "random_state_path", "dataloader_generator", "resume_from_epoch",
+                   "previous_training_res_path"]
+    sigb = list(inspect.signature(BASE.train_model).parameters)
+    assert sigb[-2:] == ["vision_layers", "transformer_layers"] and sigb[:9] == sig[:9]
+    assert list(inspect.signature(NEW.DoRALayer.__init__).parameters) == [
+        "self", "original_layer", "r", "dora_alpha", "dora_dropout"]
+    assert len(NEW.classnames66) == 66 and NEW.classnames66[0] == "metallic; artificial"
+
+
+def test_shuffle_targets_matches_reference_golden():
+    g = torch.load(os.path.join(GOLD, "shuffle_targets.pt"))
+    gen = torch.Generator().manual_seed(g["seed"])
+    out = NEW.shuffle_targets(g["targets"], generator=gen)
+    assert torch.equal(out, g["shuffled"])
+    # seed form: global RNG state is restored afterwards (NEW:747-777)
+    torch.manual_seed(5)
+    before = torch.get_rng_state()
+    a = NEW.shuffle_targets(g["targets"], perturb_seed=9)
+    assert torch.equal(torch.get_rng_state(), before)
+    assert torch.equal(a, NEW.shuffle_targets(g["targets"], perturb_seed=9))
+    assert sorted(a[:, 0].tolist()) == sorted(g["targets"][:, 0].tolist())
+
+
+def test_perturbation_window_logic():
+    p = core.Perturbation("random_target", training_run=6, length=3, seed=42, distribution="target",
+                          mean=5.75, std=9.5)
+    assert [e for e in range(12) if p.active(e)] == [5, 6, 7]      # epochs 6..8 (1-based), NEW:844-847
+    assert p.flags(5) == {"used_random_targets": True, "used_shuffled_targets": False,
+                          "used_uniform_images": False, "used_image_noise": False}
+    assert not any(p.flags(4).values())
+    none = core.Perturbation("none", 6, 3, 42, "target", 0.0, 1.0)
+    assert not none.active(6) and none.in_window(6)  # early-stop counter is frozen in the window anyway
+    # per-batch seed is independent of the epoch (NEW:920): same noise for the same batch index
+    t = torch.zeros(4, 6)
+    a = p.apply(None, t, 3, torch.device("cpu"))[1]
+    b = p.apply(None, t, 3, torch.device("cpu"))[1]
+    c = p.apply(None, t, 4, torch.device("cpu"))[1]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    gen = torch.Generator().manual_seed(42 + 6 * 1000 + 3)
+    assert torch.equal(a, torch.randn(4, 6, generator=gen) * 9.5 + 5.75)
+    u = core.Perturbation("uniform_images", 1, 1, 0, "normal", 0, 1).apply(torch.randn(2, 3, 4, 4), t, 0,
+                                                                            torch.device("cpu"))[0]
+    assert float(u.min()) == float(u.max()) == 0.5
+
+
+def test_results_csv_bootstrap_and_resume(tmp_path):
+    prev = tmp_path / "prev.csv"
+    with open(prev, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(core.NEW_HEADERS)
+        for e in range(1, 6):
+            w.writerow([e, 1.0 / e, 2.0 / e, 0.5, 0.01, False, False, False, False])
+    new = tmp_path / "sub" / "new.csv"
+    NEW._prepare_results_csv(str(new), str(prev), 3, print, None)
+    rows = list(csv.reader(open(new)))
+    assert rows[0] == core.NEW_HEADERS and [r[0] for r in rows[1:]] == ["1", "2", "3"]  # NEW:816-831
+    NEW._prepare_results_csv(str(prev), str(prev), 5, print, None)                      # in-place resume
+    assert len(list(csv.reader(open(prev)))) == 6
+    NEW._prepare_results_csv(str(new), None, 0, print, None)                            # fresh run
+    assert list(csv.reader(open(new))) == [core.NEW_HEADERS]
+
+
+def test_random_state_checkpoint_roundtrip(tmp_path):
+    from hba.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdamW([p], lr=3e-4)
+    gen = torch.Generator().manual_seed(1)
+    torch.manual_seed(77)
+    np.random.seed(78)
+    core.save_random_states(opt, 4, str(tmp_path), gen)
+    want_t, want_n, want_g = torch.rand(3), np.random.rand(3), torch.randperm(10, generator=gen)
+    ck = torch.load(tmp_path / "epoch5_random_states.pth", weights_only=False)
+    golden_keys = torch.load(os.path.join(GOLD, "tiny_training.pt"), weights_only=False)["random_state_keys"]
+    assert set(golden_keys) - {"cuda_rng_state", "cuda_rng_state_all"} <= set(ck.keys())
+    torch.manual_seed(0)
+    np.random.seed(0)
+    gen.manual_seed(0)
+    assert core.load_random_states(str(tmp_path), 5, optimizer=opt, dataloader_generator=gen)
+    assert torch.equal(torch.rand(3), want_t) and np.array_equal(np.random.rand(3), want_n)
+    assert torch.equal(torch.randperm(10, generator=gen), want_g)
+    assert core.load_random_states(str(tmp_path), 99) is False    # missing file -> warning + False
+
+
+def test_select_device_has_no_cpu_path():
+    import pytest
+    assert core.select_device(0) == torch.device("cuda:0") and core.select_device(-1) == torch.device("cuda")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        core.select_device(2)
