@@ -89,7 +89,7 @@ def test_plugin_module_surface():
     from src.models.CLIPs.clip_hba import clip
     assert "ViT-L/14" in clip._MODELS
     t = clip.tokenize("metallic; artificial")
-    assert t.shape == (1, 77) and t.dtype == torch.long and int(t.argmax()) == 3 + 1
+    assert t.shape == (1, 77) and t.dtype == torch.long and int(t.argmax()) == 3
     model = clip.build_model(clip.synthetic_state_dict("ViT-tiny-14.pt"))
     blk = model.visual.transformer.resblocks[-1]
     assert isinstance(blk.attn, torch.nn.MultiheadAttention)

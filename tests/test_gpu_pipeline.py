@@ -143,3 +143,119 @@ def test_random_target_and_shuffle_are_seed_deterministic_on_device():
     want = torch.randn(t.shape, device=DEV, generator=gen) * 9.5 + 5.75
     got = core.Perturbation("random_target", 3, 1, 42, "target", 5.75, 9.5).apply(None, t, 1, DEV)[1]
     assert torch.equal(got, want)
+
+
+def test_trunk_cache_is_bit_identical(tiny_checkpoint):
+    """Frozen-trunk cache (north star item 2): the cached step equals recomputation bit for bit."""
+    import hba
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    from hba.engine import TrunkCache
+    from oracle.synth import synthetic_problem
+    prob = synthetic_problem()
+    x = prob["train_images"][:4].to(DEV)
+    y66 = torch.randn(4, 6, generator=torch.Generator().manual_seed(3)).to(DEV)
+    for precision in ("bf16", "fp32"):
+        hba.set_precision(precision)
+        model = build_model(NEW).to(DEV)
+        eng = model.clip_model.hba_engine()
+        crit = torch.nn.MSELoss()
+
+        def run(ids):
+            for p in model.parameters():
+                p.grad = None
+            eng.batch_ids = ids
+            pred = model(x)
+            crit(pred, y66).backward()
+            return pred.detach().clone(), [p.grad.clone() for p in model.parameters() if p.requires_grad]
+
+        base_pred, base_grads = run(None)
+        eng.trunk_cache = TrunkCache(16)
+        fill_pred, fill_grads = run([3, 7, 1, 9])          # miss: computes the trunk and stores it
+        assert eng.trunk_cache.present == {1, 3, 7, 9}
+        hit_pred, hit_grads = run([3, 7, 1, 9])            # hit: trunk skipped
+        assert torch.equal(base_pred, fill_pred) and torch.equal(base_pred, hit_pred)
+        for a, b, c in zip(base_grads, fill_grads, hit_grads):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        with torch.no_grad():                              # eval path, permuted subset of cached ids
+            eng.batch_ids = [9, 3]
+            sub = model(x[[3, 0]])
+        assert torch.equal(sub, base_pred[[3, 0]])
+    hba.set_precision("bf16")
+
+
+def _write_things_like_dataset(root, n_train=12, n_rsa=8, seed=0):
+    """A THINGS-shaped dataset on disk: PNG images, the SPoSE csv layout (index, image name, 66 target
+    columns; NEW:191-202), the 48-image-style inference csv and RDM48_triplet.mat."""
+    import pandas as pd
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    img_dir = os.path.join(root, "imgs")
+    os.makedirs(img_dir, exist_ok=True)
+
+    def make(prefix, n):
+        names = []
+        for i in range(n):
+            name = f"{prefix}{i:03d}.png"
+            Image.fromarray(rng.integers(0, 255, (40, 52, 3), dtype=np.uint8)).save(os.path.join(img_dir, name))
+            names.append(name)
+        return names
+    tr, rs = make("train", n_train), make("rsa", n_rsa)
+    cols = {"image": tr}
+    for k in range(66):
+        cols[f"dim{k}"] = rng.standard_normal(n_train) * 9.5 + 5.75
+    pd.DataFrame(cols).to_csv(os.path.join(root, "train.csv"))
+    cols = {"image": rs}
+    for k in range(66):
+        cols[f"dim{k}"] = rng.standard_normal(n_rsa)
+    pd.DataFrame(cols).to_csv(os.path.join(root, "rsa.csv"))
+    rdm = 1 - np.corrcoef(rng.standard_normal((n_rsa, 10)))
+    np.fill_diagonal(rdm, 0)
+    scipy.io.savemat(os.path.join(root, "RDM48_triplet.mat"), {"RDM48_triplet": rdm})
+    return img_dir
+
+
+def test_run_behavioral_training_drivers_end_to_end(tiny_checkpoint, tmp_path):
+    """The config-dict contract of BDRV:11-33 / SWEEP:118-147 end to end on files: baseline run
+    (split + per-epoch checkpoints), then a sweep condition that resumes from baseline epoch 1 with a
+    random-target window — once with the HBM-resident loaders + trunk cache, once with the plain
+    DataLoader path: identical CSV rows."""
+    import hba
+    import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    hba.set_precision("bf16")
+    root = str(tmp_path)
+    img_dir = _write_things_like_dataset(root)
+    common = {"csv_file": f"{root}/train.csv", "img_dir": img_dir, "inference_csv_file": f"{root}/rsa.csv",
+              "RDM48_triplet_dir": f"{root}/RDM48_triplet.mat", "backbone": "ViT-tiny/14", "batch_size": 4,
+              "lr": 3e-4, "random_seed": 1, "vision_layers": 2, "transformer_layers": 1, "rank": 8,
+              "criterion": torch.nn.MSELoss(), "cuda": 0}
+    base_cfg = dict(common, epochs=2, train_portion=0.75, early_stopping_patience=20, logger=None,
+                    checkpoint_path=f"{root}/base/model.pth", training_res_path=f"{root}/base/res.csv",
+                    dora_parameters_path=f"{root}/base/dora", random_state_path=f"{root}/base/rand")
+    BASE.run_behavioral_training(base_cfg)
+    rows = list(csv.reader(open(f"{root}/base/res.csv")))
+    assert rows[0] == ["epoch", "train_loss", "test_loss", "behavioral_rsa_rho", "behavioral_rsa_p_value"]
+    assert [r[0] for r in rows[1:]] == ["1", "2"]
+    split = torch.load(f"{root}/base/rand/dataset_split_indices.pth")
+    assert len(split["train_indices"]) == 9 and len(split["test_indices"]) == 3
+    assert os.path.exists(f"{root}/base/dora/epoch2_dora_params.pth")
+    assert os.path.exists(f"{root}/base/rand/epoch2_random_states.pth")
+
+    results = {}
+    for tag, resident in (("resident", True), ("plain", False)):
+        cfg = dict(common, epochs=3, early_stopping_patience=10, hba_resident=resident,
+                   checkpoint_path=f"{root}/{tag}/model.pth", training_res_path=f"{root}/{tag}/res.csv",
+                   dora_parameters_path=f"{root}/{tag}/dora", random_state_path=f"{root}/{tag}/rand",
+                   baseline_dora_directory=f"{root}/base/dora", baseline_random_state_path=f"{root}/base/rand",
+                   baseline_split_indices_path=f"{root}/base/rand/dataset_split_indices.pth",
+                   perturb_type="random_target", perturb_length=1, perturb_distribution="target",
+                   perturb_seed=42, training_run=2, resume_from_epoch=1,
+                   previous_training_res_path=f"{root}/base/res.csv")
+        NEW.run_behavioral_training(cfg)
+        results[tag] = list(csv.reader(open(cfg["training_res_path"])))
+    r = results["resident"]
+    assert r[0][5:] == ["used_random_targets", "used_shuffled_targets", "used_uniform_images", "used_image_noise"]
+    assert [row[0] for row in r[1:]] == ["1", "2", "3"]          # epoch 1 pre-populated from the baseline
+    assert r[1][:5] == rows[1][:5]
+    assert r[2][5] == "True" and r[3][5] == "False"              # random targets in epoch 2 only
+    assert r == results["plain"]                                 # resident + cached == plain, exactly

@@ -32,6 +32,8 @@ from torchvision import transforms
 from tqdm import tqdm
 
 from hba import DoRALayer, ops, rsa
+from hba.data import ResidentLoader, ResidentStore
+from hba.engine import TrunkCache
 from hba.optim import FusedAdamW
 from src.models.CLIPs.clip_hba import clip
 
@@ -82,6 +84,7 @@ class ThingsDataset(Dataset):
     """(image_name, image[3,224,224], targets[66]) rows of the SPoSE csv (NEW:180-204)."""
 
     def __init__(self, csv_file, img_dir):
+        self.csv_file = csv_file
         self.img_dir = img_dir
         self.transform = _things_transform()
         self.annotations = pd.read_csv(csv_file, index_col=0)
@@ -287,6 +290,50 @@ def load_random_states(random_state_path, epoch, optimizer=None, dataloader_gene
     return True
 
 
+# ------------------------------------------------------------------------------- resident data / cache
+_STORES = {}
+
+
+def resident_loaders(config, dataset, train_dataset, test_dataset, inference_dataset, device,
+                     dataloader_generator, train_indices=None, test_indices=None):
+    """HBM-resident equivalents of the three DataLoaders of NEW:1123-1126 (same batch order and
+    generator consumption; images decoded once per process instead of once per epoch)."""
+    key = (config['csv_file'], config['img_dir'], str(device))
+    if key not in _STORES:
+        _STORES[key] = ResidentStore(dataset, device)
+    ikey = (config['inference_csv_file'], config['img_dir'], str(device))
+    if ikey not in _STORES:
+        _STORES[ikey] = ResidentStore(inference_dataset, device)
+    bs = config['batch_size']
+    train_loader = ResidentLoader(_STORES[key], bs, shuffle=True, generator=dataloader_generator,
+                                  index_map=train_indices, dataset=train_dataset)
+    test_loader = ResidentLoader(_STORES[key], bs, shuffle=False, index_map=test_indices,
+                                 dataset=test_dataset)
+    inference_loader = ResidentLoader(_STORES[ikey], bs, shuffle=False, dataset=inference_dataset)
+    return train_loader, test_loader, inference_loader
+
+
+def enable_trunk_cache(model, n_images):
+    """Frozen-trunk activation cache (hba.engine.TrunkCache) sized for every distinct image."""
+    eng = _engine_of(model)
+    if eng is not None and eng.trunk_cache is None:
+        from hba.data import _NAME_IDS
+        eng.trunk_cache = TrunkCache(max(n_images, len(_NAME_IDS)) + 64)
+
+
+def _engine_of(model):
+    cm = getattr(_unwrap(model), "clip_model", None)
+    return cm.hba_engine() if hasattr(cm, "hba_engine") else None
+
+
+def _announce_ids(model, loader, allowed=True):
+    """Tells the engine which images the next forward batch holds (ResidentLoader only), so that the
+    frozen-trunk cache can be used; never for perturbed images."""
+    eng = _engine_of(model)
+    if eng is not None:
+        eng.batch_ids = getattr(loader, "last_ids", None) if allowed else None
+
+
 # ------------------------------------------------------------------------------- evaluation
 def evaluate_model(model, data_loader, device, criterion):
     """NEW:584-602: sample-weighted mean loss; accumulated on the device, one read at the end."""
@@ -297,6 +344,7 @@ def evaluate_model(model, data_loader, device, criterion):
                                        file=sys.stderr):
             images = images.to(device, non_blocking=True)
             targets = targets.to(device, non_blocking=True)
+            _announce_ids(model, data_loader)
             total += criterion(model(images), targets).double() * images.size(0)
     return float(total) / len(data_loader.dataset)
 
@@ -317,6 +365,7 @@ def behavioral_RSA(model, inference_loader, device, logger=None):
     names, chunks = [], []
     with torch.no_grad():
         for image_name, image in inference_loader:
+            _announce_ids(model, inference_loader)
             chunks.append(model(image.to(device, non_blocking=True)))
             names.extend(image_name)
     emb = torch.cat(chunks, 0)
@@ -348,6 +397,7 @@ def shuffle_targets(targets, perturb_seed=None, generator=None):
     return shuffled
 
 
+IMAGE_PERTURBATIONS = ("image_noise", "uniform_images")
 PERTURB_FLAGS = {"random_target": "used_random_targets", "label_shuffle": "used_shuffled_targets",
                  "uniform_images": "used_uniform_images", "image_noise": "used_image_noise"}
 
@@ -428,6 +478,7 @@ def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, ep
         if active:
             images, targets = perturb.apply(images, targets, batch_idx, device)
         optimizer.zero_grad()
+        _announce_ids(model, train_loader, allowed=not (active and perturb.kind in IMAGE_PERTURBATIONS))
         predictions = model(images)
         loss = criterion(predictions, targets)
         bad = guard.check(predictions, loss.reshape(1), targets)

@@ -12,7 +12,7 @@ from functions._pipeline_core import (  # noqa: F401  (re-exported reference sur
     BASE_HEADERS, CLIPHBA, DoRALayer, ThingsDataset, ThingsInferenceDataset, append_csv_row,
     apply_dora_to_ViT, build_model, count_trainable_parameters, describe_run, evaluate_model,
     load_clip_to_cpu, make_optimizer, open_logger, save_random_states, seed_everything, select_device,
-    setup_logger, switch_dora_layers, train_one_epoch)
+    setup_logger, switch_dora_layers, train_one_epoch, enable_trunk_cache, resident_loaders)
 from functions._pipeline_core import behavioral_RSA as _behavioral_RSA
 from functions.spose_dimensions import classnames66  # noqa: F401
 from src.models.clip_hba_utils import save_dora_parameters
@@ -86,13 +86,20 @@ def run_behavioral_training(config):
                                                RDM48_triplet_dir=config['RDM48_triplet_dir'])
     dataloader_generator = torch.Generator()
     dataloader_generator.manual_seed(config['random_seed'])
-    train_loader = DataLoader(train_dataset, batch_size=config['batch_size'], shuffle=True,
-                              generator=dataloader_generator)
-    test_loader = DataLoader(test_dataset, batch_size=config['batch_size'], shuffle=False)
-    inference_loader = DataLoader(inference_dataset, batch_size=config['batch_size'], shuffle=False)
     device = select_device(config['cuda'])
+    if config.get('hba_resident', True):
+        train_loader, test_loader, inference_loader = resident_loaders(
+            config, dataset, train_dataset, test_dataset, inference_dataset, device, dataloader_generator,
+            list(train_dataset.indices), list(test_dataset.indices))
+    else:
+        train_loader = DataLoader(train_dataset, batch_size=config['batch_size'], shuffle=True,
+                                  generator=dataloader_generator)
+        test_loader = DataLoader(test_dataset, batch_size=config['batch_size'], shuffle=False)
+        inference_loader = DataLoader(inference_dataset, batch_size=config['batch_size'], shuffle=False)
     model = build_model(config, device, logger)
     model.to(device)
+    if config.get('hba_resident', True) and config.get('hba_trunk_cache', True):
+        enable_trunk_cache(model, len(dataset) + len(inference_dataset))
     optimizer = make_optimizer(model, config['lr'])
     describe_run(model, config, logger)
     train_model(model, train_loader, test_loader, inference_loader, device, optimizer, config['criterion'],

@@ -17,7 +17,8 @@ from functions._pipeline_core import (  # noqa: F401  (re-exported reference sur
     count_trainable_parameters, describe_run, evaluate_model, load_clip_to_cpu,
     load_dataset_split_indices, load_random_states, make_optimizer, open_logger,
     replace_with_gaussian_noise, save_dora_parameters, save_random_states, seed_everything,
-    select_device, setup_logger, shuffle_targets, switch_dora_layers, train_one_epoch)
+    select_device, setup_logger, shuffle_targets, switch_dora_layers, train_one_epoch,
+    enable_trunk_cache, resident_loaders)
 from functions.spose_dimensions import classnames66  # noqa: F401
 
 
@@ -135,11 +136,17 @@ def run_behavioral_training(config):
                                                RDM48_triplet_dir=config['RDM48_triplet_dir'])
     dataloader_generator = torch.Generator()
     dataloader_generator.manual_seed(config['random_seed'])
-    train_loader = DataLoader(train_dataset, batch_size=config['batch_size'], shuffle=True,
-                              generator=dataloader_generator)
-    test_loader = DataLoader(test_dataset, batch_size=config['batch_size'], shuffle=False)
-    inference_loader = DataLoader(inference_dataset, batch_size=config['batch_size'], shuffle=False)
     device = select_device(config['cuda'])
+    if config.get('hba_resident', True):
+        # same batch order / generator consumption as the DataLoaders of NEW:1123-1126, images in HBM
+        train_loader, test_loader, inference_loader = resident_loaders(
+            config, dataset, train_dataset, test_dataset, inference_dataset, device, dataloader_generator,
+            split_info['train_indices'], split_info['test_indices'])
+    else:
+        train_loader = DataLoader(train_dataset, batch_size=config['batch_size'], shuffle=True,
+                                  generator=dataloader_generator)
+        test_loader = DataLoader(test_dataset, batch_size=config['batch_size'], shuffle=False)
+        inference_loader = DataLoader(inference_dataset, batch_size=config['batch_size'], shuffle=False)
     model = build_model(config, device, logger)
     training_run = config['training_run']
     resume_from_epoch = config.get('resume_from_epoch', 0)
@@ -154,6 +161,8 @@ def run_behavioral_training(config):
     else:
         logger.info("Using original DoRA parameters from model initialization")
     model.to(device)
+    if config.get('hba_resident', True) and config.get('hba_trunk_cache', True):
+        enable_trunk_cache(model, len(dataset) + len(inference_dataset))
     optimizer = make_optimizer(model, config['lr'])
     if resume_from_epoch > 0:
         prior = config.get('resume_random_state_path') or config.get('baseline_random_state_path')

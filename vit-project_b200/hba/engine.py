@@ -66,6 +66,8 @@ class Engine:
         self._bufs = {}
         self._stamp = None
         self.cache_text = True
+        self.trunk_cache = None   # TrunkCache: frozen-trunk activations per image id (exact reuse)
+        self.batch_ids = None     # image ids of the next forward batch (consumed by run_forward)
         self._text_cache = None
         self._gen = 0
         self.launches = 0  # kernels launched by the last run_forward / run_backward (our own count)
@@ -76,7 +78,8 @@ class Engine:
         return self.precision == "fp32"
 
     def _param_stamp(self):
-        return sum(p._version for p in self.model.parameters()) + 7919 * sum(
+        # frozen tensors only: trainable adapter parameters are read live on every call
+        return sum(p._version for p in self.model.parameters() if not p.requires_grad) + 7919 * sum(
             b._version for b in self.model.buffers())
 
     def _operand(self, W, K_pad=None, transpose=False):
@@ -225,6 +228,12 @@ class Engine:
 
     def _block_full(self, tw, blk, tag, x_in, x_mid, x_out, B, w_out, b_out, keep=None):
         """One full residual attention block on all M = B*T rows (x_* are fp32 [M, d])."""
+        a = self._attn_part(tw, blk, tag, x_in, B, keep.get("a_f32") if keep else None)
+        self._live_part(tw, blk, tag, a, x_in, x_mid, x_out, B, w_out, b_out, keep)
+
+    def _attn_part(self, tw, blk, tag, x_in, B, a_f32=None):
+        """ln_1 -> in_proj -> softmax attention on all rows; returns the attention output as a GEMM
+        operand (and in fp32 when `a_f32` is given).  Frozen in every block of the reference setup."""
         T, d, H = tw.T, tw.d, tw.heads
         M = B * T
         h = self._opbuf(tag + ".h", M, d)
@@ -232,15 +241,22 @@ class Engine:
         qkv = self._qkv_buffer(tag, M, d)
         self._gemm_qkv(h, blk.w_in, blk.b_in, qkv, M)
         a = self._opbuf(tag + ".a", M, d)
-        ops.attention_fwd(qkv, B, T, H, causal=tw.causal, out=a,
-                          out_f32=keep.get("a_f32") if keep else None)
+        ops.attention_fwd(qkv, B, T, H, causal=tw.causal, out=a, out_f32=a_f32)
+        self.launches += 3
+        return a
+
+    def _live_part(self, tw, blk, tag, a, x_in, x_mid, x_out, B, w_out, b_out, keep=None):
+        """out_proj (+ residual) -> ln_2 -> MLP (+ residual) on all rows."""
+        d = tw.d
+        M = B * tw.T
         ops.gemm(a, w_out, M, bias=b_out, residual=x_in, out_f32=x_mid)
+        h = self._opbuf(tag + ".h", M, d)
         ops.layernorm_fwd(x_mid, M, d, blk.ln2_w, blk.ln2_b, LN_EPS, y=h)
         hid = self._opbuf(tag + ".hid", M, 4 * d)
         ops.gemm(h, blk.w_fc, M, bias=blk.b_fc, act=HBA_ACT_QUICKGELU, out=hid,
                  pre_out=keep.get("h_pre") if keep else None)
         ops.gemm(hid, blk.w_proj, M, bias=blk.b_proj, residual=x_mid, out_f32=x_out)
-        self.launches += 6
+        self.launches += 4
 
     def _rows_tail(self, tw, blk, tag, a_rows, x_res, R, w_out, b_out, keep):
         """out_proj + MLP of a block on R selected rows (CLS rows / EOT rows).
@@ -295,7 +311,7 @@ class Engine:
             self._block_full(tw, blk, "v", x, x, x, B, blk.w_out, blk.b_out)
         return x, tw
 
-    def vision_head(self, x, tw, B, adapters, need_grad):
+    def vision_head(self, x, tw, B, adapters, need_grad, cache_ctx=None):
         """Blocks L-2 (full) and L-1 (CLS row only) + ln_post + proj.  `adapters` maps block index
         -> (W, bias) for adapter blocks.  Returns (img_feat [B,E] fp32, saved dict)."""
         L = len(tw.blocks)
@@ -312,8 +328,7 @@ class Engine:
                 trainP = need_grad and Wp.requires_grad
                 saved["trainP"] = trainP
                 if trainP:
-                    keepP = {"a_f32": self._keep("aP", (M, d)),
-                             "h_pre": self._keep("hpreP", (M, 4 * d),
+                    keepP = {"h_pre": self._keep("hpreP", (M, 4 * d),
                                                  torch.float32 if self.split else torch.bfloat16)}
                     saved["keepP"] = keepP
                 bP = bp.detach()
@@ -322,7 +337,23 @@ class Engine:
                 saved["trainP"] = False
             x_mid = self._keep("xmidP", (M, d)) if keepP else x
             x_out = self._keep("xoutP", (M, d)) if need_grad else x
-            self._block_full(tw, blkP, "v", x, x_mid, x_out, B, wP, bP, keep=keepP)
+            a_f32 = None
+            if cache_ctx is not None and cache_ctx["hit"]:
+                # frozen half of block P (ln_1, in_proj, attention) comes from the trunk cache
+                a_f32 = cache_ctx["a"]
+                a = self._opbuf("v.a", M, d)
+                ops.split_bf16(a_f32, a)
+                self.launches += 1
+            else:
+                fill = cache_ctx is not None
+                if keepP or fill:
+                    a_f32 = self._keep("aP", (M, d))
+                a = self._attn_part(tw, blkP, "v", x, B, a_f32)
+                if fill:
+                    cache_ctx["cache"].store(cache_ctx["ids"], x, a_f32)
+            if keepP:
+                keepP["a_f32"] = a_f32
+            self._live_part(tw, blkP, "v", a, x, x_mid, x_out, B, wP, bP, keep=keepP)
             if keepP:
                 keepP["x_mid"] = x_mid
             x = x_out
@@ -429,8 +460,18 @@ class Engine:
         tokens = tokens if tokens.is_contiguous() else tokens.contiguous()
         B = images.shape[0]
         L = len(self.vis.blocks)
-        x, tw = self.vision_trunk(images, max(L - 2, 0))
-        img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad)
+        ids, self.batch_ids = self.batch_ids, None
+        cache_ctx = None
+        native = images.shape[2] == self.res and images.shape[3] == self.res
+        if self.trunk_cache is not None and ids is not None and L >= 2 and native:
+            if len(ids) != B:
+                raise RuntimeError("libhba: batch_ids does not match the image batch")
+            cache_ctx = self.trunk_cache.lookup(self, ids)
+        if cache_ctx is not None and cache_ctx["hit"]:
+            x, tw = cache_ctx["x"], self.vis
+        else:
+            x, tw = self.vision_trunk(images, max(L - 2, 0))
+        img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad, cache_ctx)
         txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
         pred = torch.empty(B, txt_feat.shape[0], device=self.device)
         ops.cos_head_fwd(img_feat, txt_feat, self.logit_scale, pred)
@@ -537,6 +578,53 @@ class Engine:
     def _frozen_wt(self, blk):
         raise RuntimeError("libhba: backward through a frozen out_proj of the last block is not "
                            "staged (adapter expected on the last vision block)")
+
+
+class TrunkCache:
+    """HBM cache of the frozen vision trunk per image: the input of block L-2 and that block's
+    attention output (ln_1 -> in_proj -> attention is frozen-on-frozen there), both fp32.
+
+    Exactness: train images are never augmented (NEW:183-188) and blocks 0..L-3 plus the attention
+    half of block L-2 hold no trainable parameter (NEW:665-669), so for an un-perturbed image these
+    activations are identical in every epoch; the cached path runs the same kernels on the same
+    values and is bit-identical to recomputation.  Callers must not pass ids for perturbed images
+    (`image_noise`, `uniform_images` windows, NEW:880-916)."""
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.x = self.a = None
+        self.present = set()
+        self.stamp = None
+
+    def _ensure(self, eng):
+        width = eng.vis.T * eng.vis.d
+        stamp = (eng.precision, eng._stamp, width, str(eng.device))
+        if self.x is None or self.stamp != stamp:
+            self.x = torch.empty(self.capacity, width, device=eng.device)
+            self.a = torch.empty(self.capacity, width, device=eng.device)
+            self.present = set()
+            self.stamp = stamp
+
+    def lookup(self, eng, ids):
+        self._ensure(eng)
+        ids = [int(i) for i in ids]
+        if max(ids) >= self.capacity or min(ids) < 0:
+            raise RuntimeError("TrunkCache: image id outside the cache capacity")
+        ids_dev = torch.tensor(ids, dtype=torch.int64, device=eng.device)
+        ctx = {"cache": self, "ids": (ids, ids_dev), "hit": all(i in self.present for i in ids)}
+        if ctx["hit"]:
+            B, d = len(ids), eng.vis.d
+            ctx["x"] = torch.index_select(self.x, 0, ids_dev, out=eng._buf("v.x", (B, self.x.shape[1]))
+                                          ).view(B * eng.vis.T, d)
+            ctx["a"] = torch.index_select(self.a, 0, ids_dev, out=eng._buf("v.acache", (B, self.x.shape[1]))
+                                          ).view(B * eng.vis.T, d)
+        return ctx
+
+    def store(self, ids, x, a_f32):
+        host, dev = ids
+        self.x.index_copy_(0, dev, x.view(len(host), -1))
+        self.a.index_copy_(0, dev, a_f32.view(len(host), -1))
+        self.present.update(host)
 
 
 def get_engine(model) -> Engine:

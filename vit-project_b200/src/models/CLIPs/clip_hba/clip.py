@@ -212,14 +212,14 @@ def _download(url, root):
 
 def tokenize(texts, context_length=CONTEXT_LENGTH):
     """str | list[str] -> int64 [n, context_length]: [SOT, word ids ..., EOT, 0-pad].
-    With the BPE vocabulary unavailable offline, each lower-cased whitespace/punctuation token maps to
+    With the BPE vocabulary unavailable offline, each lower-cased whitespace-separated word maps to
     a stable pseudo-id (sha256); EOT stays the row maximum, which is all the model relies on
     (``text.argmax(-1)``).  A str yields [1,77] like the published tokenizer, so the reference's
     ``torch.stack([clip.tokenize(c) ...])`` (NEW:282) gives [66,1,77]."""
     rows = []
     for t in ([texts] if isinstance(texts, str) else list(texts)):
         ids = [SOT_TOKEN]
-        for w in t.lower().replace(",", " , ").replace(";", " ; ").split()[: context_length - 2]:
+        for w in t.lower().replace(",", " , ").split()[: context_length - 2]:
             h = int.from_bytes(hashlib.sha256(w.encode()).digest()[:4], "little")
             ids.append(1 + h % (SOT_TOKEN - 1))
         ids.append(EOT_TOKEN)
