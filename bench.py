@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     return ap.parse_args()
 
 
@@ -188,6 +189,85 @@ def build_gpu_model(args, device):
     return model, opt
 
 
+EPOCHS_PER_CONDITION = 55  # reference sweep mean: 64.0 h * 3600 / 97 conditions / 43.5 s per epoch
+
+
+def measure_sweep(args, device, world):
+    """Perturbation-sweep throughput (BASELINE.json metric, second half): epochs of the drop-in
+    `train_model` (NEW:782-1063: 1444 train + 362 test + 48 RSA images, per-epoch eval, RSA, CSV row,
+    DoRA + random-state checkpoints) on HBM-resident synthetic data with the frozen-trunk cache.
+    One condition = EPOCHS_PER_CONDITION epochs; one condition per GPU, no collective."""
+    import tempfile
+    import numpy as np
+    import scipy.io
+    import torch
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    from functions import _pipeline_core as core
+    from hba.data import ResidentLoader, ResidentStore
+    n_train, n_test, n_rsa, bs = 1444, 362, 48, args.batch
+    g = torch.Generator(device=device).manual_seed(5)
+    imgs = torch.randn(n_train + n_test, 3, 224, 224, device=device, generator=g)
+    tgts = torch.randn(n_train + n_test, N_CLASSES, device=device, generator=g) * 9.5 + 5.75
+    rsa_imgs = torch.randn(n_rsa, 3, 224, 224, device=device, generator=g)
+    store = ResidentStore(None, device, names=[f"img{i}" for i in range(n_train + n_test)], images=imgs,
+                          targets=tgts)
+    rstore = ResidentStore(None, device, names=[f"rsa{i}" for i in range(n_rsa)], images=rsa_imgs)
+    tmp = tempfile.mkdtemp(prefix="hba_sweep_")
+    rdm = 1 - np.corrcoef(np.random.default_rng(2).standard_normal((n_rsa, 66)))
+    np.fill_diagonal(rdm, 0)
+    scipy.io.savemat(os.path.join(tmp, "RDM48_triplet.mat"), {"RDM48_triplet": rdm})
+
+    class _Rsa:  # carries the attributes behavioral_RSA reads from loader.dataset (NEW:636)
+        RDM48_triplet_dir = os.path.join(tmp, "RDM48_triplet.mat")
+
+        def __len__(self):
+            return n_rsa
+
+    model, opt = build_gpu_model(args, device)
+    core.enable_trunk_cache(model, n_train + n_test + n_rsa)
+    gen = torch.Generator()
+    gen.manual_seed(1)
+    perm = torch.randperm(n_train + n_test, generator=torch.Generator().manual_seed(1)).tolist()
+    tl = ResidentLoader(store, bs, shuffle=True, generator=gen, index_map=perm[:n_train])
+    el = ResidentLoader(store, bs, shuffle=False, index_map=perm[n_train:])
+    rl = ResidentLoader(rstore, bs, shuffle=False, dataset=_Rsa())
+    crit = torch.nn.MSELoss()
+    import logging
+    logging.disable(logging.CRITICAL)
+
+    def run(first, last, tag):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            NEW.train_model(model, tl, el, rl, device, opt, crit, epochs=last,
+                            training_res_path=os.path.join(tmp, "res.csv"), training_run=2, perturb_length=1,
+                            perturb_seed=42, mean=5.75, std=9.5, perturb_distribution="target",
+                            perturb_type="random_target", logger=None, early_stopping_patience=1000,
+                            dora_parameters_path=os.path.join(tmp, "dora"),
+                            random_state_path=os.path.join(tmp, "rand"), dataloader_generator=gen,
+                            resume_from_epoch=first,
+                            previous_training_res_path=os.path.join(tmp, "res.csv") if first else None)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    k = 3
+    t_fill = run(0, 1, "fill")          # epoch 1: trunk computed once per image, cache filled
+    t_cached = run(1, 1 + k, "cached")  # epochs 2..k+1: frozen trunk served from HBM
+    logging.disable(logging.NOTSET)
+    sec_epoch = t_cached / k
+    imgs_epoch = n_train + n_test + n_rsa
+    return {"conditions_per_hour": world * 3600.0 / (EPOCHS_PER_CONDITION * sec_epoch), "unit": "conditions/h",
+            "epochs_per_condition": EPOCHS_PER_CONDITION, "sec_per_epoch_cached": sec_epoch,
+            "sec_first_epoch_cache_fill": t_fill, "images_per_epoch": imgs_epoch,
+            "blended_images_per_s": world * imgs_epoch / sec_epoch,
+            "config": "train_model epochs on 1444/362/48 synthetic HBM-resident images, batch %d, random_target "
+                      "window, per-epoch eval + RSA + CSV + DoRA/random-state checkpoints, frozen-trunk cache; "
+                      "wall clock incl. host" % bs,
+            "reference_baseline": "1.52 conditions/h, 43.5 s/epoch on one unnamed GPU (BASELINE.md, derived)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -301,6 +381,17 @@ def main():
                      "gemm_ms_per_step": gemm_ms / args.steps,
                      "gemm_share_of_step": gemm_ms / ms},
     }
+    if not args.no_sweep:
+        del model, opt
+        torch.cuda.empty_cache()
+        sw = measure_sweep(args, device, world)
+        if dist is not None:
+            t = torch.tensor([sw["sec_per_epoch_cached"]], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sw["sec_per_epoch_cached"] = float(t)
+            sw["conditions_per_hour"] = world * 3600.0 / (EPOCHS_PER_CONDITION * float(t))
+            sw["blended_images_per_s"] = world * sw["images_per_epoch"] / float(t)
+        out["sweep"] = sw
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

@@ -147,15 +147,35 @@ def replace_with_gaussian_noise(image, mean, std):
 
 
 # ------------------------------------------------------------------------------- model
+_FROZEN_MODELS = {}
+
+
 def load_clip_to_cpu(backbone_name):
-    """NEW:251-265 through the plug-in clip module."""
+    """NEW:251-265 through the plug-in clip module.
+
+    The frozen CLIP is kept per process (HBA_REUSE_MODEL=0 disables it): a sweep worker runs many
+    conditions in one process (SWEEP:192-223) and every one of them starts from the same frozen
+    checkpoint, so the staged weights and the frozen-trunk cache survive from condition to condition.
+    On reuse the adapters of the previous condition are unwrapped back to the original out_proj."""
+    reuse = os.environ.get("HBA_REUSE_MODEL", "1") != "0"
     path = clip._download(clip._MODELS[backbone_name], os.path.expanduser("~/.cache/clip"))
+    key = (backbone_name, path, os.path.getmtime(path))
+    if reuse and key in _FROZEN_MODELS:
+        model = _FROZEN_MODELS[key]
+        for tower in (model.visual.transformer, model.transformer):
+            for blk in tower.resblocks:
+                if isinstance(blk.attn.out_proj, DoRALayer):
+                    blk.attn.out_proj = blk.attn.out_proj.original_layer
+        return model
     try:
         jit = torch.jit.load(path, map_location="cpu").eval()
         state_dict = jit.state_dict()
     except RuntimeError:
         state_dict = torch.load(path, map_location="cpu")
-    return clip.build_model(state_dict)
+    model = clip.build_model(state_dict)
+    if reuse:
+        _FROZEN_MODELS[key] = model
+    return model
 
 
 class CLIPHBA(nn.Module):

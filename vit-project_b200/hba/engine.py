@@ -79,8 +79,14 @@ class Engine:
 
     def _param_stamp(self):
         # frozen tensors only: trainable adapter parameters are read live on every call
-        return sum(p._version for p in self.model.parameters() if not p.requires_grad) + 7919 * sum(
+        stamp = sum(p._version for p in self.model.parameters() if not p.requires_grad) + 7919 * sum(
             b._version for b in self.model.buffers())
+        # which out_proj slots hold adapters is part of the staging (module surgery restages)
+        slots = tuple(id(blk.attn.out_proj.original_layer) if hasattr(blk.attn.out_proj, "original_layer")
+                      else -id(blk.attn.out_proj)
+                      for tower in (self.model.visual.transformer, self.model.transformer)
+                      for blk in tower.resblocks)
+        return (stamp, slots)
 
     def _operand(self, W, K_pad=None, transpose=False):
         W = W.detach()

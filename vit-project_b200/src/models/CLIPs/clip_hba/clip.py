@@ -163,10 +163,15 @@ def build_model(state_dict):
     if "visual.proj" not in state_dict:
         raise NotImplementedError("libhba covers the ViT CLIP variants only (ResNet towers are out "
                                   "of scope: the reference drivers use ViT-L/14)")
-    model = CLIP(**_arch_from_state_dict(state_dict))
-    sd = {k: v for k, v in state_dict.items()
-          if k not in ("input_resolution", "context_length", "vocab_size")}
-    model.load_state_dict(sd)
+    # modules are created on the meta device (no throw-away random init of 428 M parameters) and
+    # take ownership of the checkpoint tensors
+    with torch.device("meta"):
+        model = CLIP(**_arch_from_state_dict(state_dict))
+    sd = {k: (v.detach().clone().float() if torch.is_floating_point(v) else v.detach().clone())
+          for k, v in state_dict.items() if k not in ("input_resolution", "context_length", "vocab_size")}
+    model.load_state_dict(sd, assign=True)
+    for p_ in model.parameters():
+        p_.requires_grad_(True)
     return model.eval()
 
 
