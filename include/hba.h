@@ -38,7 +38,9 @@ int hba_device_check(void);
  * Replaces every nn.Linear / in_proj / out_proj / conv1-as-GEMM of the un-vendored CLIP towers
  * reached through NEW:298 (F.linear at TORCH functional.py:6244 in_proj, :6690 out_proj) and the
  * timm ViT-B/16 linears of VIT:138-140.
- *   A, B are bf16, K-major (row-major [rows, ld]); K % 64 == 0; lda/ldb % 8 == 0.
+ *   A, B are bf16, K-major (row-major [rows, ld]) by default; lda/ldb % 8 == 0.  With a_mn_major /
+ *   b_mn_major the operand is stored [K, M] / [K, N] instead (MN-major UMMA descriptors), which gives
+ *   dW = dY^T X and dX = dY W without any transposed copy.  K % 64 == 0 unless nsplit == 1.
  *   nsplit == 1: plain bf16 product.
  *   nsplit == 3: "fp32 mode" — A and B each hold a hi part at column 0 and a lo part at column
  *     offset a_lo_off / b_lo_off (x ~= hi + lo, both bf16); the kernel accumulates
@@ -85,6 +87,8 @@ typedef struct hba_gemm_params {
   int32_t out_lo_off;
   int32_t transpose_out;
   int32_t max_ctas; /* 0 = one persistent CTA per SM */
+  int32_t a_mn_major; /* A stored as [K, lda] (M contiguous): C = A^T-layout product, no transpose pass */
+  int32_t b_mn_major; /* B stored as [K, ldb] (N contiguous), e.g. dX = dY . W with W [out, in] as is */
 } hba_gemm_params;
 
 int hba_gemm_bf16(const hba_gemm_params* p, void* stream);
@@ -113,7 +117,8 @@ int hba_layernorm_bwd(const float* dy, int64_t ld_dy, const float* x, int64_t ro
  * embedding + ln_pre, reached via NEW:298).
  * im2col: image [B,3,H,W] fp32 NCHW -> patches [B*gh*gw, ld_out] bf16 hi/lo, column index
  *         = c*P*P + py*P + px (conv weight [width, 3, P, P] flattened), zero padded to ld.
- * assemble: x[b,0,:] = cls + pos[0]; x[b,1+p,:] = conv[b*np+p,:] + pos[1+p]; then ln_pre.
+ * assemble: x[b,0,:] = cls + pos[0]; x[b,1+p,:] = conv[b*np+p,:] + pos[1+p]; then ln_pre
+ *           (gamma == NULL: no LayerNorm, the timm ViT-B/16 layout of VIT:283).
  */
 int hba_im2col_patches(const float* image, int32_t B, int32_t H, int32_t W, int32_t P, void* out,
                        int64_t ld_out, int64_t lo_off, void* stream);
@@ -219,6 +224,25 @@ int hba_softmax_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* label
                            int32_t C, float* loss, float* d_logits, int64_t ld_d,
                            int32_t* correct_top1, float* workspace /* >= 2*B floats */,
                            void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Extra kernels of the fully-trained ViT-B/16 data-parallel baseline (VIT:125-165: every parameter
+ * receives a gradient).
+ * hba_colsum: out[c] (+)= sum_r x[r, c]  (bias gradients of every Linear / the conv);
+ *   workspace >= 128 * cols floats.
+ * hba_layernorm_param_grad: dgamma_dbeta[0:cols] (+)= sum_r dy * xhat, [cols:2cols] (+)= sum_r dy;
+ *   workspace >= 2*rows + 256*cols floats.
+ * hba_attention_bwd: full softmax-attention backward, d_out [B*T, H*64] -> d_qkv [B*T, 3*H*64]
+ *   (dtypes HBA_DT_*: (bf16, bf16|f32, bf16) or (f32, f32, f32)).
+ */
+int hba_colsum(const void* x, int32_t dtype, int64_t rows, int32_t cols, int64_t ld, float* out,
+               int32_t accumulate, float* workspace, void* stream);
+int hba_layernorm_param_grad(const float* dy, int64_t ld_dy, const float* x, int64_t rows,
+                             int32_t cols, int64_t ldx, int64_t row_step, float eps,
+                             float* dgamma_dbeta, int32_t accumulate, float* workspace, void* stream);
+int hba_attention_bwd(const void* qkv, int32_t qkv_dtype, int64_t ld_qkv, int32_t B, int32_t T,
+                      int32_t H, int32_t causal, const void* d_out, int32_t do_dtype, int64_t ld_do,
+                      void* d_qkv, int32_t dq_dtype, int64_t ld_dqkv, void* stream);
 
 /* misc elementwise helpers used by the host-side engine */
 int hba_add_rows(float* dst, int64_t ld_dst, int64_t dst_row_step, const float* src,

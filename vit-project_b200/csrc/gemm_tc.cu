@@ -46,6 +46,7 @@ struct GemmArgs {
   __nv_bfloat16* out_bf16;
   int ld_bf16, out_lo_off;
   int transpose_out;
+  int a_mn, b_mn;  // operand stored MN-major: [K rows, M (resp. N) columns]
 };
 
 // x * sigmoid(1.702 x) on the SFU fast paths (ex2.approx + rcp.approx, ~2 ulp): the epilogue of the
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int num_m_tiles = (g.M + BM - 1) / BM;
   const int num_n_tiles = (g.N + BN - 1) / BN;
   const int total_tiles = num_m_tiles * num_n_tiles;
-  const int kblocks = g.K / BK;
+  const int kblocks = (g.K + BK - 1) / BK;  // a ragged last block is zero-filled by TMA
   const int kiters = kblocks * g.nsplit;
 
   if (warp == 0) {
@@ -270,8 +271,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const int b_col = kb * BK + (s == 2 ? g.b_lo_off : 0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-            tma_load_2d(sA + stage * Cfg::kABytes, &tma_a, &full_bar[stage], a_col, m0);
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], b_col, n0);
+            if (!g.a_mn) {
+              tma_load_2d(sA + stage * Cfg::kABytes, &tma_a, &full_bar[stage], a_col, m0);
+            } else {  // [K, M] storage: BM/64 boxes of 64 k-rows x 64 m-columns, 8 KB apart (LBO)
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sA + stage * Cfg::kABytes + j * 8192, &tma_a, &full_bar[stage],
+                            m0 + 64 * j + (s == 1 ? g.a_lo_off : 0), kb * BK);
+            }
+            if (!g.b_mn) {
+              tma_load_2d(sB + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], b_col, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sB + stage * Cfg::kBBytes + j * 8192, &tma_b, &full_bar[stage],
+                            n0 + 64 * j + (s == 2 ? g.b_lo_off : 0), kb * BK);
+            }
             if (++stage == kStages) stage = 0, phase ^= 1;
           }
         }
@@ -279,7 +294,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_bf16(BM, BN) | (g.a_mn ? (1u << 15) : 0u) |
+                             (g.b_mn ? (1u << 16) : 0u);
+      // K-major: +32 B per 16-element k-step inside the 128-byte swizzle row (start address += 2);
+      // MN-major: 16 k-rows of 128 B further down (start address += 128)
+      const uint32_t a_step = g.a_mn ? 128u : 2u, b_step = g.b_mn ? 128u : 2u;
+      const uint64_t mn_lbo = (uint64_t)(8192 >> 4) << 16;  // next 64-wide MN block of an MN-major tile
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -291,13 +311,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
-          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+          uint64_t a_desc = make_smem_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+          if (g.a_mn) a_desc = (a_desc & ~((uint64_t)0x3FFF << 16)) | mn_lbo;
+          if (g.b_mn) b_desc = (b_desc & ~((uint64_t)0x3FFF << 16)) | mn_lbo;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes (16 bf16) along K inside the 128-byte swizzle atom: start address += 2
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (it == kiters - 1) umma_commit(&tfull_bar[acc]);
           if (++stage == kStages) stage = 0, phase ^= 1;
@@ -357,8 +378,18 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   const uint64_t a_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->a_lo_off : 0);
   const uint64_t b_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
   CUtensorMap ta, tb;
-  HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->M, a_cols, p->lda, BM, BK));
-  HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BN, BK));
+  if (!p->a_mn_major) {
+    HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->M, a_cols, p->lda, BM, BK));
+  } else {
+    const uint64_t cols = (uint64_t)p->M + (p->nsplit == 3 ? (uint64_t)p->a_lo_off : 0);
+    HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->K, cols, p->lda, 64, 64));
+  }
+  if (!p->b_mn_major) {
+    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BN, BK));
+  } else {
+    const uint64_t cols = (uint64_t)p->N + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
+    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->K, cols, p->ldb, 64, 64));
+  }
   const int tiles = ((p->M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
   int ctas = num_sms();
   if (p->max_ctas > 0 && p->max_ctas < ctas) ctas = p->max_ctas;
@@ -375,13 +406,15 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   HBA_REQUIRE(p->A && p->B, "hba_gemm_bf16: null operand");
   HBA_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "hba_gemm_bf16: empty problem M=%d N=%d K=%d",
               p->M, p->N, p->K);
-  HBA_REQUIRE(p->K % BK == 0, "hba_gemm_bf16: K=%d must be a multiple of %d", p->K, BK);
+  // a ragged last k-block is zero-filled by TMA; a split K-major operand must then keep its hi part
+  // zero padded up to the lo part (checked below through the lo offsets)
   HBA_REQUIRE(p->lda % 8 == 0 && p->ldb % 8 == 0, "hba_gemm_bf16: lda/ldb must be multiples of 8");
   HBA_REQUIRE(p->nsplit == 1 || p->nsplit == 3, "hba_gemm_bf16: nsplit must be 1 or 3");
   if (p->nsplit == 3)
-    HBA_REQUIRE(p->a_lo_off >= p->K && p->b_lo_off >= p->K && p->a_lo_off % BK == 0 &&
-                    p->b_lo_off % BK == 0,
-                "hba_gemm_bf16: lo offsets must be >= K and multiples of %d", BK);
+    HBA_REQUIRE(p->a_lo_off >= (p->a_mn_major ? p->M : (p->K + BK - 1) / BK * BK) &&
+                    p->b_lo_off >= (p->b_mn_major ? p->N : (p->K + BK - 1) / BK * BK) && p->a_lo_off % 8 == 0 &&
+                    p->b_lo_off % 8 == 0,
+                "hba_gemm_bf16: lo offsets must lie behind the hi part and be multiples of 8");
   HBA_REQUIRE(p->out_f32 || p->out_bf16 || p->pre_out, "hba_gemm_bf16: no output");
   HBA_REQUIRE(p->act >= HBA_ACT_NONE && p->act <= HBA_ACT_GELU_ERF_GRAD, "hba_gemm_bf16: bad act");
   if (p->act == HBA_ACT_QUICKGELU_GRAD || p->act == HBA_ACT_GELU_ERF_GRAD)
@@ -409,6 +442,7 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   g.out_f32 = p->out_f32, g.ld_f32 = p->ld_f32;
   g.out_bf16 = static_cast<__nv_bfloat16*>(p->out_bf16), g.ld_bf16 = p->ld_bf16;
   g.out_lo_off = p->out_lo_off, g.transpose_out = p->transpose_out;
+  g.a_mn = p->a_mn_major, g.b_mn = p->b_mn_major;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p->N >= 256) return launch_gemm<256>(p, g, s);
   return launch_gemm<128>(p, g, s);

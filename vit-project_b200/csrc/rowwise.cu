@@ -235,6 +235,12 @@ __global__ void __launch_bounds__(256)
     }
   const float rstd = rsqrtf(warp_sum(sq) / width + eps);
   float* o = x_out + row * width;
+  if (gamma == nullptr) {  // no ln_pre (timm ViT): plain token assembly
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i)
+      if (i < nvec) *reinterpret_cast<float4*>(o + (i * 32 + lane) * 4) = v[i];
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i)
     if (i < nvec) {
@@ -366,7 +372,7 @@ extern "C" int hba_assemble_tokens_ln(const float* conv, int32_t B, int32_t n_pa
                                       int32_t width, const float* cls, const float* pos,
                                       const float* gamma, const float* beta, float eps,
                                       float* x_out, void* stream) {
-  HBA_REQUIRE(conv && cls && pos && gamma && beta && x_out && B > 0, "hba_assemble_tokens_ln: bad arguments");
+  HBA_REQUIRE(conv && cls && pos && x_out && B > 0 && (!gamma == !beta), "hba_assemble_tokens_ln: bad arguments");
   HBA_REQUIRE(width % 128 == 0 && width <= 128 * kLnMaxVec, "hba_assemble_tokens_ln: width=%d unsupported", width);
   const int64_t rows = (int64_t)B * (n_patches + 1);
   assemble_tokens_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -32,6 +32,7 @@ class GemmParams(C.Structure):
         ("out_f32", vp), ("ld_f32", i32),
         ("out_bf16", vp), ("ld_bf16", i32), ("out_lo_off", i32),
         ("transpose_out", i32), ("max_ctas", i32),
+        ("a_mn_major", i32), ("b_mn_major", i32),
     ]
 
 
@@ -62,6 +63,9 @@ SIGNATURES = {
     "hba_rank_avg_f64": (i32, [vp, i64, vp, vp, i64, vp]),
     "hba_pearson_f64": (i32, [vp, vp, i64, vp, vp, vp]),
     "hba_softmax_ce_fwd_bwd": (i32, [vp, i64, vp, i32, i32, vp, vp, i64, vp, vp, vp]),
+    "hba_colsum": (i32, [vp, i32, i64, i32, i64, vp, i32, vp, vp]),
+    "hba_layernorm_param_grad": (i32, [vp, i64, vp, i64, i32, i64, i64, f32, vp, i32, vp, vp]),
+    "hba_attention_bwd": (i32, [vp, i32, i64, i32, i32, i32, i32, vp, i32, i64, vp, i32, i64, vp]),
     "hba_add_rows": (i32, [vp, i64, i64, vp, i64, i64, i32, vp]),
     "hba_nonfinite_flag": (i32, [vp, i64, vp, vp]),
 }

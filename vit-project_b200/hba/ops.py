@@ -77,11 +77,21 @@ class Operand:
 
 def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_ACT_NONE, aux=None,
          pre_out=None, out_f32=None, out: Operand = None, transpose_out=False, alpha=1.0,
-         max_ctas=0):
-    """C[M,N] = epilogue(A . B^T) on the tcgen05 tensor pipe (hba_gemm_bf16)."""
-    M = a.rows if M is None else M
-    N, K = b.rows, b.K
-    assert a.K == K, (a.K, K)
+         max_ctas=0, a_mn=False, b_mn=False, K=None):
+    """C[M,N] = epilogue(A . B^T) on the tcgen05 tensor pipe (hba_gemm_bf16).
+    a_mn / b_mn: the operand is stored MN-major, i.e. as [K rows, M resp. N columns] (its Operand
+    then has rows = K and K = M resp. N)."""
+    if a_mn:
+        Ka, M = a.rows, (a.K if M is None else M)
+    else:
+        Ka, M = a.K, (a.rows if M is None else M)
+    Kb, N = (b.rows, b.K) if b_mn else (b.K, b.rows)
+    K = min(Ka, Kb) if K is None else K
+    assert K <= Ka and K <= Kb, (K, Ka, Kb)
+    if K % 64 and a.lo_off > 0 and b.lo_off > 0:
+        # ragged K in fp32 mode: a K-major operand must be zero padded up to its lo part
+        assert a_mn or a.lo_off >= (K + 63) // 64 * 64, "A needs zero padding up to a multiple of 64"
+        assert b_mn or b.lo_off >= (K + 63) // 64 * 64, "B needs zero padding up to a multiple of 64"
     split = a.lo_off > 0 and b.lo_off > 0
     p = GemmParams()
     p.A, p.B = a.buf.data_ptr(), b.buf.data_ptr()
@@ -104,6 +114,7 @@ def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_AC
         p.out_bf16, p.ld_bf16, p.out_lo_off = out.buf.data_ptr(), out.ld, out.lo_off
     p.transpose_out = 1 if transpose_out else 0
     p.max_ctas = max_ctas
+    p.a_mn_major, p.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -251,6 +262,24 @@ def softmax_ce(logits, labels, loss, d_logits, correct, workspace):
                                              d_logits.stride(0) if d_logits is not None else 0,
                                              _p(correct), _p(workspace), _stream()),
           "hba_softmax_ce_fwd_bwd")
+
+
+def colsum(x, out, workspace, accumulate=False):
+    rows, cols = x.shape
+    check(_lib.load().hba_colsum(_p(x), _dt(x), rows, cols, x.stride(0), _p(out), 1 if accumulate else 0,
+                                 _p(workspace), _stream()), "hba_colsum", 2)
+
+
+def layernorm_param_grad(dy, x, rows, cols, eps, dgamma_dbeta, workspace, *, row_step=1, accumulate=False):
+    check(_lib.load().hba_layernorm_param_grad(_p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0),
+                                               row_step, eps, _p(dgamma_dbeta), 1 if accumulate else 0,
+                                               _p(workspace), _stream()), "hba_layernorm_param_grad", 3)
+
+
+def attention_bwd(qkv, B, T, H, d_out, d_qkv, causal=False):
+    check(_lib.load().hba_attention_bwd(_p(qkv), _dt(qkv), qkv.stride(0), B, T, H, 1 if causal else 0,
+                                        _p(d_out), _dt(d_out), d_out.stride(0), _p(d_qkv), _dt(d_qkv),
+                                        d_qkv.stride(0), _stream()), "hba_attention_bwd")
 
 
 def add_rows(dst, src, rows, cols, dst_row_step=1):

@@ -1,0 +1,483 @@
+"""ViT-B/16 classification baseline on libhba (north star item 4; reference VIT = Training/
+vit_training/baseline/train_vit_sgd.py: `timm.create_model('vit_base_patch16_224', num_classes=1000)`
+VIT:283, fp16-autocast forward + cross-entropy VIT:138-140, SGD VIT:294-299, DDP VIT:287).
+
+`VisionTransformer` carries timm's parameter names (patch_embed.proj, cls_token, pos_embed,
+blocks.N.{norm1,attn.qkv,attn.proj,norm2,mlp.fc1,mlp.fc2}, norm, head) and holds parameters only;
+`ViTEngine` sequences the C-ABI kernels for the forward and the FULL backward (every parameter gets a
+gradient).  Layout tricks that remove every transpose pass:
+    y  = x W^T      A = x   (K-major)           B = W [out, in]  (K-major)
+    dX = dY W       A = dY  (K-major)           B = W [out, in]  read MN-major   (same bf16 copy)
+    dW = dY^T X     A = dY  read MN-major       B = X            read MN-major
+Data parallelism (`DataParallelTrainer`): one process per GPU; the gradients of a block are all-reduced
+over NCCL (async, bucket = block) while the previous block's backward is still running; 1/world is
+folded into the loss gradient; fused multi-tensor SGD afterwards.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from . import ops
+from .ops import (HBA_ACT_GELU_ERF, HBA_ACT_GELU_ERF_GRAD, Operand)
+
+LN_EPS = 1e-6
+
+
+def _no_torch_path(name):
+    raise NotImplementedError(f"{name}: parameters only; the forward runs in hba.vit.ViTEngine (sm_100a)")
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.num_heads = heads
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        _no_torch_path("Attention")
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        _no_torch_path("Mlp")
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.attn = _Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        _no_torch_path("Block")
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(3, dim, patch, patch)
+
+    def forward(self, x):
+        _no_torch_path("PatchEmbed")
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0,
+                 num_classes=1000):
+        super().__init__()
+        if embed_dim // num_heads != 64:
+            raise ValueError("libhba attention kernels need head_dim 64")
+        self.img_size, self.patch_size, self.embed_dim, self.num_classes = img_size, patch_size, embed_dim, num_classes
+        self.patch_embed = _PatchEmbed(patch_size, embed_dim)
+        n_tok = (img_size // patch_size) ** 2 + 1
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, n_tok, embed_dim) * 0.02)
+        self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=LN_EPS)
+        self.head = nn.Linear(embed_dim, num_classes)
+        nn.init.normal_(self.cls_token, std=1e-6)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        """[B,3,H,W] -> logits [B, num_classes] (fp32), differentiable w.r.t. every parameter."""
+        if not x.is_cuda:
+            raise RuntimeError("hba.vit has no CPU path: move the model and the images to a CUDA device")
+        eng = get_engine(self)
+        params = eng.param_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _VitForward.apply(eng, x, *params)
+        with torch.no_grad():
+            return eng.forward(x, save=False).clone()
+
+
+def create_model(name="vit_base_patch16_224", pretrained=False, num_classes=1000, **kw):
+    """timm.create_model stand-in for the one architecture the reference trains (VIT:283)."""
+    if pretrained:
+        raise NotImplementedError("no network: pretrained timm weights are not available")
+    cfgs = {"vit_base_patch16_224": dict(embed_dim=768, depth=12, num_heads=12),
+            "vit_tiny_test": dict(embed_dim=128, depth=2, num_heads=2)}
+    if name not in cfgs:
+        raise NotImplementedError(f"hba.vit covers {sorted(cfgs)}; got {name}")
+    return VisionTransformer(num_classes=num_classes, **cfgs[name], **kw)
+
+
+def get_engine(model) -> "ViTEngine":
+    eng = model.__dict__.get("_hba_vit_engine")
+    if eng is None:
+        eng = ViTEngine(model)
+        model.__dict__["_hba_vit_engine"] = eng
+    return eng
+
+
+class ViTEngine:
+    def __init__(self, model):
+        self.m = model
+        self._bufs = {}
+        self.device = None
+        self.precision = None
+        self._params = None
+        self._wops = {}
+        self._saved_B = None
+        self.flat_grad = None
+        self.block_grad_slices = None
+
+    # ------------------------------------------------------------------ parameters / staging
+    @property
+    def split(self):
+        return self.precision == "fp32"
+
+    def param_list(self):
+        if self._params is None:
+            self._params = list(self.m.parameters())
+        return self._params
+
+    def _buf(self, name, shape, dtype=torch.float32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _opbuf(self, name, rows, K, zero=False):
+        width = 2 * K if self.split else K
+        return Operand(self._buf(name, (rows, width), torch.bfloat16, zero=zero), rows, K,
+                       K if self.split else 0)
+
+    def _setup(self, device):
+        prec = _engine.get_precision()
+        if self.device != device or self.precision != prec:
+            self.device, self.precision = device, prec
+            self._bufs.clear()
+            self._wops.clear()
+            self._grads_for = None
+
+    def stage_weights(self):
+        """bf16 (hi[/lo]) operands of every weight matrix, refreshed from the fp32 masters."""
+        m = self.m
+        mats = {"conv": m.patch_embed.proj.weight.detach().reshape(m.embed_dim, -1), "head": m.head.weight.detach()}
+        for i, blk in enumerate(m.blocks):
+            mats[f"{i}.qkv"], mats[f"{i}.proj"] = blk.attn.qkv.weight.detach(), blk.attn.proj.weight.detach()
+            mats[f"{i}.fc1"], mats[f"{i}.fc2"] = blk.mlp.fc1.weight.detach(), blk.mlp.fc2.weight.detach()
+        for k, w in mats.items():
+            op = self._wops.get(k)
+            if op is None:
+                op = Operand.empty(w.shape[0], w.shape[1], self.split, self.device)
+                self._wops[k] = op
+            ops.split_bf16(w if w.is_contiguous() else w.contiguous(), op)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, images, save=True):
+        m = self.m
+        self._setup(images.device)
+        self.stage_weights()
+        B, P, d, H = images.shape[0], m.patch_size, m.embed_dim, m.blocks[0].attn.num_heads
+        grid = images.shape[2] // P
+        if images.shape[2] != m.img_size or images.shape[3] != m.img_size:
+            raise RuntimeError("hba.vit: images must have the model's resolution")
+        npatch, T = grid * grid, grid * grid + 1
+        M = B * T
+        sp = self.split
+        adt = torch.float32 if sp else torch.bfloat16
+        images = images.contiguous().float()
+        kconv = 3 * P * P
+        patches = self._opbuf("patches", B * npatch, kconv)
+        ops.im2col_patches(images, P, patches)
+        conv = self._buf("conv", (B * npatch, d))
+        ops.gemm(patches, self._wops["conv"], B * npatch, bias=m.patch_embed.proj.bias.detach(), out_f32=conv)
+        x = self._buf("x0", (M, d))
+        ops.assemble_tokens_ln(conv, B, npatch, d, m.cls_token.detach().reshape(d),
+                               m.pos_embed.detach().reshape(T, d), None, None, LN_EPS, x)
+        for i, blk in enumerate(m.blocks):
+            tag = f"b{i}." if save else "tmp."
+            ln1 = self._opbuf(tag + "ln1", M, d)
+            ops.layernorm_fwd(x, M, d, blk.norm1.weight.detach(), blk.norm1.bias.detach(), LN_EPS, y=ln1)
+            qkv = self._buf(tag + "qkv", (M, 3 * d), adt)
+            if sp:
+                ops.gemm(ln1, self._wops[f"{i}.qkv"], M, bias=blk.attn.qkv.bias.detach(), out_f32=qkv)
+            else:
+                ops.gemm(ln1, self._wops[f"{i}.qkv"], M, bias=blk.attn.qkv.bias.detach(),
+                         out=Operand(qkv, M, 3 * d, 0))
+            att = self._opbuf(tag + "att", M, d)
+            ops.attention_fwd(qkv, B, T, H, out=att)
+            x_mid = self._buf(tag + "xmid", (M, d))
+            ops.gemm(att, self._wops[f"{i}.proj"], M, bias=blk.attn.proj.bias.detach(), residual=x, out_f32=x_mid)
+            ln2 = self._opbuf(tag + "ln2", M, d)
+            ops.layernorm_fwd(x_mid, M, d, blk.norm2.weight.detach(), blk.norm2.bias.detach(), LN_EPS, y=ln2)
+            hid = self._opbuf(tag + "hid", M, 4 * d)
+            pre = self._buf(tag + "pre", (M, 4 * d), adt) if save else None
+            ops.gemm(ln2, self._wops[f"{i}.fc1"], M, bias=blk.mlp.fc1.bias.detach(), act=HBA_ACT_GELU_ERF,
+                     out=hid, pre_out=pre)
+            x_out = self._buf(tag + "xout", (M, d))
+            ops.gemm(hid, self._wops[f"{i}.fc2"], M, bias=blk.mlp.fc2.bias.detach(), residual=x_mid, out_f32=x_out)
+            x = x_out
+        cls_n = self._opbuf("clsn", max(B, 128), d, zero=True)
+        ops.layernorm_fwd(x, B, d, m.norm.weight.detach(), m.norm.bias.detach(), LN_EPS, row_step=T, y=cls_n)
+        logits = self._buf("logits", (B, m.num_classes))
+        ops.gemm(cls_n, self._wops["head"], B, bias=m.head.bias.detach(), out_f32=logits)
+        if save:
+            self._saved_B = B
+            self._x_last = x
+        return logits
+
+    # ------------------------------------------------------------------ backward
+    def _ensure_grads(self):
+        """One flat fp32 gradient buffer; parameters are ordered so that every transformer block's
+        gradients are contiguous (one all-reduce bucket per block)."""
+        if self.flat_grad is not None and self.flat_grad.device == self.device:
+            return
+        m = self.m
+        groups = [("head", [m.norm.weight, m.norm.bias, m.head.weight, m.head.bias])]
+        for i in reversed(range(len(m.blocks))):
+            groups.append((f"block{i}", list(m.blocks[i].parameters())))
+        groups.append(("embed", [m.cls_token, m.pos_embed, m.patch_embed.proj.weight, m.patch_embed.proj.bias]))
+        pad4 = lambda n: (n + 3) // 4 * 4  # every gradient starts 16-byte aligned (GEMM epilogue stores)
+        total = sum(pad4(p.numel()) for _, ps in groups for p in ps)
+        self.flat_grad = torch.zeros(total, device=self.device)
+        self.grad_of, self.bucket_slices = {}, []
+        off = 0
+        for name, ps in groups:
+            start = off
+            for p in ps:
+                self.grad_of[id(p)] = self.flat_grad[off:off + p.numel()].view_as(p)
+                off += pad4(p.numel())
+            self.bucket_slices.append((name, start, off))
+
+    def backward(self, d_logits, on_bucket_ready=None):
+        """Fills the flat gradient buffer (bucket by bucket, calling `on_bucket_ready(name, flat_slice)`
+        as soon as a bucket is complete) from dL/dlogits [B, num_classes] fp32."""
+        m = self.m
+        self._ensure_grads()
+        G = lambda p: self.grad_of[id(p)]
+        B = self._saved_B
+        d, H, P = m.embed_dim, m.blocks[0].attn.num_heads, m.patch_size
+        T = (m.img_size // P) ** 2 + 1
+        npatch = T - 1
+        M, C = B * T, m.num_classes
+        sp = self.split
+        adt = torch.float32 if sp else torch.bfloat16
+        cs_ws = self._buf("cs_ws", (128 * max(4 * d, C, T * d) + 64,))
+        ln_ws = self._buf("ln_ws", (2 * M + 256 * d + 64,))
+        buckets = {n: (s, e) for n, s, e in self.bucket_slices}
+
+        def ready(name):
+            if on_bucket_ready is not None:
+                s, e = buckets[name]
+                on_bucket_ready(name, self.flat_grad[s:e])
+
+        # ---- head
+        Cp = (C + 63) // 64 * 64
+        g_log = self._opbuf("g_log", max(B, 128), Cp, zero=True)
+        ops.split_bf16(d_logits, Operand(g_log.buf, B, Cp, g_log.lo_off))
+        cls_n = self._opbuf("clsn", max(B, 128), d, zero=True)
+        # dW_head[c, k] = sum_b g[b, c] cls_n[b, k]  (both operands read MN-major, K = B)
+        ops.gemm(Operand(g_log.buf, B, C, g_log.lo_off), Operand(cls_n.buf, B, d, cls_n.lo_off),
+                 a_mn=True, b_mn=True, K=B, out_f32=G(m.head.weight))
+        ops.colsum(d_logits, G(m.head.bias), cs_ws)
+        d_cn = self._buf("d_cn", (B, d))
+        ops.gemm(g_log, self._wops["head"], B, b_mn=True, K=C, out_f32=d_cn)   # ragged K: TMA zero-fill
+        x = self._x_last
+        dgb = self._buf("dgb", (2 * d,))
+        ops.layernorm_param_grad(d_cn, x, B, d, LN_EPS, dgb, ln_ws, row_step=T)
+        G(m.norm.weight).copy_(dgb[:d])
+        G(m.norm.bias).copy_(dgb[d:])
+        dx = self._buf("dx", (M, d))
+        dx.zero_()
+        dx_cls = self._buf("dx_cls", (B, d))
+        ops.layernorm_bwd(d_cn, x, B, d, m.norm.weight.detach(), LN_EPS, dx_cls, row_step=T)
+        ops.add_rows(dx, dx_cls, B, d, dst_row_step=T)
+        ready("head")
+        # ---- blocks, last to first
+        for i in reversed(range(len(m.blocks))):
+            blk, tag = m.blocks[i], f"b{i}."
+            x_in = self._buf(f"b{i - 1}.xout", (M, d)) if i > 0 else self._buf("x0", (M, d))
+            x_mid, pre = self._buf(tag + "xmid", (M, d)), self._buf(tag + "pre", (M, 4 * d), adt)
+            ln1, ln2 = self._opbuf(tag + "ln1", M, d), self._opbuf(tag + "ln2", M, d)
+            att, hid = self._opbuf(tag + "att", M, d), self._opbuf(tag + "hid", M, 4 * d)
+            qkv = self._buf(tag + "qkv", (M, 3 * d), adt)
+            # fc2
+            gy = self._opbuf("gy", M, d)
+            ops.split_bf16(dx, gy)
+            ops.gemm(gy, hid, a_mn=True, b_mn=True, K=M, out_f32=G(blk.mlp.fc2.weight))
+            ops.colsum(dx, G(blk.mlp.fc2.bias), cs_ws)
+            g_hid = self._opbuf("g_hid", M, 4 * d)
+            g_hid_f = self._buf("g_hid_f", (M, 4 * d)) if sp else None
+            ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
+                     out_f32=g_hid_f)
+            # fc1
+            ops.gemm(g_hid, ln2, a_mn=True, b_mn=True, K=M, out_f32=G(blk.mlp.fc1.weight))
+            ops.colsum(g_hid_f if sp else g_hid.buf, G(blk.mlp.fc1.bias), cs_ws)
+            d_ln = self._buf("d_ln", (M, d))
+            ops.gemm(g_hid, self._wops[f"{i}.fc1"], M, b_mn=True, out_f32=d_ln)
+            ops.layernorm_param_grad(d_ln, x_mid, M, d, LN_EPS, dgb, ln_ws)
+            G(blk.norm2.weight).copy_(dgb[:d])
+            G(blk.norm2.bias).copy_(dgb[d:])
+            ops.layernorm_bwd(d_ln, x_mid, M, d, blk.norm2.weight.detach(), LN_EPS, dx, accumulate=True)
+            # attention projection
+            ops.split_bf16(dx, gy)
+            ops.gemm(gy, att, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.proj.weight))
+            ops.colsum(dx, G(blk.attn.proj.bias), cs_ws)
+            if sp:
+                d_att = self._buf("d_att_f", (M, d))
+                ops.gemm(gy, self._wops[f"{i}.proj"], M, b_mn=True, out_f32=d_att)
+                d_qkv = self._buf("d_qkv_f", (M, 3 * d))
+                ops.attention_bwd(qkv, B, T, H, d_att, d_qkv)
+                g_qkv = self._opbuf("g_qkv", M, 3 * d)
+                ops.split_bf16(d_qkv, g_qkv)
+                ops.colsum(d_qkv, G(blk.attn.qkv.bias), cs_ws)
+            else:
+                d_att = self._buf("d_att", (M, d), torch.bfloat16)
+                ops.gemm(gy, self._wops[f"{i}.proj"], M, b_mn=True, out=Operand(d_att, M, d, 0))
+                g_qkv = self._opbuf("g_qkv", M, 3 * d)
+                ops.attention_bwd(qkv, B, T, H, d_att, g_qkv.buf)
+                ops.colsum(g_qkv.buf, G(blk.attn.qkv.bias), cs_ws)
+            ops.gemm(g_qkv, ln1, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.qkv.weight))
+            ops.gemm(g_qkv, self._wops[f"{i}.qkv"], M, b_mn=True, out_f32=d_ln)
+            ops.layernorm_param_grad(d_ln, x_in, M, d, LN_EPS, dgb, ln_ws)
+            G(blk.norm1.weight).copy_(dgb[:d])
+            G(blk.norm1.bias).copy_(dgb[d:])
+            ops.layernorm_bwd(d_ln, x_in, M, d, blk.norm1.weight.detach(), LN_EPS, dx, accumulate=True)
+            ready(f"block{i}")
+        # ---- embedding: pos / cls / patch projection
+        pos_g = G(m.pos_embed).view(T * d)
+        ops.colsum(dx.view(B, T * d), pos_g, cs_ws)
+        G(m.cls_token).view(d).copy_(pos_g[:d])
+        d_patch = dx.view(B, T, d)[:, 1:, :].reshape(B * npatch, d)
+        gp = self._opbuf("gp", B * npatch, d)
+        ops.split_bf16(d_patch, gp)
+        patches = self._opbuf("patches", B * npatch, 3 * P * P)
+        ops.gemm(gp, patches, a_mn=True, b_mn=True, K=B * npatch,
+                 out_f32=G(m.patch_embed.proj.weight).view(d, 3 * P * P))
+        ops.colsum(d_patch, G(m.patch_embed.proj.bias), cs_ws)
+        ready("embed")
+        return self.flat_grad
+
+
+class _VitForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, images, *params):
+        logits = eng.forward(images, save=True)
+        ctx.eng, ctx.n = eng, len(params)
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        eng = ctx.eng
+        eng.backward(d_logits.contiguous().float())
+        grads = [eng.grad_of[id(p)].clone() if p.requires_grad else None for p in eng.param_list()]
+        return (None, None, *grads)
+
+
+class CosineAnnealingLRWithWarmup:
+    """Per-epoch schedule of VIT:206-244: linear warm-up (e+1)/warmup, then cosine to eta_min; stepped
+    once per epoch after training (VIT:352)."""
+
+    def __init__(self, optimizer, warmup_epochs, max_epochs, eta_min=0):
+        self.optimizer, self.warmup_epochs, self.max_epochs, self.eta_min = optimizer, warmup_epochs, max_epochs, eta_min
+        self.base_lrs = [g["lr"] for g in optimizer.param_groups]
+        self.current_epoch = 0
+
+    def step(self):
+        e = self.current_epoch
+        for group, base in zip(self.optimizer.param_groups, self.base_lrs):
+            if e < self.warmup_epochs:
+                group["lr"] = base * (e + 1) / self.warmup_epochs
+            else:
+                prog = (e - self.warmup_epochs) / (self.max_epochs - self.warmup_epochs)
+                group["lr"] = self.eta_min + (base - self.eta_min) * 0.5 * (1 + math.cos(math.pi * prog))
+        self.current_epoch += 1
+
+    def state_dict(self):
+        return {"current_epoch": self.current_epoch, "base_lrs": self.base_lrs, "warmup_epochs": self.warmup_epochs,
+                "max_epochs": self.max_epochs, "eta_min": self.eta_min}
+
+    def load_state_dict(self, sd):
+        self.current_epoch, self.base_lrs = sd["current_epoch"], sd["base_lrs"]
+        self.warmup_epochs, self.max_epochs, self.eta_min = sd["warmup_epochs"], sd["max_epochs"], sd["eta_min"]
+
+
+class DataParallelTrainer:
+    """Fused data-parallel training step (replaces DDP + autocast + GradScaler + SGD of VIT:132-152):
+    forward -> fused softmax-CE (mean over the GLOBAL batch: 1/world folded into the gradient) ->
+    backward with one async NCCL all-reduce per block bucket, overlapped with the remaining backward
+    -> fused multi-tensor SGD.  Works without a process group (world size 1)."""
+
+    def __init__(self, model, lr=0.1, momentum=0.9, weight_decay=1e-4, process_group=None):
+        import torch.distributed as dist
+        self.model, self.eng = model, get_engine(model)
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.group = process_group
+        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        self.lr, self.momentum, self.wd = lr, momentum, weight_decay
+        self.param_groups = [{"lr": lr}]  # so that CosineAnnealingLRWithWarmup can drive it
+        self._mom = None
+        self._first = True
+        self._table = None
+
+    def broadcast_parameters(self):
+        if self.dist:
+            for p in self.model.parameters():
+                self.dist.broadcast(p.data, src=0, group=self.group)
+
+    def step(self, images, labels):
+        eng, m = self.eng, self.model
+        logits = eng.forward(images, save=True)
+        B, C = logits.shape
+        dev = logits.device
+        loss = eng._buf("loss", (1,))
+        d_logits = eng._buf("d_logits", (B, C))
+        hits = eng._buf("hits", (1,), torch.int32)
+        ops.softmax_ce(logits, labels, loss, d_logits, hits, eng._buf("ce_ws", (2 * B,)))
+        if self.world > 1:
+            d_logits.mul_(1.0 / self.world)
+        handles = []
+
+        def on_ready(name, flat):
+            if self.dist:
+                handles.append(self.dist.all_reduce(flat, group=self.group, async_op=True))
+
+        eng.backward(d_logits, on_bucket_ready=on_ready)
+        for h in handles:
+            h.wait()
+        self._sgd()
+        return loss, hits
+
+    def _sgd(self):
+        eng = self.eng
+        if self._mom is None:
+            self._mom = torch.zeros_like(eng.flat_grad)
+            ps = eng.param_list()
+            for p in ps:
+                if not (p.is_contiguous() and p.dtype == torch.float32):
+                    raise RuntimeError("hba.vit: parameters must be contiguous fp32")
+            flat = []
+            off = {id(p): None for p in ps}
+            # momentum buffers mirror the flat gradient layout
+            base_g, base_m = eng.flat_grad.data_ptr(), self._mom.data_ptr()
+            for p in ps:
+                g = eng.grad_of[id(p)]
+                delta = g.data_ptr() - base_g
+                flat += [p.data_ptr(), g.data_ptr(), base_m + delta]
+            self._table = (torch.tensor(flat, dtype=torch.int64, device=eng.device),
+                           torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=eng.device),
+                           len(ps), sum(p.numel() for p in ps))
+        table, sizes, n, total = self._table
+        ops.sgd_multi(table, sizes, n, total, float(self.param_groups[0]["lr"]), self.momentum, self.wd,
+                      self._first)
+        self._first = False
