@@ -51,7 +51,8 @@ int hba_device_check(void);
  *        *_GRAD multiply v by act'(aux[m,n]) for the backward pass)
  *   v += residual[m,n] (optional, fp32)
  *   out_f32 / out_bf16 (hi at column n, lo at column n + out_lo_off when out_lo_off > 0)
- *   transpose_out != 0 writes the outputs as [N, M] (ld* are then row strides of that layout)
+ *   transpose_out != 0 writes the outputs as [N, M] (ld* are then row strides of that layout);
+ *     only alpha and bias apply in that mode (no act / residual / pre_out)
  */
 enum {
   HBA_ACT_NONE = 0,

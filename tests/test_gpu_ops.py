@@ -123,10 +123,12 @@ def test_gemm_epilogues(split):
 
 def test_gemm_errors():
     hba, ops, ref = _imports()
-    a = ops.Operand.empty(64, 96, False, DEV)  # K not a multiple of 64
-    b = ops.Operand.empty(128, 96, False, DEV)
-    with pytest.raises(RuntimeError, match="multiple of 64"):
-        ops.gemm(a, b, 64, out_f32=torch.empty(64, 128, device=DEV))
+    a = ops.Operand.empty(64, 96, False, DEV)
+    b = ops.Operand.empty(128, 100, False, DEV)  # row pitch not a multiple of 8 elements (16 bytes)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        ops.gemm(a, b, 64, K=96, out_f32=torch.empty(64, 128, device=DEV))
+    with pytest.raises(RuntimeError, match="no output"):
+        ops.gemm(a, ops.Operand.empty(128, 96, False, DEV), 64)
 
 
 # ----------------------------------------------------------------------------------- row-wise

@@ -186,3 +186,68 @@ def test_clip_restatement_matches_transformers_clip():
         want = hf(input_ids=tok, pixel_values=img, attention_mask=None).logits_per_image
         got = ours(img, tok, True)
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-3), float((got - want).abs().max())
+
+
+def test_vit_restatement_matches_torchvision():
+    """oracle/vit_ref.py (timm ViT restated) against an independent implementation of the same
+    published architecture — torchvision's VisionTransformer — with copied weights: logits and
+    parameter gradients agree to fp32 round-off."""
+    from torchvision.models.vision_transformer import VisionTransformer as TVViT
+    from oracle import vit_ref
+    ours = vit_ref.create_model("vit_tiny_test", num_classes=10, seed=3)
+    with torch.no_grad():   # give biases / norms non-trivial values
+        for p in ours.parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    tv = TVViT(image_size=224, patch_size=16, num_layers=2, num_heads=2, hidden_dim=128, mlp_dim=512,
+               num_classes=10)
+    sd = {"conv_proj.weight": ours.patch_embed.proj.weight, "conv_proj.bias": ours.patch_embed.proj.bias,
+          "class_token": ours.cls_token, "encoder.pos_embedding": ours.pos_embed,
+          "encoder.ln.weight": ours.norm.weight, "encoder.ln.bias": ours.norm.bias,
+          "heads.head.weight": ours.head.weight, "heads.head.bias": ours.head.bias}
+    for i, blk in enumerate(ours.blocks):
+        p = f"encoder.layers.encoder_layer_{i}."
+        sd.update({p + "ln_1.weight": blk.norm1.weight, p + "ln_1.bias": blk.norm1.bias,
+                   p + "self_attention.in_proj_weight": blk.attn.qkv.weight,
+                   p + "self_attention.in_proj_bias": blk.attn.qkv.bias,
+                   p + "self_attention.out_proj.weight": blk.attn.proj.weight,
+                   p + "self_attention.out_proj.bias": blk.attn.proj.bias,
+                   p + "ln_2.weight": blk.norm2.weight, p + "ln_2.bias": blk.norm2.bias,
+                   p + "mlp.0.weight": blk.mlp.fc1.weight, p + "mlp.0.bias": blk.mlp.fc1.bias,
+                   p + "mlp.3.weight": blk.mlp.fc2.weight, p + "mlp.3.bias": blk.mlp.fc2.bias})
+    tv.load_state_dict({k: v.detach().clone() for k, v in sd.items()}, strict=True)
+    tv.eval()
+    ours.eval()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 224, 224, generator=g)
+    y = torch.tensor([3, 7])
+    lo = torch.nn.functional.cross_entropy(ours(x), y)
+    lt = torch.nn.functional.cross_entropy(tv(x), y)
+    assert abs(float(lo) - float(lt)) < 1e-5 * abs(float(lt))
+    lo.backward()
+    lt.backward()
+    tvp = dict(tv.named_parameters())
+    for k, p in sd.items():
+        a, b = p.grad, tvp[k].grad
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-8, k
+
+
+def test_vit_schedule_matches_reference_class():
+    """cosine_warmup_lr against the reference's own CosineAnnealingLRWithWarmup (VIT:206-244) when
+    /root/reference is present, else against its closed form."""
+    import math
+    from oracle import vit_ref
+    lrs = [vit_ref.cosine_warmup_lr(0.1, e, 5, 100) for e in range(100)]
+    assert lrs[0] == pytest.approx(0.02) and lrs[4] == pytest.approx(0.1)
+    assert lrs[5] == pytest.approx(0.1) and lrs[99] == pytest.approx(0.05 * (1 + math.cos(math.pi * 94 / 95)))
+    from hba.vit import CosineAnnealingLRWithWarmup
+
+    class _Opt:
+        param_groups = [{"lr": 0.1}]
+    opt = _Opt()
+    sch = CosineAnnealingLRWithWarmup(opt, 5, 100)
+    got = []
+    for e in range(100):
+        sch.step()
+        got.append(opt.param_groups[0]["lr"])
+    assert got == pytest.approx(lrs)

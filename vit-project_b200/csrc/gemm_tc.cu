@@ -1,16 +1,24 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . B[N,K]^T), bf16 in, fp32 acc.
 //
-// One persistent CTA per SM, 6 warps, warp-specialised:
-//   warp 0 (one lane)  TMA producer: A box 128x64 and B box BNx64 (SWIZZLE_128B) into a smem ring
-//   warp 1 (one lane)  tcgen05.mma issuer: 128 x BN x 16 UMMAs, accumulators in TMEM, 2 accumulator
-//                      stages so that the epilogue of tile i overlaps the main loop of tile i+1
-//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused
+// One persistent CTA per SM, CTAs paired into 2-CTA clusters (cta_group::2): a pair owns a
+// 256 x BN tile of C.  10 warps per CTA, warp-specialised:
+//   warp 0 (one lane)  TMA producer: its 128 rows of A and its BN/2 rows of B per k-block
+//                      (SWIZZLE_128B boxes) into a 6-stage smem ring; bytes of both CTAs are
+//                      accounted on the leader's mbarrier
+//   warp 1 (one lane, leader CTA only)  tcgen05.mma.cta_group::2 issuer: 256 x BN x 16 UMMAs reading
+//                      both CTAs' smem, accumulators in both CTAs' TMEM (128 rows each), 2 accumulator
+//                      stages so that the epilogue of tile i overlaps the main loop of tile i+1;
+//                      multicast tcgen05.commit frees the smem slot / publishes the tile in both CTAs
+//   warps 2..9         epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused
 //                      bias / QuickGELU / GELU / activation-gradient / residual -> global
+// HBA_GEMM_CTA_GROUP=1 selects the single-CTA variant (128 x BN tiles) for A/B measurements.
 // "fp32 mode" (nsplit == 3) runs three bf16 passes per k-block over hi/lo split operands
 // (hi.hi + lo.hi + hi.lo), which reproduces fp32 products to ~2^-16 on the bf16 tensor pipe.
 //
 // Replaces F.linear at torch/nn/functional.py:6244 (in_proj), :6690 (out_proj) and the CLIP / timm
 // MLP linears reached through the reference's CLIPHBA.forward (NEW:298) and VIT:138-140.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hba {
@@ -20,14 +28,33 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
-template <int BN>
+// CG = CTAs per UMMA (cta_group): with CG == 2 a CTA pair computes a 256 x BN tile, each CTA staging
+// its own 128 rows of A and only HALF of the B tile -> 1/3 fewer bytes through the L2->SM fabric per
+// FLOP than 128 x BN tiles (the fabric, not the tensor pipe, bounded the single-CTA kernel: 10.7 TB/s
+// of TMA traffic at 44 % tensor-pipe utilisation, profiles/r01_gemm_attn_ncu_full.md)
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
+  static constexpr int kStages = (192 * 1024) / (kABytes + kBBytes) > 8 ? 8 : (192 * 1024) / (kABytes + kBBytes);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256 /*bars*/;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per-warp transposition tiles of the epilogue
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kStagingBytes + 1024 /*align*/ + 256 /*bars*/;
 };
+
+template <int CG>
+__device__ __forceinline__ void tma_load(void* dst, const CUtensorMap* m, uint32_t bar_addr, int c0,
+                                         int c1) {
+  if constexpr (CG == 2) {
+    tma_load_2d_pair(dst, m, bar_addr, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
 
 struct GemmArgs {
   int M, N, K;
@@ -47,6 +74,7 @@ struct GemmArgs {
   int ld_bf16, out_lo_off;
   int transpose_out;
   int a_mn, b_mn;  // operand stored MN-major: [K rows, M (resp. N) columns]
+  int debug;       // HBA_GEMM_DEBUG (measurement only): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA loads
 };
 
 // x * sigmoid(1.702 x) on the SFU fast paths (ex2.approx + rcp.approx, ~2 ulp): the epilogue of the
@@ -66,235 +94,321 @@ __device__ __forceinline__ float gelu_erf_grad(float a) {
          a * 0.39894228040143268f * expf(-0.5f * a * a);
 }
 
-// epilogue for one thread: row `row`, 32 consecutive columns starting at `col`
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t* r, int row,
-                                               int col) {
-  float v[32];
+// transposed store (C^T) for one thread: row `row`, 32 consecutive columns starting at `col`; for a
+// fixed column the 32 lanes of the warp write 32 consecutive rows, i.e. contiguous memory.  Supports
+// alpha and bias only (hba_gemm_bf16 rejects the other epilogue options with transpose_out).
+__device__ __forceinline__ void epilogue_chunk_transposed(const GemmArgs& g, const uint32_t* r, int row,
+                                                          int col) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
-  const bool full = (col + 32 <= g.N);
-  if (g.bias) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
-        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col + j < g.N) v[j] += __ldg(g.bias + col + j);
-    }
-  }
-  if (g.pre_out) {
-    if (g.pre_dtype == HBA_DT_F32) {
-      float* p = static_cast<float*>(g.pre_out) + (size_t)row * g.ld_pre + col;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col + j < g.N) p[j] = v[j];
-      }
-    } else {
-      __nv_bfloat16* p = static_cast<__nv_bfloat16*>(g.pre_out) + (size_t)row * g.ld_pre + col;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(p + j) =
-              make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                         pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col + j < g.N) p[j] = __float2bfloat16_rn(v[j]);
-      }
-    }
-  }
-  if (g.act == HBA_ACT_QUICKGELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = quickgelu(v[j]);
-  } else if (g.act == HBA_ACT_GELU_ERF) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (g.act == HBA_ACT_QUICKGELU_GRAD || g.act == HBA_ACT_GELU_ERF_GRAD) {
-    float a[32];
-    if (g.aux_dtype == HBA_DT_F32) {
-      const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (col + j < g.N) ? __ldg(p + j) : 0.f;
-    } else {
-      const __nv_bfloat16* p =
-          static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (col + j < g.N) ? __bfloat162float(p[j]) : 0.f;
-    }
-    if (g.act == HBA_ACT_QUICKGELU_GRAD) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= quickgelu_grad(a[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(a[j]);
-    }
-  }
-  if (g.residual) {
-    const float* p = g.residual + (size_t)row * g.ldr + col;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p + j));
-        v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col + j < g.N) v[j] += __ldg(p + j);
-    }
-  }
-  if (!g.transpose_out) {
-    if (g.out_f32) {
-      float* p = g.out_f32 + (size_t)row * g.ld_f32 + col;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col + j < g.N) p[j] = v[j];
-      }
-    }
-    if (g.out_bf16) {
-      __nv_bfloat16* p = g.out_bf16 + (size_t)row * g.ld_bf16 + col;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(p + j) =
-              make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                         pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-        if (g.out_lo_off > 0) {
-          float l[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) l[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(p + g.out_lo_off + j) =
-                make_uint4(pack_bf16x2(l[j], l[j + 1]), pack_bf16x2(l[j + 2], l[j + 3]),
-                           pack_bf16x2(l[j + 4], l[j + 5]), pack_bf16x2(l[j + 6], l[j + 7]));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col + j < g.N) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-            p[j] = h;
-            if (g.out_lo_off > 0)
-              p[g.out_lo_off + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-          }
-      }
-    }
-  } else {
-    // transposed store: for a fixed column the 32 lanes of the warp write 32 consecutive rows
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (col + j < g.N) {
-        if (g.out_f32) g.out_f32[(size_t)(col + j) * g.ld_f32 + row] = v[j];
-        if (g.out_bf16) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-          g.out_bf16[(size_t)(col + j) * g.ld_bf16 + row] = h;
-          if (g.out_lo_off > 0)
-            g.out_bf16[(size_t)(col + j) * g.ld_bf16 + g.out_lo_off + row] =
-                __float2bfloat16_rn(v[j] - __bfloat162float(h));
-        }
+  for (int j = 0; j < 32; ++j) {
+    if (col + j < g.N) {
+      float v = __uint_as_float(r[j]) * g.alpha;
+      if (g.bias) v += __ldg(g.bias + col + j);
+      if (g.out_f32) g.out_f32[(size_t)(col + j) * g.ld_f32 + row] = v;
+      if (g.out_bf16) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        g.out_bf16[(size_t)(col + j) * g.ld_bf16 + row] = h;
+        if (g.out_lo_off > 0)
+          g.out_bf16[(size_t)(col + j) * g.ld_bf16 + g.out_lo_off + row] =
+              __float2bfloat16_rn(v - __bfloat162float(h));
       }
     }
   }
 }
 
-template <int BN>
+// ---- coalesced epilogue --------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 columns); storing that directly makes every
+// warp-wide store touch 32 different lines, 16 bytes each.  The chunk is therefore transposed through
+// a per-warp 4 KB shared-memory tile (16-byte granules XOR-swizzled by the row: conflict-free both
+// ways); afterwards lane l owns the float4 at columns 4*(l&7).. of rows 4*i + (l>>3), i = 0..7, so a
+// warp-wide access covers 4 rows x 128 contiguous bytes.  Bias, activation, activation gradient,
+// residual and every output (fp32 / bf16 hi[/lo] / pre-activation) use that layout.
+struct Vec4 {
+  float x[4];
+};
+// explicit shared-space accesses (the 1024-byte aligned base is computed through an integer, which
+// would otherwise demote these to generic LD/ST)
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ Vec4 ld4_f32(const float* p) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  return Vec4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ Vec4 ld4_bf16(const __nv_bfloat16* p) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  return Vec4{{__low2float(a), __high2float(a), __low2float(b), __high2float(b)}};
+}
+__device__ __forceinline__ void st4_f32(float* p, const Vec4& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v.x[0], v.x[1], v.x[2], v.x[3]);
+}
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const Vec4& v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x[0], v.x[1]), pack_bf16x2(v.x[2], v.x[3]));
+}
+
+// one 32-row x 32-column chunk of the tile; `r` = this thread's accumulator row (lane = row),
+// `stage` = this warp's private 4 KB staging tile
+__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, const uint32_t* r,
+                                                         uint32_t stage, int row0, int col0, int lane) {
+  const int cq = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * cq;
+  const int nvalid = g.N - col;  // >= 4: whole float4 in range
+  const bool vec = nvalid >= 4;
+  // loads that do not depend on the accumulator are issued first (they overlap the transposition)
+  Vec4 bias = {{0.f, 0.f, 0.f, 0.f}};
+  if (g.bias) {
+    if (vec) bias = ld4_f32(g.bias + col);
+    else
+      for (int e = 0; e < 4; ++e) if (e < nvalid) bias.x[e] = __ldg(g.bias + col + e);
+  }
+  Vec4 res[8];
+  if (g.residual) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      res[i] = Vec4{{0.f, 0.f, 0.f, 0.f}};
+      if (row < g.M) {
+        const float* p = g.residual + (size_t)row * g.ldr + col;
+        if (vec) res[i] = ld4_f32(p);
+        else
+          for (int e = 0; e < 4; ++e) if (e < nvalid) res[i].x[e] = __ldg(p + e);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]) * g.alpha,
+           __uint_as_float(r[4 * j + 1]) * g.alpha, __uint_as_float(r[4 * j + 2]) * g.alpha,
+           __uint_as_float(r[4 * j + 3]) * g.alpha);
+  __syncwarp();
+  Vec4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + rsub;
+    const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
+    v[i] = Vec4{{t.x + bias.x[0], t.y + bias.x[1], t.z + bias.x[2], t.w + bias.x[3]}};
+  }
+  __syncwarp();  // the staging tile may be rewritten by the next chunk from here on
+  if (nvalid <= 0) return;
+  if (g.pre_out) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      if (row >= g.M) continue;
+      if (g.pre_dtype == HBA_DT_F32) {
+        float* p = static_cast<float*>(g.pre_out) + (size_t)row * g.ld_pre + col;
+        if (vec) st4_f32(p, v[i]);
+        else
+          for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = v[i].x[e];
+      } else {
+        __nv_bfloat16* p = static_cast<__nv_bfloat16*>(g.pre_out) + (size_t)row * g.ld_pre + col;
+        if (vec) st4_bf16(p, v[i]);
+        else
+          for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = __float2bfloat16_rn(v[i].x[e]);
+      }
+    }
+  }
+  if (g.act == HBA_ACT_QUICKGELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i].x[e] = quickgelu(v[i].x[e]);
+  } else if (g.act == HBA_ACT_GELU_ERF) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i].x[e] = gelu_erf(v[i].x[e]);
+  } else if (g.act == HBA_ACT_QUICKGELU_GRAD || g.act == HBA_ACT_GELU_ERF_GRAD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      if (row >= g.M) continue;
+      Vec4 a = {{0.f, 0.f, 0.f, 0.f}};
+      if (g.aux_dtype == HBA_DT_F32) {
+        const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
+        if (vec && (g.ld_aux & 3) == 0) a = ld4_f32(p);
+        else
+          for (int e = 0; e < 4; ++e) if (e < nvalid) a.x[e] = __ldg(p + e);
+      } else {
+        const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
+        if (vec && (g.ld_aux & 3) == 0) a = ld4_bf16(p);
+        else
+          for (int e = 0; e < 4; ++e) if (e < nvalid) a.x[e] = __bfloat162float(p[e]);
+      }
+      if (g.act == HBA_ACT_QUICKGELU_GRAD) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[i].x[e] *= quickgelu_grad(a.x[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[i].x[e] *= gelu_erf_grad(a.x[e]);
+      }
+    }
+  }
+  if (g.residual) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i].x[e] += res[i].x[e];
+  }
+  if (g.out_f32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      if (row >= g.M) continue;
+      float* p = g.out_f32 + (size_t)row * g.ld_f32 + col;
+      if (vec) st4_f32(p, v[i]);
+      else
+        for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = v[i].x[e];
+    }
+  }
+  if (g.out_bf16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + 4 * i + rsub;
+      if (row >= g.M) continue;
+      __nv_bfloat16* p = g.out_bf16 + (size_t)row * g.ld_bf16 + col;
+      if (vec) {
+        st4_bf16(p, v[i]);
+        if (g.out_lo_off > 0) {
+          Vec4 l;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            l.x[e] = v[i].x[e] - __bfloat162float(__float2bfloat16_rn(v[i].x[e]));
+          st4_bf16(p + g.out_lo_off, l);
+        }
+      } else {
+        for (int e = 0; e < 4; ++e)
+          if (e < nvalid) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v[i].x[e]);
+            p[e] = h;
+            if (g.out_lo_off > 0)
+              p[g.out_lo_off + e] = __float2bfloat16_rn(v[i].x[e] - __bfloat162float(h));
+          }
+      }
+    }
+  }
+}
+
+template <int BN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                    const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int BNC = BN / CG;   // rows of B this CTA stages per k-block
+  constexpr int TM = BM * CG;    // rows of C per tile (per CTA pair when CG == 2)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + kStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes);
+  uint8_t* sStage = sB + kStages * Cfg::kBBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: the compiler then knows the role branches below are warp-uniform and keeps
+  // descriptors / barrier addresses in uniform registers (no per-instruction waterfall loops around
+  // UTCHMMA / UTMALDG)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;  // 0 = leader (issues the UMMAs)
+  const int worker = blockIdx.x / CG, num_workers = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], 1);   // the leader's producer arrives (+ the tx bytes of both CTAs)
+      mbar_init(&empty_bar[i], 1);  // one (multicast) tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps * CG);  // one arrival per epilogue warp of the pair
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be live before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m_tiles = (g.M + BM - 1) / BM;
+  const int num_m_tiles = (g.M + TM - 1) / TM;
   const int num_n_tiles = (g.N + BN - 1) / BN;
   const int total_tiles = num_m_tiles * num_n_tiles;
   const int kblocks = (g.K + BK - 1) / BK;  // a ragged last block is zero-filled by TMA
   const int kiters = kblocks * g.nsplit;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m_tiles) * BM;
-        const int n0 = (tile / num_m_tiles) * BN;
+      // where this CTA's TMA bytes are accounted: the pair leader's barriers
+      const uint32_t full0 = (CG == 2) ? mapa_u32(&full_bar[0], 0) : smem_u32(&full_bar[0]);
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+        const int m0 = (tile % num_m_tiles) * TM + rank * BM;
+        const int n0 = (tile / num_m_tiles) * BN + rank * BNC;
         for (int kb = 0; kb < kblocks; ++kb) {
           for (int s = 0; s < g.nsplit; ++s) {
             const int a_col = kb * BK + (s == 1 ? g.a_lo_off : 0);
             const int b_col = kb * BK + (s == 2 ? g.b_lo_off : 0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+            if (g.debug & 2) {
+              if (rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
+              __syncwarp();
+              if (++stage == kStages) stage = 0, phase ^= 1;
+              continue;
+            }
+            uint8_t* dA = sA + stage * Cfg::kABytes;
+            uint8_t* dB = sB + stage * Cfg::kBBytes;
+            const uint32_t fb = full0 + 8u * stage;
+            if (elect_one()) {
+            if (rank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], CG * (Cfg::kABytes + Cfg::kBBytes));
             if (!g.a_mn) {
-              tma_load_2d(sA + stage * Cfg::kABytes, &tma_a, &full_bar[stage], a_col, m0);
+              tma_load<CG>(dA, &tma_a, fb, a_col, m0);
             } else {  // [K, M] storage: BM/64 boxes of 64 k-rows x 64 m-columns, 8 KB apart (LBO)
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(sA + stage * Cfg::kABytes + j * 8192, &tma_a, &full_bar[stage],
-                            m0 + 64 * j + (s == 1 ? g.a_lo_off : 0), kb * BK);
+                tma_load<CG>(dA + j * 8192, &tma_a, fb, m0 + 64 * j + (s == 1 ? g.a_lo_off : 0),
+                             kb * BK);
             }
             if (!g.b_mn) {
-              tma_load_2d(sB + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], b_col, n0);
+              tma_load<CG>(dB, &tma_b, fb, b_col, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sB + stage * Cfg::kBBytes + j * 8192, &tma_b, &full_bar[stage],
-                            n0 + 64 * j + (s == 2 ? g.b_lo_off : 0), kb * BK);
+              for (int j = 0; j < BNC / 64; ++j)
+                tma_load<CG>(dB + j * 8192, &tma_b, fb, n0 + 64 * j + (s == 2 ? g.b_lo_off : 0),
+                             kb * BK);
             }
+            }
+            __syncwarp();
             if (++stage == kStages) stage = 0, phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, BN) | (g.a_mn ? (1u << 15) : 0u) |
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, BN) | (g.a_mn ? (1u << 15) : 0u) |
                              (g.b_mn ? (1u << 16) : 0u);
       // K-major: +32 B per 16-element k-step inside the 128-byte swizzle row (start address += 2);
       // MN-major: 16 k-rows of 128 B further down (start address += 128)
@@ -304,7 +418,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -315,12 +429,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           uint64_t b_desc = make_smem_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
           if (g.a_mn) a_desc = (a_desc & ~((uint64_t)0x3FFF << 16)) | mn_lbo;
           if (g.b_mn) b_desc = (b_desc & ~((uint64_t)0x3FFF << 16)) | mn_lbo;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc,
-                      (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (it == kiters - 1) umma_commit(&tfull_bar[acc]);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+            if constexpr (CG == 2)
+              umma_bf16_pair(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, accum);
+            else
+              umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, accum);
+          }
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
+          if (it == kiters - 1) {
+            if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc], 3);
+            else umma_commit(&tfull_bar[acc]);
+          }
+          }
+          __syncwarp();
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
         acc ^= 1;
@@ -331,10 +457,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
+    const uint32_t tempty_addr[2] = {
+        (CG == 2) ? mapa_u32(&tempty_bar[0], 0) : smem_u32(&tempty_bar[0]),
+        (CG == 2) ? mapa_u32(&tempty_bar[1], 0) : smem_u32(&tempty_bar[1])};
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m_tiles) * BM;
+    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      const int m0 = (tile % num_m_tiles) * TM + rank * BM;
       const int n0 = (tile / num_m_tiles) * BN;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -346,35 +475,55 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         tmem_ld_32x32b_x32(taddr, r);
         tmem_ld_wait();
         const int col = n0 + c * 32;
-        if (row < g.M && col < g.N) epilogue_chunk(g, r, row, col);
+        if (g.debug & 1) continue;
+        if (g.transpose_out) {
+          if (row < g.M && col < g.N) epilogue_chunk_transposed(g, r, row, col);
+        } else if (m0 + q * 32 < g.M && col < g.N) {  // warp-uniform
+          epilogue_chunk_coalesced(g, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) mbar_arrive_cluster(tempty_addr[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if constexpr (CG == 2) {
+    cluster_sync_all();  // the leader's UMMAs read the peer's smem and signal its barriers until the end
+    if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
-template <int BN>
+static int gemm_cta_group() {
+  static int cg = 0;
+  if (cg == 0) {
+    const char* e = getenv("HBA_GEMM_CTA_GROUP");
+    cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  return cg;
+}
+
+template <int BN, int CG>
 static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d>): %s", BN, cudaGetErrorString(e));
+      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>): %s", BN, CG, cudaGetErrorString(e));
       return HBA_ERR_CUDA;
     }
     attr_set = true;
   }
+  constexpr int BNC = BN / CG;
   const uint64_t a_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->a_lo_off : 0);
   const uint64_t b_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
   CUtensorMap ta, tb;
@@ -385,16 +534,33 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
     HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->K, cols, p->lda, 64, 64));
   }
   if (!p->b_mn_major) {
-    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BN, BK));
+    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BNC, BK));
   } else {
     const uint64_t cols = (uint64_t)p->N + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
     HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->K, cols, p->ldb, 64, 64));
   }
-  const int tiles = ((p->M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
-  int ctas = num_sms();
-  if (p->max_ctas > 0 && p->max_ctas < ctas) ctas = p->max_ctas;
-  if (tiles < ctas) ctas = tiles;
-  gemm_tc_kernel<BN><<<ctas, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, g);
+  const int tiles = ((p->M + BM * CG - 1) / (BM * CG)) * ((p->N + BN - 1) / BN);
+  int workers = num_sms() / CG;
+  if (p->max_ctas > 0 && p->max_ctas / CG < workers) workers = p->max_ctas / CG > 0 ? p->max_ctas / CG : 1;
+  if (tiles < workers) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * CG));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, ta, tb, g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("gemm_tc_kernel<%d,%d> launch: %s", BN, CG, cudaGetErrorString(e));
+    return HBA_ERR_CUDA;
+  }
   return check_launch("gemm_tc_kernel");
 }
 
@@ -419,6 +585,9 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   HBA_REQUIRE(p->act >= HBA_ACT_NONE && p->act <= HBA_ACT_GELU_ERF_GRAD, "hba_gemm_bf16: bad act");
   if (p->act == HBA_ACT_QUICKGELU_GRAD || p->act == HBA_ACT_GELU_ERF_GRAD)
     HBA_REQUIRE(p->aux != nullptr, "hba_gemm_bf16: activation gradient needs aux");
+  if (p->transpose_out)
+    HBA_REQUIRE(p->act == HBA_ACT_NONE && !p->residual && !p->pre_out,
+                "hba_gemm_bf16: transpose_out supports alpha and bias only");
   if (!p->transpose_out) {
     HBA_REQUIRE(!p->out_f32 || (p->ld_f32 % 4 == 0 && ((uintptr_t)p->out_f32 & 15) == 0),
                 "hba_gemm_bf16: out_f32 must be 16-byte aligned with ld %% 4 == 0");
@@ -443,7 +612,19 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   g.out_bf16 = static_cast<__nv_bfloat16*>(p->out_bf16), g.ld_bf16 = p->ld_bf16;
   g.out_lo_off = p->out_lo_off, g.transpose_out = p->transpose_out;
   g.a_mn = p->a_mn_major, g.b_mn = p->b_mn_major;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("HBA_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    g.debug = dbg;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->N >= 256) return launch_gemm<256>(p, g, s);
-  return launch_gemm<128>(p, g, s);
+  if (gemm_cta_group() == 2) {
+    if (p->N >= 256) return launch_gemm<256, 2>(p, g, s);
+    return launch_gemm<128, 2>(p, g, s);
+  }
+  if (p->N >= 256) return launch_gemm<256, 1>(p, g, s);
+  return launch_gemm<128, 1>(p, g, s);
 }

@@ -229,7 +229,7 @@ class ViTEngine:
             x = x_out
         cls_n = self._opbuf("clsn", max(B, 128), d, zero=True)
         ops.layernorm_fwd(x, B, d, m.norm.weight.detach(), m.norm.bias.detach(), LN_EPS, row_step=T, y=cls_n)
-        logits = self._buf("logits", (B, m.num_classes))
+        logits = self._buf("logits", (B, (m.num_classes + 3) // 4 * 4))[:, :m.num_classes]  # 16-byte rows
         ops.gemm(cls_n, self._wops["head"], B, bias=m.head.bias.detach(), out_f32=logits)
         if save:
             self._saved_B = B
@@ -237,6 +237,10 @@ class ViTEngine:
         return logits
 
     # ------------------------------------------------------------------ backward
+    def d_logits_buffer(self, B):
+        C = self.m.num_classes
+        return self._buf("dl_pad", (B, (C + 3) // 4 * 4), zero=True)[:, :C]
+
     def _ensure_grads(self):
         """One flat fp32 gradient buffer; parameters are ordered so that every transformer block's
         gradients are contiguous (one all-reduce bucket per block)."""
@@ -284,7 +288,11 @@ class ViTEngine:
         # ---- head
         Cp = (C + 63) // 64 * 64
         g_log = self._opbuf("g_log", max(B, 128), Cp, zero=True)
-        ops.split_bf16(d_logits, Operand(g_log.buf, B, Cp, g_log.lo_off))
+        dl_pad = self.d_logits_buffer(B)   # [B, C] view of a zero-padded [B, pad4(C)] buffer
+        if d_logits.data_ptr() != dl_pad.data_ptr():
+            dl_pad.copy_(d_logits)
+        d_logits = dl_pad
+        ops.split_bf16(self._buf("dl_pad", (B, (C + 3) // 4 * 4), zero=True), Operand(g_log.buf, B, Cp, g_log.lo_off))
         cls_n = self._opbuf("clsn", max(B, 128), d, zero=True)
         # dW_head[c, k] = sum_b g[b, c] cls_n[b, k]  (both operands read MN-major, K = B)
         ops.gemm(Operand(g_log.buf, B, C, g_log.lo_off), Operand(cls_n.buf, B, d, cls_n.lo_off),
@@ -441,7 +449,7 @@ class DataParallelTrainer:
         B, C = logits.shape
         dev = logits.device
         loss = eng._buf("loss", (1,))
-        d_logits = eng._buf("d_logits", (B, C))
+        d_logits = eng.d_logits_buffer(B)
         hits = eng._buf("hits", (1,), torch.int32)
         ops.softmax_ce(logits, labels, loss, d_logits, hits, eng._buf("ce_ws", (2 * B,)))
         if self.world > 1:
