@@ -336,7 +336,7 @@ extern "C" int hba_attention_fwd(const void* qkv, int32_t qkv_dtype, int64_t ld_
     return attention_fwd_dispatch<float>(static_cast<const float*>(qkv), ld_qkv, B, T, H, causal,
                                          first_row_only, static_cast<__nv_bfloat16*>(out), ld_out,
                                          lo_off, out_f32, ld_of, s);
-  if (qkv_dtype == HBA_DT_BF16 && !first_row_only && lo_off == 0 && T <= 264 && ld_qkv % 8 == 0 &&
+  if (qkv_dtype == HBA_DT_BF16 && !first_row_only && lo_off == 0 && T <= 257 && ld_qkv % 8 == 0 &&
       (!out || ld_out % 8 == 0) && (!out_f32 || ld_of % 4 == 0) && getenv("HBA_ATTN_SIMT") == nullptr)
     return attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, causal,
                                static_cast<__nv_bfloat16*>(out), ld_out, out_f32, ld_of, s);

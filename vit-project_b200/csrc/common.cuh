@@ -195,14 +195,21 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// execution-only rendezvous of the cluster (no memory ordering: avoids MEMBAR.ALL.GPU at teardown)
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // shared::cluster address of `p` (a shared::cta pointer of this CTA) in the CTA of rank `rank`
 __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// (default .release.cta semantics: an explicit .release.cluster costs MEMBAR.ALL + ERRBAR, i.e. the
+// epilogue warp would wait for all its global stores to drain before handing the accumulator back)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
 }
 // TMA load issued by either CTA of a pair into ITS OWN shared memory; the bytes are accounted on

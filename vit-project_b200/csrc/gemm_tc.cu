@@ -157,32 +157,39 @@ __device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, const Vec4& v) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x[0], v.x[1]), pack_bf16x2(v.x[2], v.x[3]));
 }
 
+__device__ __forceinline__ float act_runtime(int act, float v, float a) {
+  switch (act) {
+    case HBA_ACT_QUICKGELU: return quickgelu(v);
+    case HBA_ACT_GELU_ERF: return gelu_erf(v);
+    case HBA_ACT_QUICKGELU_GRAD: return v * quickgelu_grad(a);
+    case HBA_ACT_GELU_ERF_GRAD: return v * gelu_erf_grad(a);
+    default: return v;
+  }
+}
+
 // one 32-row x 32-column chunk of the tile; `r` = this thread's accumulator row (lane = row),
-// `stage` = this warp's private 4 KB staging tile
+// `stage` = shared-space address of this warp's private 4 KB staging tile.  ACT is a template
+// parameter: each kernel instance carries only its own activation code (the erf variants are long and
+// a kernel with all five thrashed the instruction cache: stall_no_inst was the #2 stall reason)
+template <int ACT>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, const uint32_t* r,
                                                          uint32_t stage, int row0, int col0, int lane) {
   const int cq = lane & 7, rsub = lane >> 3;
   const int col = col0 + 4 * cq;
-  const int nvalid = g.N - col;  // >= 4: whole float4 in range
+  const int nvalid = g.N - col;  // >= 4: the whole float4 is in range
   const bool vec = nvalid >= 4;
+  constexpr bool kGrad = (ACT == HBA_ACT_QUICKGELU_GRAD || ACT == HBA_ACT_GELU_ERF_GRAD);
   // loads that do not depend on the accumulator are issued first (they overlap the transposition)
   Vec4 bias = {{0.f, 0.f, 0.f, 0.f}};
-  if (g.bias) {
-    if (vec) bias = ld4_f32(g.bias + col);
-    else
-      for (int e = 0; e < 4; ++e) if (e < nvalid) bias.x[e] = __ldg(g.bias + col + e);
-  }
   Vec4 res[8];
-  if (g.residual) {
+  if (vec) {
+    if (g.bias) bias = ld4_f32(g.bias + col);
+    if (g.residual) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + rsub;
-      res[i] = Vec4{{0.f, 0.f, 0.f, 0.f}};
-      if (row < g.M) {
-        const float* p = g.residual + (size_t)row * g.ldr + col;
-        if (vec) res[i] = ld4_f32(p);
-        else
-          for (int e = 0; e < 4; ++e) if (e < nvalid) res[i].x[e] = __ldg(p + e);
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        res[i] = Vec4{{0.f, 0.f, 0.f, 0.f}};
+        if (row < g.M) res[i] = ld4_f32(g.residual + (size_t)row * g.ldr + col);
       }
     }
   }
@@ -192,93 +199,75 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
            __uint_as_float(r[4 * j + 1]) * g.alpha, __uint_as_float(r[4 * j + 2]) * g.alpha,
            __uint_as_float(r[4 * j + 3]) * g.alpha);
   __syncwarp();
-  Vec4 v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rl = 4 * i + rsub;
-    const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
-    v[i] = Vec4{{t.x + bias.x[0], t.y + bias.x[1], t.z + bias.x[2], t.w + bias.x[3]}};
-  }
-  __syncwarp();  // the staging tile may be rewritten by the next chunk from here on
-  if (nvalid <= 0) return;
-  if (g.pre_out) {
+  if (vec) {
+    Vec4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + rsub;
-      if (row >= g.M) continue;
-      if (g.pre_dtype == HBA_DT_F32) {
-        float* p = static_cast<float*>(g.pre_out) + (size_t)row * g.ld_pre + col;
-        if (vec) st4_f32(p, v[i]);
+      const int rl = 4 * i + rsub;
+      const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
+      v[i] = Vec4{{t.x + bias.x[0], t.y + bias.x[1], t.z + bias.x[2], t.w + bias.x[3]}};
+    }
+    if (g.pre_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        if (row >= g.M) continue;
+        if (g.pre_dtype == HBA_DT_F32)
+          st4_f32(static_cast<float*>(g.pre_out) + (size_t)row * g.ld_pre + col, v[i]);
         else
-          for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = v[i].x[e];
-      } else {
-        __nv_bfloat16* p = static_cast<__nv_bfloat16*>(g.pre_out) + (size_t)row * g.ld_pre + col;
-        if (vec) st4_bf16(p, v[i]);
-        else
-          for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = __float2bfloat16_rn(v[i].x[e]);
+          st4_bf16(static_cast<__nv_bfloat16*>(g.pre_out) + (size_t)row * g.ld_pre + col, v[i]);
       }
     }
-  }
-  if (g.act == HBA_ACT_QUICKGELU) {
+    if constexpr (ACT == HBA_ACT_QUICKGELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[i].x[e] = quickgelu(v[i].x[e]);
-  } else if (g.act == HBA_ACT_GELU_ERF) {
+        for (int e = 0; e < 4; ++e) v[i].x[e] = quickgelu(v[i].x[e]);
+    } else if constexpr (ACT == HBA_ACT_GELU_ERF) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[i].x[e] = gelu_erf(v[i].x[e]);
-  } else if (g.act == HBA_ACT_QUICKGELU_GRAD || g.act == HBA_ACT_GELU_ERF_GRAD) {
+        for (int e = 0; e < 4; ++e) v[i].x[e] = gelu_erf(v[i].x[e]);
+    } else if constexpr (kGrad) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + rsub;
-      if (row >= g.M) continue;
-      Vec4 a = {{0.f, 0.f, 0.f, 0.f}};
-      if (g.aux_dtype == HBA_DT_F32) {
-        const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
-        if (vec && (g.ld_aux & 3) == 0) a = ld4_f32(p);
-        else
-          for (int e = 0; e < 4; ++e) if (e < nvalid) a.x[e] = __ldg(p + e);
-      } else {
-        const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
-        if (vec && (g.ld_aux & 3) == 0) a = ld4_bf16(p);
-        else
-          for (int e = 0; e < 4; ++e) if (e < nvalid) a.x[e] = __bfloat162float(p[e]);
-      }
-      if (g.act == HBA_ACT_QUICKGELU_GRAD) {
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        if (row >= g.M) continue;
+        Vec4 a;
+        if (g.aux_dtype == HBA_DT_F32) {
+          const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
+          if ((g.ld_aux & 3) == 0) a = ld4_f32(p);
+          else a = Vec4{{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}};
+        } else {
+          const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
+          if ((g.ld_aux & 3) == 0) a = ld4_bf16(p);
+          else a = Vec4{{__bfloat162float(p[0]), __bfloat162float(p[1]), __bfloat162float(p[2]),
+                         __bfloat162float(p[3])}};
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[i].x[e] *= quickgelu_grad(a.x[e]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[i].x[e] *= gelu_erf_grad(a.x[e]);
+        for (int e = 0; e < 4; ++e)
+          v[i].x[e] *= (ACT == HBA_ACT_QUICKGELU_GRAD) ? quickgelu_grad(a.x[e]) : gelu_erf_grad(a.x[e]);
       }
     }
-  }
-  if (g.residual) {
+    if (g.residual) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[i].x[e] += res[i].x[e];
-  }
-  if (g.out_f32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + rsub;
-      if (row >= g.M) continue;
-      float* p = g.out_f32 + (size_t)row * g.ld_f32 + col;
-      if (vec) st4_f32(p, v[i]);
-      else
-        for (int e = 0; e < 4; ++e) if (e < nvalid) p[e] = v[i].x[e];
+        for (int e = 0; e < 4; ++e) v[i].x[e] += res[i].x[e];
     }
-  }
-  if (g.out_bf16) {
+    if (g.out_f32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + 4 * i + rsub;
-      if (row >= g.M) continue;
-      __nv_bfloat16* p = g.out_bf16 + (size_t)row * g.ld_bf16 + col;
-      if (vec) {
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        if (row < g.M) st4_f32(g.out_f32 + (size_t)row * g.ld_f32 + col, v[i]);
+      }
+    }
+    if (g.out_bf16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + 4 * i + rsub;
+        if (row >= g.M) continue;
+        __nv_bfloat16* p = g.out_bf16 + (size_t)row * g.ld_bf16 + col;
         st4_bf16(p, v[i]);
         if (g.out_lo_off > 0) {
           Vec4 l;
@@ -287,20 +276,48 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
             l.x[e] = v[i].x[e] - __bfloat162float(__float2bfloat16_rn(v[i].x[e]));
           st4_bf16(p + g.out_lo_off, l);
         }
-      } else {
-        for (int e = 0; e < 4; ++e)
-          if (e < nvalid) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(v[i].x[e]);
-            p[e] = h;
-            if (g.out_lo_off > 0)
-              p[g.out_lo_off + e] = __float2bfloat16_rn(v[i].x[e] - __bfloat162float(h));
-          }
+      }
+    }
+  } else if (nvalid > 0) {
+    // ragged last columns (N % 4 != 0): element-wise, not unrolled (cold path)
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + rsub;
+      const int row = row0 + rl;
+      if (row >= g.M) continue;
+      const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
+      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll 1
+      for (int e = 0; e < nvalid; ++e) {
+        float v = tv[e] + (g.bias ? __ldg(g.bias + col + e) : 0.f);
+        if (g.pre_out) {
+          if (g.pre_dtype == HBA_DT_F32)
+            static_cast<float*>(g.pre_out)[(size_t)row * g.ld_pre + col + e] = v;
+          else
+            static_cast<__nv_bfloat16*>(g.pre_out)[(size_t)row * g.ld_pre + col + e] = __float2bfloat16_rn(v);
+        }
+        float a = 0.f;
+        if (kGrad)
+          a = g.aux_dtype == HBA_DT_F32
+                  ? __ldg(static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col + e)
+                  : __bfloat162float(static_cast<const __nv_bfloat16*>(g.aux)[(size_t)row * g.ld_aux + col + e]);
+        v = act_runtime(ACT, v, a);
+        if (g.residual) v += __ldg(g.residual + (size_t)row * g.ldr + col + e);
+        if (g.out_f32) g.out_f32[(size_t)row * g.ld_f32 + col + e] = v;
+        if (g.out_bf16) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          g.out_bf16[(size_t)row * g.ld_bf16 + col + e] = h;
+          if (g.out_lo_off > 0)
+            g.out_bf16[(size_t)row * g.ld_bf16 + g.out_lo_off + col + e] =
+                __float2bfloat16_rn(v - __bfloat162float(h));
+        }
       }
     }
   }
+  __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                    const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
@@ -479,7 +496,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (g.transpose_out) {
           if (row < g.M && col < g.N) epilogue_chunk_transposed(g, r, row, col);
         } else if (m0 + q * 32 < g.M && col < g.N) {  // warp-uniform
-          epilogue_chunk_coalesced(g, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
+          epilogue_chunk_coalesced<ACT>(g, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
         }
       }
       tc_fence_before();
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   tc_fence_before();
   if constexpr (CG == 2) {
-    cluster_sync_all();  // the leader's UMMAs read the peer's smem and signal its barriers until the end
+    cluster_sync_relaxed();  // the leader's UMMAs read the peer's smem and signal its barriers until the end
     if (warp == 1) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
   } else {
     __syncthreads();
@@ -508,12 +525,12 @@ static int gemm_cta_group() {
   return cg;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int ACT>
 static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, ACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) {
@@ -555,7 +572,7 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG>, ta, tb, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, ACT>, ta, tb, g);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("gemm_tc_kernel<%d,%d> launch: %s", BN, CG, cudaGetErrorString(e));
@@ -621,10 +638,26 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
     g.debug = dbg;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool wide = p->N >= 256;
   if (gemm_cta_group() == 2) {
-    if (p->N >= 256) return launch_gemm<256, 2>(p, g, s);
-    return launch_gemm<128, 2>(p, g, s);
+    switch (p->act) {
+#define HBA_GEMM_CASE(A) \
+  case A:                \
+    return wide ? launch_gemm<256, 2, A>(p, g, s) : launch_gemm<128, 2, A>(p, g, s);
+      HBA_GEMM_CASE(HBA_ACT_NONE)
+      HBA_GEMM_CASE(HBA_ACT_QUICKGELU)
+      HBA_GEMM_CASE(HBA_ACT_GELU_ERF)
+      HBA_GEMM_CASE(HBA_ACT_QUICKGELU_GRAD)
+      HBA_GEMM_CASE(HBA_ACT_GELU_ERF_GRAD)
+#undef HBA_GEMM_CASE
+    }
   }
-  if (p->N >= 256) return launch_gemm<256, 1>(p, g, s);
-  return launch_gemm<128, 1>(p, g, s);
+  // single-CTA variant (HBA_GEMM_CTA_GROUP=1): kept for A/B measurements of the plain and QuickGELU paths
+  if (p->act == HBA_ACT_NONE)
+    return wide ? launch_gemm<256, 1, HBA_ACT_NONE>(p, g, s) : launch_gemm<128, 1, HBA_ACT_NONE>(p, g, s);
+  if (p->act == HBA_ACT_QUICKGELU)
+    return wide ? launch_gemm<256, 1, HBA_ACT_QUICKGELU>(p, g, s)
+                : launch_gemm<128, 1, HBA_ACT_QUICKGELU>(p, g, s);
+  set_error("hba_gemm_bf16: HBA_GEMM_CTA_GROUP=1 supports HBA_ACT_NONE / HBA_ACT_QUICKGELU only");
+  return HBA_ERR_ARG;
 }
