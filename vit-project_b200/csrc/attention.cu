@@ -151,75 +151,133 @@ __global__ void __launch_bounds__(kAttnWarps * 32, 1)
   }
 }
 
-// CLS-row-only forward: one warp per (sequence, head); K and V are streamed from global memory.
+// ---- CLS-row-only kernels (last vision block, SURVEY 7 "row pruning") -------------------------
+// One 256-thread CTA per (sequence, head).  Scores: one thread per key, reading its 64-element K row
+// with 16-byte loads; block-wide max / sum; P.V and the dq accumulation use a (32 key-groups x 8
+// eight-dim chunks) thread grid, so that 8 consecutive threads read one contiguous K / V row.
+constexpr int kR0Threads = 256;
+constexpr int kR0MaxKeys = 32 * kMaxKeyChunks;  // 288
+
+// 8 consecutive elements (16-byte aligned for bf16, 32-byte for fp32) as floats
 template <typename T>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void load8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __bfloat1622float2(h[e]);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ float dot64(const T* row, const float* sv) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float v[8];
+    load8(row + 8 * c, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += v[e] * sv[8 * c + e];
+  }
+  return acc;
+}
+__device__ __forceinline__ float block_max256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kR0Threads / 32; ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kR0Threads / 32; ++w) r += red[w];
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kR0Threads)
     attention_row0_fwd_kernel(const T* __restrict__ qkv, int64_t ld_qkv, int Bn, int Tn, int H,
                               __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t lo_off,
                               float* __restrict__ out_f32, int64_t ld_of) {
-  __shared__ float sP[4][kMaxKeyChunks * 32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x * 4 + warp;
-  if (bh >= Bn * H) return;
-  const int b = bh / H, h = bh % H, d = H * kHd;
+  __shared__ __align__(16) float sq[kHd];
+  __shared__ float sp[kR0MaxKeys];
+  __shared__ float red[kR0Threads / 32];
+  __shared__ float so[32][kHd + 1];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / H, h = blockIdx.x % H, d = H * kHd;
   const T* base = qkv + (int64_t)b * Tn * ld_qkv + h * kHd;
-  const float q_lo = 0.125f * ld_as_float(base + lane), q_hi = 0.125f * ld_as_float(base + lane + 32);
-  const int nchunks = (Tn + 31) >> 5;
-  float s[kMaxKeyChunks];
+  if (tid < kHd) sq[tid] = 0.125f * ld_as_float(base + tid);
+  __syncthreads();
+  float s[2];
   float mx = -INFINITY;
 #pragma unroll
-  for (int jj = 0; jj < kMaxKeyChunks; ++jj) {
-    s[jj] = -INFINITY;
-    if (jj < nchunks) {
-      // dot products of the 32 keys of this chunk, computed cooperatively (lane owns dims), then
-      // redistributed so that lane l keeps key 32*jj + l
-      for (int u = 0; u < 32; ++u) {
-        const int j = 32 * jj + u;
-        float part = 0.f;
-        if (j < Tn) {
-          const T* kr = base + (int64_t)j * ld_qkv + d;
-          part = q_lo * ld_as_float(kr + lane) + q_hi * ld_as_float(kr + lane + 32);
-        }
-        part = warp_sum(part);
-        if (lane == u && j < Tn) s[jj] = part;
-      }
-      mx = fmaxf(mx, s[jj]);
-    }
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    s[u] = -INFINITY;
+    if (j < Tn) s[u] = dot64(base + (int64_t)j * ld_qkv + d, sq);
+    mx = fmaxf(mx, s[u]);
   }
-  mx = warp_max(mx);
+  mx = block_max256(mx, red);
   float sum = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < kMaxKeyChunks; ++jj) {
-    const float e = (s[jj] == -INFINITY) ? 0.f : expf(s[jj] - mx);
-    s[jj] = e;
-    sum += e;
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    if (j < Tn) {
+      s[u] = expf(s[u] - mx);
+      sum += s[u];
+    }
   }
-  sum = warp_sum(sum);
+  sum = block_sum256(sum, red);
   const float inv = 1.0f / sum;
 #pragma unroll
-  for (int jj = 0; jj < kMaxKeyChunks; ++jj)
-    if (jj < nchunks) sP[warp][32 * jj + lane] = s[jj] * inv;
-  __syncwarp();
-  float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < Tn; ++j) {
-    const float p = sP[warp][j];
-    const T* vr = base + (int64_t)j * ld_qkv + 2 * d;
-    o0 += p * ld_as_float(vr + lane);
-    o1 += p * ld_as_float(vr + lane + 32);
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    if (j < Tn) sp[j] = s[u] * inv;
   }
-  const int c = h * kHd + lane;
-  if (out) {
-    __nv_bfloat16 hi, lo;
-    split_bf16(o0, hi, lo);
-    out[(int64_t)b * ld_out + c] = hi;
-    if (lo_off > 0) out[(int64_t)b * ld_out + lo_off + c] = lo;
-    split_bf16(o1, hi, lo);
-    out[(int64_t)b * ld_out + c + 32] = hi;
-    if (lo_off > 0) out[(int64_t)b * ld_out + lo_off + c + 32] = lo;
+  __syncthreads();
+  const int grp = tid >> 3, c = tid & 7;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j = grp; j < Tn; j += 32) {
+    float v[8];
+    load8(base + (int64_t)j * ld_qkv + 2 * d + 8 * c, v);
+    const float pj = sp[j];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += pj * v[e];
   }
-  if (out_f32) {
-    out_f32[(int64_t)b * ld_of + c] = o0;
-    out_f32[(int64_t)b * ld_of + c + 32] = o1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) so[grp][8 * c + e] = acc[e];
+  __syncthreads();
+  if (tid < kHd) {
+    float o = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < 32; ++gq) o += so[gq][tid];
+    const int col = h * kHd + tid;
+    if (out) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(o, hi, lo);
+      out[(int64_t)b * ld_out + col] = hi;
+      if (lo_off > 0) out[(int64_t)b * ld_out + lo_off + col] = lo;
+    }
+    if (out_f32) out_f32[(int64_t)b * ld_of + col] = o;
   }
 }
 
@@ -227,63 +285,100 @@ __global__ void __launch_bounds__(128)
 //   p = softmax(q0 K^T / 8); dV_j = p_j dO; dp_j = dO.V_j; ds_j = p_j (dp_j - sum_k p_k dp_k);
 //   dq0 = sum_j ds_j K_j / 8; dK_j = ds_j q0 / 8; dq_i = 0 for i > 0.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kR0Threads)
     attention_row0_bwd_kernel(const T* __restrict__ qkv, int64_t ld_qkv, int Bn, int Tn, int H,
                               const float* __restrict__ d_out, int64_t ld_do,
                               float* __restrict__ d_qkv, int64_t ld_dqkv) {
-  __shared__ float sS[4][kMaxKeyChunks * 32];  // p, then ds
-  __shared__ float sD[4][kMaxKeyChunks * 32];  // dp
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x * 4 + warp;
-  if (bh >= Bn * H) return;
-  const int b = bh / H, h = bh % H, d = H * kHd;
+  __shared__ __align__(16) float sq[kHd];    // q0 (unscaled)
+  __shared__ __align__(16) float sdo[kHd];   // dO
+  __shared__ float sp[kR0MaxKeys];           // p
+  __shared__ float sds[kR0MaxKeys];          // ds
+  __shared__ float red[kR0Threads / 32];
+  __shared__ float so[32][kHd + 1];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / H, h = blockIdx.x % H, d = H * kHd;
   const T* base = qkv + (int64_t)b * Tn * ld_qkv + h * kHd;
   float* gbase = d_qkv + (int64_t)b * Tn * ld_dqkv + h * kHd;
-  const float q_lo = ld_as_float(base + lane), q_hi = ld_as_float(base + lane + 32);
-  const float do_lo = d_out[(int64_t)b * ld_do + h * kHd + lane];
-  const float do_hi = d_out[(int64_t)b * ld_do + h * kHd + lane + 32];
-  // pass 1: scores and dp for every key (lane owns dims; warp_sum per key)
-  float mx = -INFINITY;
-  for (int j = 0; j < Tn; ++j) {
-    const T* kr = base + (int64_t)j * ld_qkv + d;
-    const T* vr = base + (int64_t)j * ld_qkv + 2 * d;
-    float sc = 0.125f * (q_lo * ld_as_float(kr + lane) + q_hi * ld_as_float(kr + lane + 32));
-    float dp = do_lo * ld_as_float(vr + lane) + do_hi * ld_as_float(vr + lane + 32);
-    sc = warp_sum(sc);
-    dp = warp_sum(dp);
-    if (lane == 0) sS[warp][j] = sc, sD[warp][j] = dp;
-    mx = fmaxf(mx, sc);
+  if (tid < kHd) {
+    sq[tid] = ld_as_float(base + tid);
+    sdo[tid] = d_out[(int64_t)b * ld_do + h * kHd + tid];
   }
-  __syncwarp();
+  __syncthreads();
+  float sc[2], dp[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    sc[u] = -INFINITY, dp[u] = 0.f;
+    if (j < Tn) {
+      sc[u] = 0.125f * dot64(base + (int64_t)j * ld_qkv + d, sq);
+      dp[u] = dot64(base + (int64_t)j * ld_qkv + 2 * d, sdo);
+    }
+    mx = fmaxf(mx, sc[u]);
+  }
+  mx = block_max256(mx, red);
   float sum = 0.f;
-  for (int j = lane; j < Tn; j += 32) sum += expf(sS[warp][j] - mx);
-  sum = warp_sum(sum);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    if (j < Tn) {
+      sc[u] = expf(sc[u] - mx);
+      sum += sc[u];
+    }
+  }
+  sum = block_sum256(sum, red);
   const float inv = 1.0f / sum;
   float dot = 0.f;
-  for (int j = lane; j < Tn; j += 32) {
-    const float p = expf(sS[warp][j] - mx) * inv;
-    sS[warp][j] = p;
-    dot += p * sD[warp][j];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    if (j < Tn) {
+      sc[u] *= inv;
+      dot += sc[u] * dp[u];
+    }
   }
-  dot = warp_sum(dot);
-  __syncwarp();
-  // pass 2: gradients
-  float dq_lo = 0.f, dq_hi = 0.f;
-  for (int j = 0; j < Tn; ++j) {
-    const float p = sS[warp][j];
-    const float ds = p * (sD[warp][j] - dot);
-    const T* kr = base + (int64_t)j * ld_qkv + d;
-    dq_lo += ds * ld_as_float(kr + lane);
-    dq_hi += ds * ld_as_float(kr + lane + 32);
-    float* gr = gbase + (int64_t)j * ld_dqkv;
-    gr[d + lane] = 0.125f * ds * q_lo;
-    gr[d + lane + 32] = 0.125f * ds * q_hi;
-    gr[2 * d + lane] = p * do_lo;
-    gr[2 * d + lane + 32] = p * do_hi;
-    if (j > 0) gr[lane] = 0.f, gr[lane + 32] = 0.f;
+  dot = block_sum256(dot, red);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = tid + kR0Threads * u;
+    if (j < Tn) {
+      sp[j] = sc[u];
+      sds[j] = sc[u] * (dp[u] - dot);
+    }
   }
-  gbase[lane] = 0.125f * dq_lo;
-  gbase[lane + 32] = 0.125f * dq_hi;
+  __syncthreads();
+  // dq0 = 0.125 * sum_j ds_j K_j: (32 key groups) x (8 dim chunks), reduced through shared memory
+  const int grp = tid >> 3, c = tid & 7;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j = grp; j < Tn; j += 32) {
+    float v[8];
+    load8(base + (int64_t)j * ld_qkv + d + 8 * c, v);
+    const float dsj = sds[j];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += dsj * v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) so[grp][8 * c + e] = acc[e];
+  // dK_j = 0.125 ds_j q0, dV_j = p_j dO, dq_j = 0 (j > 0): 16 threads per key row segment (float4 each)
+  const int c4 = tid & 15;
+  const float4 q4 = *reinterpret_cast<const float4*>(sq + 4 * c4);
+  const float4 do4 = *reinterpret_cast<const float4*>(sdo + 4 * c4);
+  for (int j = tid >> 4; j < Tn; j += kR0Threads / 16) {
+    const float dsj = 0.125f * sds[j], pj = sp[j];
+    float* gr = gbase + (int64_t)j * ld_dqkv + 4 * c4;
+    if (j > 0) *reinterpret_cast<float4*>(gr) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(gr + d) = make_float4(dsj * q4.x, dsj * q4.y, dsj * q4.z, dsj * q4.w);
+    *reinterpret_cast<float4*>(gr + 2 * d) = make_float4(pj * do4.x, pj * do4.y, pj * do4.z, pj * do4.w);
+  }
+  __syncthreads();
+  if (tid < kHd) {
+    float o = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < 32; ++gq) o += so[gq][tid];
+    gbase[tid] = 0.125f * o;
+  }
 }
 
 int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
@@ -295,8 +390,8 @@ static int attention_fwd_dispatch(const T* qkv, int64_t ld_qkv, int B, int Tn, i
                                   int first_row_only, __nv_bfloat16* out, int64_t ld_out,
                                   int64_t lo_off, float* out_f32, int64_t ld_of, cudaStream_t s) {
   if (first_row_only) {
-    attention_row0_fwd_kernel<T><<<(B * H + 3) / 4, 128, 0, s>>>(qkv, ld_qkv, B, Tn, H, out, ld_out,
-                                                               lo_off, out_f32, ld_of);
+    attention_row0_fwd_kernel<T><<<B * H, kR0Threads, 0, s>>>(qkv, ld_qkv, B, Tn, H, out, ld_out, lo_off,
+                                                            out_f32, ld_of);
     return check_launch("attention_row0_fwd_kernel");
   }
   const int Tp = (Tn + 3) & ~3;
@@ -331,6 +426,9 @@ extern "C" int hba_attention_fwd(const void* qkv, int32_t qkv_dtype, int64_t ld_
   HBA_REQUIRE(qkv && (out || out_f32) && B > 0 && T > 0 && H > 0, "hba_attention_fwd: bad arguments");
   HBA_REQUIRE(T <= 32 * kMaxKeyChunks, "hba_attention_fwd: T=%d exceeds %d", T, 32 * kMaxKeyChunks);
   HBA_REQUIRE(!(first_row_only && causal), "hba_attention_fwd: first_row_only with causal is unsupported");
+  if (first_row_only)
+    HBA_REQUIRE(ld_qkv % 8 == 0 && ((uintptr_t)qkv & 15) == 0,
+                "hba_attention_fwd: first_row_only needs 16-byte aligned qkv rows (ld %% 8 == 0)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (qkv_dtype == HBA_DT_F32)
     return attention_fwd_dispatch<float>(static_cast<const float*>(qkv), ld_qkv, B, T, H, causal,
@@ -354,12 +452,14 @@ extern "C" int hba_attention_bwd_row0(const void* qkv, int32_t qkv_dtype, int64_
                                       float* d_qkv, int64_t ld_dqkv, void* stream) {
   HBA_REQUIRE(qkv && d_out && d_qkv && B > 0 && T > 0 && H > 0, "hba_attention_bwd_row0: bad arguments");
   HBA_REQUIRE(T <= 32 * kMaxKeyChunks, "hba_attention_bwd_row0: T=%d exceeds %d", T, 32 * kMaxKeyChunks);
+  HBA_REQUIRE(ld_qkv % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ld_dqkv % 4 == 0 && ((uintptr_t)d_qkv & 15) == 0,
+              "hba_attention_bwd_row0: qkv / d_qkv rows must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (qkv_dtype == HBA_DT_F32)
-    attention_row0_bwd_kernel<float><<<(B * H + 3) / 4, 128, 0, s>>>(
+    attention_row0_bwd_kernel<float><<<B * H, kR0Threads, 0, s>>>(
         static_cast<const float*>(qkv), ld_qkv, B, T, H, d_out, ld_do, d_qkv, ld_dqkv);
   else if (qkv_dtype == HBA_DT_BF16)
-    attention_row0_bwd_kernel<__nv_bfloat16><<<(B * H + 3) / 4, 128, 0, s>>>(
+    attention_row0_bwd_kernel<__nv_bfloat16><<<B * H, kR0Threads, 0, s>>>(
         static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, d_out, ld_do, d_qkv, ld_dqkv);
   else {
     set_error("hba_attention_bwd_row0: unknown dtype %d", qkv_dtype);

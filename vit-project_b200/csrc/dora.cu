@@ -188,44 +188,101 @@ __global__ void __launch_bounds__(kDoraThreads)
     }
   }
   __syncthreads();
-  // dA[k, c0 + j] = scale * sum_i Bm[i,k] dV[i,j]; thread -> (k, j), r*8 <= 512 outputs
+  // dA[k, c0 + j] = scale * sum_i Bm[i,k] dV[i,j].  Lane = rank index k (two per lane when r > 32), the
+  // 8 warps split the rows: every Bm row (one 128-byte line at r = 32) is read exactly once, coalesced,
+  // 16 rows in flight per warp; dV[i, j] is a shared-memory broadcast.  Cross-warp sum through smem.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float accA[2][kDoraCols];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+    for (int j = 0; j < kDoraCols; ++j) accA[h2][j] = 0.f;
+  const int rows_per_warp = (in_f + 7) / 8;
+  const int i_begin = warp * rows_per_warp, i_end = min(in_f, i_begin + rows_per_warp);
+  for (int i0 = i_begin; i0 < i_end; i0 += 16) {
+    float b0[16], b1[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = i0 + u;
+      b0[u] = (i < i_end && lane < r) ? __ldg(Bm + (size_t)i * r + lane) : 0.f;
+      b1[u] = (i < i_end && lane + 32 < r) ? __ldg(Bm + (size_t)i * r + lane + 32) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = min(i0 + u, in_f - 1);
+      const float4 d0 = *reinterpret_cast<const float4*>(sDV + (size_t)i * kDoraCols);
+      const float4 d1 = *reinterpret_cast<const float4*>(sDV + (size_t)i * kDoraCols + 4);
+      const float dv[kDoraCols] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < kDoraCols; ++j) {
+        accA[0][j] += b0[u] * dv[j];
+        accA[1][j] += b1[u] * dv[j];
+      }
+    }
+  }
+  __syncthreads();  // every warp is done reading sDV: reuse it for the per-warp partial sums
+  float* part = sDV;  // [8 warps][64 k][8 j] floats = 16 KB (the launcher reserves at least that)
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+    for (int j = 0; j < kDoraCols; ++j)
+      part[((size_t)warp * 64 + lane + 32 * h2) * kDoraCols + j] = accA[h2][j];
+  __syncthreads();
   for (int t = threadIdx.x; t < r * kDoraCols; t += kDoraThreads) {
     const int k = t / kDoraCols, j = t % kDoraCols;
     float acc = 0.f;
-    for (int i = 0; i < in_f; ++i) acc += __ldg(Bm + (size_t)i * r + k) * sDV[(size_t)i * kDoraCols + j];
+#pragma unroll
+    for (int w = 0; w < kDoraThreads / 32; ++w) acc += part[((size_t)w * 64 + k) * kDoraCols + j];
     dA[(size_t)k * out_f + c0 + j] = scale * acc;
   }
 }
 
-// backward, phase 2 (row-owning warps): dB[i,k] = scale * sum_j dV[i,j] A[k,j]
-constexpr int kDbChunk = 128;
+// backward, phase 2 (row-owning warps): dB[i,k] = scale * sum_j dV[i,j] A[k,j].
+// The CTA stages 32 rank rows of A (all out_f columns, <= 2048) in shared memory once; a warp owns
+// one row i, its lanes split the columns (coalesced reads of dV, 32 loads in flight), every lane keeps
+// 32 partial sums (one per rank index) and the warp reduces them with shuffles at the end.
+constexpr int kDbMaxCols = 1024;
 __global__ void __launch_bounds__(256)
     dora_merge_bwd_rows_kernel(const float* __restrict__ dV, const float* __restrict__ A, int in_f,
                                int out_f, int r, float scale, float* __restrict__ dB) {
-  __shared__ float sA[kDoraMaxRank][kDbChunk + 1];
+  extern __shared__ __align__(16) float sAr[];  // [32][out_f + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + warp;
-  float acc0 = 0.f, acc1 = 0.f;
-  for (int c0 = 0; c0 < out_f; c0 += kDbChunk) {
+  const int pitch = out_f + 1;
+  for (int k0 = 0; k0 < r; k0 += 32) {
     __syncthreads();
-    for (int t = threadIdx.x; t < r * kDbChunk; t += 256) {
-      const int k = t / kDbChunk, j = t % kDbChunk;
-      sA[k][j] = (c0 + j < out_f) ? A[(size_t)k * out_f + c0 + j] : 0.f;
+    for (int t = threadIdx.x; t < 32 * (out_f / 4); t += 256) {
+      const int k = t / (out_f / 4), j4 = (t % (out_f / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < r) v = __ldg(reinterpret_cast<const float4*>(A + (size_t)(k0 + k) * out_f + j4));
+      float* dst = sAr + (size_t)k * pitch + j4;
+      dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
     }
     __syncthreads();
     if (i < in_f) {
-      const float* row = dV + (size_t)i * out_f + c0;
-      const int lim = min(kDbChunk, out_f - c0);
-      for (int j = 0; j < lim; ++j) {
-        const float d = __ldg(row + j);
-        if (lane < r) acc0 += d * sA[lane][j];
-        if (lane + 32 < r) acc1 += d * sA[lane + 32][j];
+      float acc[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+      for (int c0 = 0; c0 < out_f; c0 += 256) {
+        float dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = c0 + lane + 32 * u;
+          dv[u] = (j < out_f) ? __ldg(dV + (size_t)i * out_f + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = min(c0 + lane + 32 * u, out_f - 1);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[k] += dv[u] * sAr[(size_t)k * pitch + j];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float t = warp_sum(acc[k]);
+        if (lane == k && k0 + k < r) dB[(size_t)i * r + k0 + k] = scale * t;
       }
     }
-  }
-  if (i < in_f) {
-    if (lane < r) dB[(size_t)i * r + lane] = scale * acc0;
-    if (lane + 32 < r) dB[(size_t)i * r + lane + 32] = scale * acc1;
   }
 }
 
@@ -261,8 +318,10 @@ extern "C" int hba_dora_merge_bwd(const float* G, int64_t ld_g, const float* D, 
                                   float* workspace, void* stream) {
   HBA_REQUIRE(G && D && A && Bm && m && dm && dA && dB && workspace, "hba_dora_merge_bwd: null pointer");
   HBA_CHECK(dora_check("hba_dora_merge_bwd", in_f, out_f, r));
+  HBA_REQUIRE(out_f <= 1792, "hba_dora_merge_bwd: out_features=%d exceeds the shared-memory staging (max 1792)", out_f);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = (size_t)in_f * kDoraCols * sizeof(float);
+  // [in_f][8] dV tile, later reused for the [8 warps][64][8] partial sums of dA
+  const size_t smem = (size_t)(in_f > 512 ? in_f : 512) * kDoraCols * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 - 4096 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(dora_merge_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -276,6 +335,17 @@ extern "C" int hba_dora_merge_bwd(const float* G, int64_t ld_g, const float* D, 
   dora_merge_bwd_cols_kernel<<<out_f / kDoraCols, kDoraThreads, smem, s>>>(
       G, ld_g, D, A, Bm, m, in_f, out_f, r, scale, eps, dm, dA, workspace);
   HBA_CHECK(check_launch("dora_merge_bwd_cols_kernel"));
-  dora_merge_bwd_rows_kernel<<<(in_f + 7) / 8, 256, 0, s>>>(workspace, A, in_f, out_f, r, scale, dB);
+  const size_t smem_rows = (size_t)32 * (out_f + 1) * sizeof(float);
+  static size_t configured_rows = 0;
+  if (smem_rows > configured_rows) {
+    cudaError_t e = cudaFuncSetAttribute(dora_merge_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("hba_dora_merge_bwd: cannot reserve %zu bytes of shared memory: %s", smem_rows, cudaGetErrorString(e));
+      return HBA_ERR_CUDA;
+    }
+    configured_rows = smem_rows;
+  }
+  dora_merge_bwd_rows_kernel<<<(in_f + 7) / 8, 256, smem_rows, s>>>(workspace, A, in_f, out_f, r, scale, dB);
   return check_launch("dora_merge_bwd_rows_kernel");
 }

@@ -62,11 +62,14 @@ __device__ __forceinline__ void ln_store(float4 y, int c, float* y_f32, __nv_bfl
     __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
     split_bf16(y.x, h0, l0), split_bf16(y.y, h1, l1), split_bf16(y.z, h2, l2),
         split_bf16(y.w, h3, l3);
-    *reinterpret_cast<__nv_bfloat162*>(y_bf16 + c) = __nv_bfloat162(h0, h1);
-    *reinterpret_cast<__nv_bfloat162*>(y_bf16 + c + 2) = __nv_bfloat162(h2, h3);
+    // one 8-byte store per lane: a warp writes 256 contiguous bytes per instruction
+    __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+    *reinterpret_cast<uint2*>(y_bf16 + c) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
     if (lo_off > 0) {
-      *reinterpret_cast<__nv_bfloat162*>(y_bf16 + lo_off + c) = __nv_bfloat162(l0, l1);
-      *reinterpret_cast<__nv_bfloat162*>(y_bf16 + lo_off + c + 2) = __nv_bfloat162(l2, l3);
+      __nv_bfloat162 q0(l0, l1), q1(l2, l3);
+      *reinterpret_cast<uint2*>(y_bf16 + lo_off + c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&q0), *reinterpret_cast<uint32_t*>(&q1));
     }
   }
 }
@@ -340,7 +343,7 @@ extern "C" int hba_layernorm_fwd(const float* x, int64_t rows, int32_t cols, int
                                  int64_t lo_off, void* stream) {
   HBA_REQUIRE(x && gamma && beta && (y_f32 || y_bf16) && rows > 0, "hba_layernorm_fwd: bad arguments");
   HBA_REQUIRE(cols % 128 == 0 && cols <= 128 * kLnMaxVec, "hba_layernorm_fwd: cols=%d must be a multiple of 128 and <= %d", cols, 128 * kLnMaxVec);
-  HBA_REQUIRE(ldx % 4 == 0 && ld_yf % 4 == 0 && ld_yb % 2 == 0 && lo_off % 2 == 0, "hba_layernorm_fwd: leading dimensions must keep 16-byte alignment");
+  HBA_REQUIRE(ldx % 4 == 0 && ld_yf % 4 == 0 && ld_yb % 4 == 0 && lo_off % 4 == 0 && ((uintptr_t)y_bf16 & 7) == 0, "hba_layernorm_fwd: leading dimensions must keep 16-byte (fp32) / 8-byte (bf16) alignment");
   layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, rows, cols, ldx, row_step < 1 ? 1 : row_step, gamma, beta, eps, y_f32, ld_yf,
       static_cast<__nv_bfloat16*>(y_bf16), ld_yb, lo_off);
