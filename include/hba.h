@@ -244,6 +244,20 @@ int hba_layernorm_param_grad(const float* dy, int64_t ld_dy, const float* x, int
 int hba_attention_bwd(const void* qkv, int32_t qkv_dtype, int64_t ld_qkv, int32_t B, int32_t T,
                       int32_t H, int32_t causal, const void* d_out, int32_t do_dtype, int64_t ld_do,
                       void* d_qkv, int32_t dq_dtype, int64_t ld_dqkv, void* stream);
+/* Tensor-core (tcgen05) pair for the bf16 training step, T <= 256 (ViT-B/16: T = 197), all matrices
+ * bf16 with leading dimensions that are multiples of 8:
+ * hba_attention_fwd_lse: as hba_attention_fwd (out [B*T, H*64] bf16) and additionally writes
+ *   lse [B, H, T] fp32 = log2(sum_j exp(s_ij / 8)) (log2 domain), the only softmax statistic the
+ *   backward needs.
+ * hba_attention_bwd_lse: d_out [B*T, H*64] -> d_qkv [B*T, 3*H*64] from qkv, the forward's out and lse
+ *   (autograd of SDPA as reached by VIT:138-145; dS = P o (dP - rowsum(dO o O)), FlashAttention-2 form).
+ */
+int hba_attention_fwd_lse(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T, int32_t H,
+                          int32_t causal, void* out, int64_t ld_out, float* lse, void* stream);
+int hba_attention_bwd_lse(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T, int32_t H,
+                          int32_t causal, const void* out, int64_t ld_out, const void* d_out,
+                          int64_t ld_do, const float* lse, void* d_qkv, int64_t ld_dqkv,
+                          void* stream);
 
 /* misc elementwise helpers used by the host-side engine */
 int hba_add_rows(float* dst, int64_t ld_dst, int64_t dst_row_step, const float* src,

@@ -151,6 +151,40 @@ def test_attention_bwd_full(B, T, H, causal, mode):
     assert rel_err(dq.float(), want) < tol, rel_err(dq.float(), want)
 
 
+@pytest.mark.parametrize("B,T,H,causal", [(2, 197, 2, False), (3, 50, 1, False), (2, 77, 3, True), (1, 256, 2, False),
+                                          (4, 128, 1, False), (2, 16, 1, False), (2, 130, 1, True),
+                                          (27, 197, 12, False)])
+def test_attention_tensor_core_fwd_lse_bwd(B, T, H, causal):
+    """tcgen05 forward (+ lse) / backward pair of the bf16 training step against autograd on the fp64
+    formula; (27, 197, 12) gives every CTA of the persistent kernels more than one unit."""
+    hba, ops = _imports()
+    g = torch.Generator().manual_seed(B * 100 + T)
+    d = H * 64
+    qkv = (torch.randn(B * T, 3 * d, generator=g) * 0.7).to(torch.bfloat16)
+    do = torch.randn(B * T, d, generator=g).to(torch.bfloat16)
+    ref = qkv.double().requires_grad_(True)
+    q, k, v = ref.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if causal:
+        s = s + torch.full((T, T), float("-inf"), dtype=torch.float64).triu_(1)
+    o = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B * T, d)
+    o.backward(do.double())
+    want_lse = torch.logsumexp(s, -1) * 1.4426950408889634   # [B, H, T], log2 domain
+    out = torch.empty(B * T, d, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B * H * T, device=DEV)
+    dq = torch.full((B * T, 3 * d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.attention_fwd_lse(qkv.to(DEV), B, T, H, out, lse, causal=causal)
+    ops.attention_bwd_lse(qkv.to(DEV), B, T, H, out, do.to(DEV), lse, dq, causal=causal)
+    torch.cuda.synchronize()
+    assert rel_err(out.float(), o.detach()) < 1e-2
+    assert float((lse.cpu().double().view(B, H, T) - want_lse.detach()).abs().max()) < 2e-3
+    got, want = dq.float().cpu().double(), ref.grad
+    assert bool(torch.isfinite(got).all())
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        e = rel_err(got[:, sl], want[:, sl])
+        assert e < 1.5e-2, (name, e)
+
+
 def _pair(seed=3, num_classes=10):
     from hba import vit
     from oracle import vit_ref

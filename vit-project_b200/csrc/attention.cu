@@ -382,8 +382,11 @@ __global__ void __launch_bounds__(kR0Threads)
 }
 
 int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
-                        __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of,
+                        __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of, float* lse,
                         cudaStream_t stream);
+int attention_bwd_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
+                            const __nv_bfloat16* o, int64_t ld_o, const __nv_bfloat16* d_out, int64_t ld_do,
+                            const float* lse, __nv_bfloat16* d_qkv, int64_t ld_dqkv, cudaStream_t stream);
 
 template <typename T>
 static int attention_fwd_dispatch(const T* qkv, int64_t ld_qkv, int B, int Tn, int H, int causal,
@@ -437,7 +440,7 @@ extern "C" int hba_attention_fwd(const void* qkv, int32_t qkv_dtype, int64_t ld_
   if (qkv_dtype == HBA_DT_BF16 && !first_row_only && lo_off == 0 && T <= 257 && ld_qkv % 8 == 0 &&
       (!out || ld_out % 8 == 0) && (!out_f32 || ld_of % 4 == 0) && getenv("HBA_ATTN_SIMT") == nullptr)
     return attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, causal,
-                               static_cast<__nv_bfloat16*>(out), ld_out, out_f32, ld_of, s);
+                               static_cast<__nv_bfloat16*>(out), ld_out, out_f32, ld_of, nullptr, s);
   if (qkv_dtype == HBA_DT_BF16)
     return attention_fwd_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B,
                                                  T, H, causal, first_row_only,
@@ -466,4 +469,27 @@ extern "C" int hba_attention_bwd_row0(const void* qkv, int32_t qkv_dtype, int64_
     return HBA_ERR_ARG;
   }
   return check_launch("attention_row0_bwd_kernel");
+}
+
+extern "C" int hba_attention_fwd_lse(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T, int32_t H,
+                                     int32_t causal, void* out, int64_t ld_out, float* lse, void* stream) {
+  HBA_REQUIRE(qkv && out && lse && B > 0 && T > 0 && H > 0, "hba_attention_fwd_lse: bad arguments");
+  HBA_REQUIRE(T <= 257 && ld_qkv % 8 == 0 && ld_out % 8 == 0, "hba_attention_fwd_lse: T=%d (max 257) / leading dimensions unsupported", T);
+  return attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, causal,
+                             static_cast<__nv_bfloat16*>(out), ld_out, nullptr, 0, lse,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hba_attention_bwd_lse(const void* qkv, int64_t ld_qkv, int32_t B, int32_t T, int32_t H,
+                                     int32_t causal, const void* o, int64_t ld_o, const void* d_out,
+                                     int64_t ld_do, const float* lse, void* d_qkv, int64_t ld_dqkv,
+                                     void* stream) {
+  HBA_REQUIRE(qkv && o && d_out && lse && d_qkv && B > 0 && T > 0 && H > 0, "hba_attention_bwd_lse: bad arguments");
+  HBA_REQUIRE(T <= 256, "hba_attention_bwd_lse: T=%d exceeds 256", T);
+  HBA_REQUIRE(ld_qkv % 8 == 0 && ld_o % 8 == 0 && ld_do % 8 == 0 && ld_dqkv % 8 == 0,
+              "hba_attention_bwd_lse: leading dimensions must be multiples of 8");
+  return attention_bwd_tc_launch(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, B, T, H, causal,
+                                 static_cast<const __nv_bfloat16*>(o), ld_o,
+                                 static_cast<const __nv_bfloat16*>(d_out), ld_do, lse,
+                                 static_cast<__nv_bfloat16*>(d_qkv), ld_dqkv, static_cast<cudaStream_t>(stream));
 }

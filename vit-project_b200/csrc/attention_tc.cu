@@ -133,6 +133,7 @@ struct AttnTcArgs {
   float scale_log2;  // log2(e) / sqrt(64)
   const __nv_bfloat16* qkv;
   int64_t ld_qkv;
+  float* lse;        // optional [B, H, T]: log2-domain log-sum-exp per row (P = 2^(s*scale - lse)), for the backward
   long long* trace;  // debug: per-item phase time stamps of CTA 0 (hba_debug_attention_trace), else null
 };
 
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (lane == 0) mbar_arrive(&p_full[grp]);
       const float p_extra = extra_valid ? ex2_approx(fmaf(s_extra, g.scale_log2, -mxs)) : 0.f;
       sum += p_extra;
+      if (g.lse && qi < g.T) g.lse[((int64_t)b * g.H + h) * g.T + qi] = mxs + __log2f(sum);
       // ---- O epilogue ----
       mbar_wait(&o_full[grp], use & 1);
       tc_fence_after();
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (j < kTcMaxRows) asm volatile("st.shared.f32 [%0], %1;" ::"r"(pbuf + 4 * j), "f"(p) : "memory");
           }
           sum = warp_sum(sum);
+          if (g.lse && lane == 0) g.lse[((int64_t)b * g.H + h) * g.T + qi] = mxs + __log2f(sum);
           __syncwarp();
           float a0 = 0.f, a1 = 0.f;
           for (int j = 0; j <= last_key; ++j) {
@@ -534,7 +537,7 @@ static long long* g_attn_trace = nullptr;
 
 // host launcher, called from hba_attention_fwd (attention.cu) for bf16 activations
 int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
-                        __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of,
+                        __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of, float* lse,
                         cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -571,6 +574,7 @@ int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, 
   g.scale_log2 = 1.4426950408889634f * 0.125f;
   g.qkv = qkv, g.ld_qkv = ld_qkv;
   g.trace = g_attn_trace;
+  g.lse = lse;
   CUtensorMap t128, t16;
   const uint64_t rows = (uint64_t)B * T, cols = (uint64_t)3 * H * kTcHd;
   HBA_CHECK(make_tma_2d_bf16(&t128, qkv, rows, cols, ld_qkv, 128, 64));

@@ -282,6 +282,23 @@ def attention_bwd(qkv, B, T, H, d_out, d_qkv, causal=False):
                                         d_qkv.stride(0), _stream()), "hba_attention_bwd")
 
 
+def attention_fwd_lse(qkv, B, T, H, out, lse, causal=False):
+    """bf16 tensor-core forward that also writes lse [B, H, T] (log2 domain) for attention_bwd_lse."""
+    assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and lse.dtype == torch.float32
+    assert lse.is_contiguous() and lse.numel() >= B * H * T
+    check(_lib.load().hba_attention_fwd_lse(_p(qkv), qkv.stride(0), B, T, H, 1 if causal else 0, _p(out),
+                                            out.stride(0), _p(lse), _stream()), "hba_attention_fwd_lse")
+
+
+def attention_bwd_lse(qkv, B, T, H, out, d_out, lse, d_qkv, causal=False):
+    for t in (qkv, out, d_out, d_qkv):
+        assert t.dtype == torch.bfloat16
+    assert lse.dtype == torch.float32 and lse.is_contiguous()
+    check(_lib.load().hba_attention_bwd_lse(_p(qkv), qkv.stride(0), B, T, H, 1 if causal else 0, _p(out),
+                                            out.stride(0), _p(d_out), d_out.stride(0), _p(lse), _p(d_qkv),
+                                            d_qkv.stride(0), _stream()), "hba_attention_bwd_lse")
+
+
 def add_rows(dst, src, rows, cols, dst_row_step=1):
     check(_lib.load().hba_add_rows(_p(dst), dst.stride(0), dst_row_step, _p(src), src.stride(0), rows,
                                    cols, _stream()), "hba_add_rows")

@@ -215,7 +215,10 @@ class ViTEngine:
                 ops.gemm(ln1, self._wops[f"{i}.qkv"], M, bias=blk.attn.qkv.bias.detach(),
                          out=Operand(qkv, M, 3 * d, 0))
             att = self._opbuf(tag + "att", M, d)
-            ops.attention_fwd(qkv, B, T, H, out=att)
+            if sp or not save or T > 256:
+                ops.attention_fwd(qkv, B, T, H, out=att)
+            else:  # tensor-core pair: the forward also leaves the softmax statistic for the backward
+                ops.attention_fwd_lse(qkv, B, T, H, att.buf, self._buf(tag + "lse", (B * H * T,)))
             x_mid = self._buf(tag + "xmid", (M, d))
             ops.gemm(att, self._wops[f"{i}.proj"], M, bias=blk.attn.proj.bias.detach(), residual=x, out_f32=x_mid)
             ln2 = self._opbuf(tag + "ln2", M, d)
@@ -353,7 +356,11 @@ class ViTEngine:
                 d_att = self._buf("d_att", (M, d), torch.bfloat16)
                 ops.gemm(gy, self._wops[f"{i}.proj"], M, b_mn=True, out=Operand(d_att, M, d, 0))
                 g_qkv = self._opbuf("g_qkv", M, 3 * d)
-                ops.attention_bwd(qkv, B, T, H, d_att, g_qkv.buf)
+                if T > 256:
+                    ops.attention_bwd(qkv, B, T, H, d_att, g_qkv.buf)
+                else:
+                    ops.attention_bwd_lse(qkv, B, T, H, att.buf, d_att, self._buf(tag + "lse", (B * H * T,)),
+                                          g_qkv.buf)
                 ops.colsum(g_qkv.buf, G(blk.attn.qkv.bias), cs_ws)
             ops.gemm(g_qkv, ln1, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.qkv.weight))
             ops.gemm(g_qkv, self._wops[f"{i}.qkv"], M, b_mn=True, out_f32=d_ln)
