@@ -241,6 +241,15 @@ int hba_colsum(const void* x, int32_t dtype, int64_t rows, int32_t cols, int64_t
 int hba_layernorm_param_grad(const float* dy, int64_t ld_dy, const float* x, int64_t rows,
                              int32_t cols, int64_t ldx, int64_t row_step, float eps,
                              float* dgamma_dbeta, int32_t accumulate, float* workspace, void* stream);
+/* Fused LayerNorm backward of the trained ViT: dx (+)= LN'(dy), optional bf16 hi[/lo] copy of the
+ * resulting dx (operand of the next GEMMs), dgamma_dbeta [2*cols] (+)=, and dx_colsum [cols] = column
+ * sums of the resulting dx (bias gradient of the Linear feeding this residual stream); one pass over
+ * HBM.  cols in {128, 256, 512, 768, 1024}; workspace >= 2 * #SM * 3 * cols floats. */
+int hba_layernorm_bwd_fused(const float* dy, int64_t ld_dy, const float* x, int64_t rows,
+                            int32_t cols, int64_t ldx, const float* gamma, float eps, float* dx,
+                            int64_t ld_dx, int32_t accumulate, void* dx_bf16, int64_t ld_b,
+                            int64_t lo_off, float* dgamma_dbeta, int32_t accumulate_params,
+                            float* dx_colsum, float* workspace, void* stream);
 int hba_attention_bwd(const void* qkv, int32_t qkv_dtype, int64_t ld_qkv, int32_t B, int32_t T,
                       int32_t H, int32_t causal, const void* d_out, int32_t do_dtype, int64_t ld_do,
                       void* d_qkv, int32_t dq_dtype, int64_t ld_dqkv, void* stream);

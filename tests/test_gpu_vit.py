@@ -151,6 +151,38 @@ def test_attention_bwd_full(B, T, H, causal, mode):
     assert rel_err(dq.float(), want) < tol, rel_err(dq.float(), want)
 
 
+@pytest.mark.parametrize("rows,cols,accumulate,lo", [(1000, 768, True, False), (37, 128, False, True),
+                                                     (5000, 1024, True, False), (9, 256, True, True)])
+def test_layernorm_bwd_fused(rows, cols, accumulate, lo):
+    """dx, its bf16 hi/lo copy, dgamma|dbeta and colsum(dx) of the one-pass kernel vs the fp64 formulas."""
+    hba, ops = _imports()
+    g = torch.Generator().manual_seed(rows + cols)
+    eps = 1e-6
+    x = (torch.randn(rows, cols, generator=g) * 2 + 0.5).to(DEV)
+    dy = torch.randn(rows, cols, generator=g).to(DEV)
+    gamma = (torch.rand(cols, generator=g) + 0.5).to(DEV)
+    dx0 = torch.randn(rows, cols, generator=g).to(DEV)
+    xd = x.double().requires_grad_(True)
+    gd = gamma.double().requires_grad_(True)
+    bd = torch.zeros(cols, dtype=torch.float64, device=DEV, requires_grad=True)
+    torch.nn.functional.layer_norm(xd, (cols,), gd, bd, eps).backward(dy.double())
+    want_dx = xd.grad + (dx0.double() if accumulate else 0)
+    dx = dx0.clone()
+    op = ops.Operand.empty(rows, cols, lo, DEV)
+    dgb = torch.empty(2 * cols, device=DEV)
+    cs = torch.empty(cols, device=DEV)
+    ws = torch.empty(2 * 148 * 3 * cols, device=DEV)
+    ops.layernorm_bwd_fused(dy, x, rows, cols, gamma, eps, dx, dgb, ws, accumulate=accumulate, dx_op=op,
+                            dx_colsum=cs)
+    torch.cuda.synchronize()
+    assert rel_err(dx, want_dx) < 2e-5
+    assert rel_err(dgb[:cols], gd.grad) < 2e-5 and rel_err(dgb[cols:], bd.grad) < 2e-5
+    scale = float(want_dx.abs().sum(0).max())
+    assert float((cs.double() - want_dx.sum(0)).abs().max()) < 1e-5 * scale
+    got = op.buf[:, :cols].float() + (op.buf[:, cols:2 * cols].float() if lo else 0)
+    assert rel_err(got, want_dx) < (2e-5 if lo else 5e-3)
+
+
 @pytest.mark.parametrize("B,T,H,causal", [(2, 197, 2, False), (3, 50, 1, False), (2, 77, 3, True), (1, 256, 2, False),
                                           (4, 128, 1, False), (2, 16, 1, False), (2, 130, 1, True),
                                           (27, 197, 12, False)])

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--model", default="vit_base_patch16_224")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -56,10 +58,15 @@ def main():
     torch.cuda.synchronize()
     c0 = ops.COUNTERS["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.profile:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(a.steps):
         loss, _ = tr.step(images, labels)
     e1.record()
+    if a.profile:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()

@@ -86,12 +86,29 @@ __device__ __forceinline__ float quickgelu_grad(float a) {
   const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * a));
   return s * (1.0f + 1.702f * a * (1.0f - s));
 }
+// erf-GELU (timm / nn.GELU default, VIT:283) and its derivative.  erf(|x|) = 1 - poly5(t) exp(-x^2),
+// t = 1 / (1 + p |x|) (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 = fp32 epsilon): one ex2.approx and
+// one rcp.approx on the SFU plus 8 FMAs, and the exponential is the very one the derivative's
+// density term needs.  erff() + expf() made the dX GEMM of fc2 epilogue-bound (858 us vs 250 us).
+__device__ __forceinline__ float erf_abs(float ax, float e /* exp(-ax^2) */) {
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return fmaf(-p * t, e, 1.0f);
+}
 __device__ __forceinline__ float gelu_erf(float v) {
-  return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  const float x = v * 0.70710678118654752f;
+  const float e = __expf(-x * x);
+  const float er = copysignf(erf_abs(fabsf(x), e), v);
+  return 0.5f * v * (1.0f + er);
 }
 __device__ __forceinline__ float gelu_erf_grad(float a) {
-  return 0.5f * (1.0f + erff(a * 0.70710678118654752f)) +
-         a * 0.39894228040143268f * expf(-0.5f * a * a);
+  const float x = a * 0.70710678118654752f;
+  const float e = __expf(-x * x);  // = exp(-a^2 / 2)
+  const float er = copysignf(erf_abs(fabsf(x), e), a);
+  return fmaf(a * 0.39894228040143268f, e, 0.5f * (1.0f + er));
 }
 
 // transposed store (C^T) for one thread: row `row`, 32 consecutive columns starting at `col`; for a

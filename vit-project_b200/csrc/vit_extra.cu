@@ -107,6 +107,139 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused LayerNorm backward of the fully-trained ViT (replaces five passes over the [rows, cols]
+// gradients: statistics, dx, dgamma / dbeta partials, the bf16 copy of dx that feeds the next GEMMs and
+// the column sums of dx = the bias gradient of the Linear in front of the LayerNorm's input):
+//   dx (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//   part[block][0:cols] = sum dy * xhat, [cols:2cols] = sum dy, [2cols:3cols] = sum dx (after +=)
+// One warp per row, rows cyclic over all warps of the grid; every lane keeps its NVEC*4 columns of the
+// three column sums in registers over all its rows (deterministic: fixed row -> warp assignment,
+// fixed reduction order).  HBM traffic: read dy, x (, dx) + write dx fp32 (, bf16) - one pass.
+template <int NVEC>
+__global__ void __launch_bounds__(256)
+    layernorm_bwd_fused_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ x,
+                               int64_t rows, int64_t ldx, const float* __restrict__ gamma, float eps,
+                               float* dx, int64_t ld_dx, int accumulate, __nv_bfloat16* __restrict__ dx_bf16,
+                               int64_t ld_b, int64_t lo_off, float* __restrict__ part) {
+  constexpr int cols = NVEC * 128;
+  __shared__ float red[3 * cols];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[NVEC], ab[NVEC], ac[NVEC];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gm[NVEC];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += stride) {
+    const float* xr = x + row * ldx;
+    const float* dyr = dy + row * ld_dy;
+    float* dxr = dx + row * ld_dx;
+    float4 v[NVEC], d[NVEC], pv[NVEC];
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) d[i] = *reinterpret_cast<const float4*>(dyr + (i * 32 + lane) * 4);
+    if (accumulate) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) pv[i] = *reinterpret_cast<const float4*>(dxr + (i * 32 + lane) * 4);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * (1.0f / cols);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / cols) + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      v[i].x *= rstd, v[i].y *= rstd, v[i].z *= rstd, v[i].w *= rstd;  // xhat
+      ag[i].x += d[i].x * v[i].x, ag[i].y += d[i].y * v[i].y, ag[i].z += d[i].z * v[i].z, ag[i].w += d[i].w * v[i].w;
+      ab[i].x += d[i].x, ab[i].y += d[i].y, ab[i].z += d[i].z, ab[i].w += d[i].w;
+      d[i].x *= gm[i].x, d[i].y *= gm[i].y, d[i].z *= gm[i].z, d[i].w *= gm[i].w;  // g
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
+    }
+    s1 = warp_sum(s1) * (1.0f / cols);
+    s2 = warp_sum(s2) * (1.0f / cols);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (d[i].x - s1 - v[i].x * s2);
+      o.y = rstd * (d[i].y - s1 - v[i].y * s2);
+      o.z = rstd * (d[i].z - s1 - v[i].z * s2);
+      o.w = rstd * (d[i].w - s1 - v[i].w * s2);
+      if (accumulate) o.x += pv[i].x, o.y += pv[i].y, o.z += pv[i].z, o.w += pv[i].w;
+      *reinterpret_cast<float4*>(dxr + c) = o;
+      ac[i].x += o.x, ac[i].y += o.y, ac[i].z += o.z, ac[i].w += o.w;
+      if (dx_bf16) {
+        __nv_bfloat16* b = dx_bf16 + row * ld_b + c;
+        const uint32_t h0 = pack_bf16x2(o.x, o.y), h1 = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(b) = make_uint2(h0, h1);
+        if (lo_off > 0) {
+          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h0));
+          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h1));
+          *reinterpret_cast<uint2*>(b + lo_off) =
+              make_uint2(pack_bf16x2(o.x - f0.x, o.y - f0.y), pack_bf16x2(o.z - f1.x, o.w - f1.y));
+        }
+      }
+    }
+  }
+  // block reduction in a fixed order: warp 0 stores, warps 1..7 add one after the other
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        float4* r0 = reinterpret_cast<float4*>(red + (i * 32 + lane) * 4);
+        float4* r1 = reinterpret_cast<float4*>(red + cols + (i * 32 + lane) * 4);
+        float4* r2 = reinterpret_cast<float4*>(red + 2 * cols + (i * 32 + lane) * 4);
+        if (w == 0) {
+          *r0 = ag[i], *r1 = ab[i], *r2 = ac[i];
+        } else {
+          float4 t = *r0;
+          t.x += ag[i].x, t.y += ag[i].y, t.z += ag[i].z, t.w += ag[i].w;
+          *r0 = t;
+          t = *r1;
+          t.x += ab[i].x, t.y += ab[i].y, t.z += ab[i].z, t.w += ab[i].w;
+          *r1 = t;
+          t = *r2;
+          t.x += ac[i].x, t.y += ac[i].y, t.z += ac[i].z, t.w += ac[i].w;
+          *r2 = t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < 3 * cols; c += 256) part[(size_t)blockIdx.x * 3 * cols + c] = red[c];
+}
+
+// out_dgb[0:2cols] (+)= sum_b part[b][0:2cols]; out_cs[0:cols] = sum_b part[b][2cols:3cols]
+__global__ void ln_fused_final_kernel(const float* __restrict__ part, int nblocks, int cols,
+                                      float* __restrict__ out_dgb, int accumulate,
+                                      float* __restrict__ out_cs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 3 * cols) return;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= nblocks; k += 4) {
+    t0 += part[(size_t)k * 3 * cols + c];
+    t1 += part[(size_t)(k + 1) * 3 * cols + c];
+    t2 += part[(size_t)(k + 2) * 3 * cols + c];
+    t3 += part[(size_t)(k + 3) * 3 * cols + c];
+  }
+  for (; k < nblocks; ++k) t0 += part[(size_t)k * 3 * cols + c];
+  const float t = (t0 + t1) + (t2 + t3);
+  if (c < 2 * cols) out_dgb[c] = accumulate ? out_dgb[c] + t : t;
+  else if (out_cs) out_cs[c - 2 * cols] = t;
+}
+
+// ------------------------------------------------------------------------------------------
 // Full attention backward (CUDA cores, fp32 math), one CTA per (sequence, head), head_dim 64.
 //   P = softmax(Q K^T / 8 [+causal]); dP = dO V^T; D_i = sum_j P_ij dP_ij; dS = P (dP - D) / 8
 //   dQ = dS K; dK = dS^T Q; dV = P^T dO
@@ -341,4 +474,37 @@ extern "C" int hba_attention_bwd(const void* qkv, int32_t qkv_dtype, int64_t ld_
     return launch_attention_bwd<float, float, float>(qkv, ld_qkv, B, T, H, causal, d_out, ld_do, d_qkv, ld_dqkv, s);
   set_error("hba_attention_bwd: unsupported dtype combination (%d, %d, %d)", qkv_dtype, do_dtype, dq_dtype);
   return HBA_ERR_ARG;
+}
+
+extern "C" int hba_layernorm_bwd_fused(const float* dy, int64_t ld_dy, const float* x, int64_t rows,
+                                       int32_t cols, int64_t ldx, const float* gamma, float eps,
+                                       float* dx, int64_t ld_dx, int32_t accumulate, void* dx_bf16,
+                                       int64_t ld_b, int64_t lo_off, float* dgamma_dbeta,
+                                       int32_t accumulate_params, float* dx_colsum, float* workspace,
+                                       void* stream) {
+  HBA_REQUIRE(dy && x && gamma && dx && dgamma_dbeta && workspace && rows > 0, "hba_layernorm_bwd_fused: bad arguments");
+  HBA_REQUIRE(ldx % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && ld_b % 4 == 0 && lo_off % 4 == 0,
+              "hba_layernorm_bwd_fused: leading dimensions must be multiples of 4");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int blocks = 2 * num_sms();
+  if ((int64_t)blocks * 8 > rows) blocks = (int)((rows + 7) / 8);
+  __nv_bfloat16* b = static_cast<__nv_bfloat16*>(dx_bf16);
+#define HBA_LN_FUSED(NV)                                                                            \
+  layernorm_bwd_fused_kernel<NV><<<blocks, 256, 0, s>>>(dy, ld_dy, x, rows, ldx, gamma, eps, dx, ld_dx, \
+                                                        accumulate, b, ld_b, lo_off, workspace)
+  switch (cols) {
+    case 128: HBA_LN_FUSED(1); break;
+    case 256: HBA_LN_FUSED(2); break;
+    case 512: HBA_LN_FUSED(4); break;
+    case 768: HBA_LN_FUSED(6); break;
+    case 1024: HBA_LN_FUSED(8); break;
+    default:
+      set_error("hba_layernorm_bwd_fused: cols=%d (supported: 128, 256, 512, 768, 1024)", cols);
+      return HBA_ERR_ARG;
+  }
+#undef HBA_LN_FUSED
+  HBA_CHECK(check_launch("layernorm_bwd_fused_kernel"));
+  ln_fused_final_kernel<<<(3 * cols + 255) / 256, 256, 0, s>>>(workspace, blocks, cols, dgamma_dbeta,
+                                                             accumulate_params, dx_colsum);
+  return check_launch("ln_fused_final_kernel");
 }

@@ -66,6 +66,8 @@ SIGNATURES = {
     "hba_colsum": (i32, [vp, i32, i64, i32, i64, vp, i32, vp, vp]),
     "hba_layernorm_param_grad": (i32, [vp, i64, vp, i64, i32, i64, i64, f32, vp, i32, vp, vp]),
     "hba_attention_bwd": (i32, [vp, i32, i64, i32, i32, i32, i32, vp, i32, i64, vp, i32, i64, vp]),
+    "hba_layernorm_bwd_fused": (i32, [vp, i64, vp, i64, i32, i64, vp, f32, vp, i64, i32, vp, i64, i64, vp, i32, vp,
+                                      vp, vp]),
     "hba_attention_fwd_lse": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, vp, vp]),
     "hba_attention_bwd_lse": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp]),
     "hba_add_rows": (i32, [vp, i64, i64, vp, i64, i64, i32, vp]),

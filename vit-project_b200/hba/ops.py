@@ -282,6 +282,17 @@ def attention_bwd(qkv, B, T, H, d_out, d_qkv, causal=False):
                                         d_qkv.stride(0), _stream()), "hba_attention_bwd")
 
 
+def layernorm_bwd_fused(dy, x, rows, cols, gamma, eps, dx, dgamma_dbeta, workspace, *, accumulate=False,
+                        dx_op: Operand = None, dx_colsum=None, accumulate_params=False):
+    """One pass: dx (+)= LN backward, bf16 operand copy of dx, dgamma|dbeta, column sums of dx."""
+    assert workspace.numel() >= 2 * 148 * 3 * cols
+    check(_lib.load().hba_layernorm_bwd_fused(
+        _p(dy), dy.stride(0), _p(x), rows, cols, x.stride(0), _p(gamma), eps, _p(dx), dx.stride(0),
+        1 if accumulate else 0, _p(dx_op.buf) if dx_op is not None else None,
+        dx_op.ld if dx_op is not None else 0, dx_op.lo_off if dx_op is not None else 0, _p(dgamma_dbeta),
+        1 if accumulate_params else 0, _p(dx_colsum), _p(workspace), _stream()), "hba_layernorm_bwd_fused", 2)
+
+
 def attention_fwd_lse(qkv, B, T, H, out, lse, causal=False):
     """bf16 tensor-core forward that also writes lse [B, H, T] (log2 domain) for attention_bwd_lse."""
     assert qkv.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and lse.dtype == torch.float32

@@ -315,6 +315,26 @@ class ViTEngine:
         ops.add_rows(dx, dx_cls, B, d, dst_row_step=T)
         ready("head")
         # ---- blocks, last to first
+        lnf_ws = self._buf("lnf_ws", (2 * 148 * 3 * d,))
+        cs_scratch = self._buf("cs_scratch", (d,))
+
+        def ln_backward(d_ln, x_saved, norm, gy, colsum_out):
+            """dx += LN'(d_ln); gy = bf16(dx); norm.weight / norm.bias grads; colsum_out = colsum(dx)."""
+            gw, gb = G(norm.weight), G(norm.bias)
+            if gb.data_ptr() == gw.data_ptr() + 4 * d:
+                dgb_out = self.flat_grad[(gw.data_ptr() - self.flat_grad.data_ptr()) // 4:][:2 * d]
+            else:
+                dgb_out = dgb
+            ops.layernorm_bwd_fused(d_ln, x_saved, M, d, norm.weight.detach(), LN_EPS, dx, dgb_out, lnf_ws,
+                                    accumulate=True, dx_op=gy, dx_colsum=colsum_out)
+            if dgb_out is dgb:
+                gw.copy_(dgb[:d])
+                gb.copy_(dgb[d:])
+
+        gy = self._opbuf("gy", M, d)
+        ops.split_bf16(dx, gy)
+        last = len(m.blocks) - 1
+        ops.colsum(dx, G(m.blocks[last].mlp.fc2.bias), cs_ws)
         for i in reversed(range(len(m.blocks))):
             blk, tag = m.blocks[i], f"b{i}."
             x_in = self._buf(f"b{i - 1}.xout", (M, d)) if i > 0 else self._buf("x0", (M, d))
@@ -322,11 +342,8 @@ class ViTEngine:
             ln1, ln2 = self._opbuf(tag + "ln1", M, d), self._opbuf(tag + "ln2", M, d)
             att, hid = self._opbuf(tag + "att", M, d), self._opbuf(tag + "hid", M, 4 * d)
             qkv = self._buf(tag + "qkv", (M, 3 * d), adt)
-            # fc2
-            gy = self._opbuf("gy", M, d)
-            ops.split_bf16(dx, gy)
+            # fc2 (gy = bf16 of dx and the fc2 bias gradient come from the previous fused LN backward)
             ops.gemm(gy, hid, a_mn=True, b_mn=True, K=M, out_f32=G(blk.mlp.fc2.weight))
-            ops.colsum(dx, G(blk.mlp.fc2.bias), cs_ws)
             g_hid = self._opbuf("g_hid", M, 4 * d)
             g_hid_f = self._buf("g_hid_f", (M, 4 * d)) if sp else None
             ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
@@ -336,14 +353,9 @@ class ViTEngine:
             ops.colsum(g_hid_f if sp else g_hid.buf, G(blk.mlp.fc1.bias), cs_ws)
             d_ln = self._buf("d_ln", (M, d))
             ops.gemm(g_hid, self._wops[f"{i}.fc1"], M, b_mn=True, out_f32=d_ln)
-            ops.layernorm_param_grad(d_ln, x_mid, M, d, LN_EPS, dgb, ln_ws)
-            G(blk.norm2.weight).copy_(dgb[:d])
-            G(blk.norm2.bias).copy_(dgb[d:])
-            ops.layernorm_bwd(d_ln, x_mid, M, d, blk.norm2.weight.detach(), LN_EPS, dx, accumulate=True)
+            ln_backward(d_ln, x_mid, blk.norm2, gy, G(blk.attn.proj.bias))
             # attention projection
-            ops.split_bf16(dx, gy)
             ops.gemm(gy, att, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.proj.weight))
-            ops.colsum(dx, G(blk.attn.proj.bias), cs_ws)
             if sp:
                 d_att = self._buf("d_att_f", (M, d))
                 ops.gemm(gy, self._wops[f"{i}.proj"], M, b_mn=True, out_f32=d_att)
@@ -364,10 +376,7 @@ class ViTEngine:
                 ops.colsum(g_qkv.buf, G(blk.attn.qkv.bias), cs_ws)
             ops.gemm(g_qkv, ln1, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.qkv.weight))
             ops.gemm(g_qkv, self._wops[f"{i}.qkv"], M, b_mn=True, out_f32=d_ln)
-            ops.layernorm_param_grad(d_ln, x_in, M, d, LN_EPS, dgb, ln_ws)
-            G(blk.norm1.weight).copy_(dgb[:d])
-            G(blk.norm1.bias).copy_(dgb[d:])
-            ops.layernorm_bwd(d_ln, x_in, M, d, blk.norm1.weight.detach(), LN_EPS, dx, accumulate=True)
+            ln_backward(d_ln, x_in, blk.norm1, gy, G(m.blocks[i - 1].mlp.fc2.bias) if i > 0 else cs_scratch)
             ready(f"block{i}")
         # ---- embedding: pos / cls / patch projection
         pos_g = G(m.pos_embed).view(T * d)
