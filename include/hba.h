@@ -90,6 +90,10 @@ typedef struct hba_gemm_params {
   int32_t max_ctas; /* 0 = one persistent CTA per SM */
   int32_t a_mn_major; /* A stored as [K, lda] (M contiguous): C = A^T-layout product, no transpose pass */
   int32_t b_mn_major; /* B stored as [K, ldb] (N contiguous), e.g. dX = dY . W with W [out, in] as is */
+  int32_t k_slices;   /* > 1: split-K for weight-gradient shapes (few output tiles, K = rows of the batch):
+                         every (tile, K slice) is a work item; the slices are summed in a fixed order
+                         (deterministic).  Needs k_workspace and a plain out_f32 epilogue, N % 4 == 0 */
+  float* k_workspace; /* >= k_slices * M * N floats, 16-byte aligned */
 } hba_gemm_params;
 
 int hba_gemm_bf16(const hba_gemm_params* p, void* stream);

@@ -85,6 +85,41 @@ def test_gemm_mn_major_and_ragged_k(M, N, K, a_mn, b_mn, split):
     assert rel_err(out, want) < tol, (rel_err(out, want), tol)
 
 
+@pytest.mark.parametrize("M,N,K,slices", [(768, 768, 5000, 7), (768, 3072, 2048, 2), (256, 128, 1000, 16),
+                                          (1000, 768, 777, "auto"), (768, 768, 50432, "auto")])
+@pytest.mark.parametrize("split", [False, True])
+def test_gemm_split_k(M, N, K, slices, split):
+    """dW = dY^T X with the K range split into slices (deterministic fixed-order reduction): equal to
+    the exact product of the bf16 operands and bit-identical from run to run."""
+    hba, ops = _imports()
+    g = torch.Generator().manual_seed(M + N + K)
+    pad8 = lambda n: (n + 7) // 8 * 8
+    at = torch.zeros(K, pad8(M), device=DEV)
+    at[:, :M] = torch.randn(K, M, generator=g).to(DEV)
+    bt = torch.zeros(K, pad8(N), device=DEV)
+    bt[:, :N] = torch.randn(K, N, generator=g).to(DEV)
+    A = make_operand(ops, at, split)
+    A = ops.Operand(A.buf, K, M, A.lo_off)
+    Bo = make_operand(ops, bt, split)
+    Bo = ops.Operand(Bo.buf, K, N, Bo.lo_off)
+    ws = torch.empty(16 * M * N, device=DEV)
+    outs = []
+    for _ in range(2):
+        out = torch.full((M, N), float("nan"), device=DEV)
+        ops.gemm(A, Bo, a_mn=True, b_mn=True, K=K, out_f32=out, k_slices=slices, k_workspace=ws)
+        outs.append(out)
+    ref = torch.empty(M, N, device=DEV)
+    ops.gemm(A, Bo, a_mn=True, b_mn=True, K=K, out_f32=ref)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    if split:
+        want, tol = at[:, :M].double().t() @ bt[:, :N].double(), 4e-5   # bf16x3 drops lo.lo (~2^-16 per product)
+    else:
+        want, tol = operand_value(A, K, M).t() @ operand_value(Bo, K, N), 2e-6 * math.sqrt(K)
+    assert rel_err(outs[0], want) < tol, (rel_err(outs[0], want), tol)
+    assert rel_err(outs[0], ref) < 2e-6 * math.sqrt(K)   # same products, different fp32 summation order
+
+
 @pytest.mark.parametrize("rows,cols", [(1, 128), (777, 768), (5000, 1000), (50432, 768)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_colsum(rows, cols, dtype):

@@ -74,6 +74,8 @@ struct GemmArgs {
   int ld_bf16, out_lo_off;
   int transpose_out;
   int a_mn, b_mn;  // operand stored MN-major: [K rows, M (resp. N) columns]
+  int k_slices;    // split-K: work item = (tile, K slice); slice s writes out_f32 + s * slice_stride
+  size_t slice_stride;
   int debug;       // HBA_GEMM_DEBUG (measurement only): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA loads
 };
 
@@ -90,25 +92,32 @@ __device__ __forceinline__ float quickgelu_grad(float a) {
 // t = 1 / (1 + p |x|) (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 = fp32 epsilon): one ex2.approx and
 // one rcp.approx on the SFU plus 8 FMAs, and the exponential is the very one the derivative's
 // density term needs.  erff() + expf() made the dX GEMM of fc2 epilogue-bound (858 us vs 250 us).
-__device__ __forceinline__ float erf_abs(float ax, float e /* exp(-ax^2) */) {
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return fmaf(-p * t, e, 1.0f);
+// h(v) = 0.5 * erfc(|v| / sqrt 2): Phi(v) = h for v < 0, 1 - h for v > 0.  `e` = exp(-v^2 / 2).
+__device__ __forceinline__ float half_erfc_abs(float av, float e) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, av, 1.0f)));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return p * t * e;
 }
+__device__ __forceinline__ float exp_neg_half_sq(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * v * -0.72134752044448170f));  // -0.5 * log2(e)
+  return e;
+}
+// gelu(v) = v Phi(v) = relu(v) - |v| h(v)
 __device__ __forceinline__ float gelu_erf(float v) {
-  const float x = v * 0.70710678118654752f;
-  const float e = __expf(-x * x);
-  const float er = copysignf(erf_abs(fabsf(x), e), v);
-  return 0.5f * v * (1.0f + er);
+  const float av = fabsf(v);
+  return fmaf(-av, half_erfc_abs(av, exp_neg_half_sq(v)), fmaxf(v, 0.0f));
 }
+// gelu'(a) = Phi(a) + a phi(a)
 __device__ __forceinline__ float gelu_erf_grad(float a) {
-  const float x = a * 0.70710678118654752f;
-  const float e = __expf(-x * x);  // = exp(-a^2 / 2)
-  const float er = copysignf(erf_abs(fabsf(x), e), a);
-  return fmaf(a * 0.39894228040143268f, e, 0.5f * (1.0f + er));
+  const float e = exp_neg_half_sq(a);
+  const float h = half_erfc_abs(fabsf(a), e);
+  const float phi_cdf = a > 0.0f ? 1.0f - h : h;
+  return fmaf(a * 0.39894228040143268f, e, phi_cdf);
 }
 
 // transposed store (C^T) for one thread: row `row`, 32 consecutive columns starting at `col`; for a
@@ -189,8 +198,9 @@ __device__ __forceinline__ float act_runtime(int act, float v, float a) {
 // parameter: each kernel instance carries only its own activation code (the erf variants are long and
 // a kernel with all five thrashed the instruction cache: stall_no_inst was the #2 stall reason)
 template <int ACT>
-__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, const uint32_t* r,
-                                                         uint32_t stage, int row0, int col0, int lane) {
+__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, float* __restrict__ out_f32,
+                                                         const uint32_t* r, uint32_t stage, int row0,
+                                                         int col0, int lane) {
   const int cq = lane & 7, rsub = lane >> 3;
   const int col = col0 + 4 * cq;
   const int nvalid = g.N - col;  // >= 4: the whole float4 is in range
@@ -199,8 +209,27 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
   // loads that do not depend on the accumulator are issued first (they overlap the transposition)
   Vec4 bias = {{0.f, 0.f, 0.f, 0.f}};
   Vec4 res[8];
+  Vec4 aux[kGrad ? 8 : 1];
   if (vec) {
     if (g.bias) bias = ld4_f32(g.bias + col);
+    if constexpr (kGrad) {
+      // all eight pre-activation vectors in flight at once (one after the other inside the math loop
+      // they cost eight exposed DRAM round trips per chunk: 785 us for the fc2 dX GEMM of ViT-B/16)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = min(row0 + 4 * i + rsub, g.M - 1);
+        if (g.aux_dtype == HBA_DT_F32) {
+          const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
+          if ((g.ld_aux & 3) == 0) aux[i] = ld4_f32(p);
+          else aux[i] = Vec4{{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}};
+        } else {
+          const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
+          if ((g.ld_aux & 3) == 0) aux[i] = ld4_bf16(p);
+          else aux[i] = Vec4{{__bfloat162float(p[0]), __bfloat162float(p[1]), __bfloat162float(p[2]),
+                              __bfloat162float(p[3])}};
+        }
+      }
+    }
     if (g.residual) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -247,24 +276,10 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
         for (int e = 0; e < 4; ++e) v[i].x[e] = gelu_erf(v[i].x[e]);
     } else if constexpr (kGrad) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4 * i + rsub;
-        if (row >= g.M) continue;
-        Vec4 a;
-        if (g.aux_dtype == HBA_DT_F32) {
-          const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
-          if ((g.ld_aux & 3) == 0) a = ld4_f32(p);
-          else a = Vec4{{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}};
-        } else {
-          const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(g.aux) + (size_t)row * g.ld_aux + col;
-          if ((g.ld_aux & 3) == 0) a = ld4_bf16(p);
-          else a = Vec4{{__bfloat162float(p[0]), __bfloat162float(p[1]), __bfloat162float(p[2]),
-                         __bfloat162float(p[3])}};
-        }
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          v[i].x[e] *= (ACT == HBA_ACT_QUICKGELU_GRAD) ? quickgelu_grad(a.x[e]) : gelu_erf_grad(a.x[e]);
-      }
+          v[i].x[e] *= (ACT == HBA_ACT_QUICKGELU_GRAD) ? quickgelu_grad(aux[i].x[e]) : gelu_erf_grad(aux[i].x[e]);
     }
     if (g.residual) {
 #pragma unroll
@@ -272,11 +287,11 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[i].x[e] += res[i].x[e];
     }
-    if (g.out_f32) {
+    if (out_f32) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = row0 + 4 * i + rsub;
-        if (row < g.M) st4_f32(g.out_f32 + (size_t)row * g.ld_f32 + col, v[i]);
+        if (row < g.M) st4_f32(out_f32 + (size_t)row * g.ld_f32 + col, v[i]);
       }
     }
     if (g.out_bf16) {
@@ -320,7 +335,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, cons
                   : __bfloat162float(static_cast<const __nv_bfloat16*>(g.aux)[(size_t)row * g.ld_aux + col + e]);
         v = act_runtime(ACT, v, a);
         if (g.residual) v += __ldg(g.residual + (size_t)row * g.ldr + col + e);
-        if (g.out_f32) g.out_f32[(size_t)row * g.ld_f32 + col + e] = v;
+        if (out_f32) out_f32[(size_t)row * g.ld_f32 + col + e] = v;
         if (g.out_bf16) {
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
           g.out_bf16[(size_t)row * g.ld_bf16 + col + e] = h;
@@ -389,7 +404,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int num_n_tiles = (g.N + BN - 1) / BN;
   const int total_tiles = num_m_tiles * num_n_tiles;
   const int kblocks = (g.K + BK - 1) / BK;  // a ragged last block is zero-filled by TMA
-  const int kiters = kblocks * g.nsplit;
+  // split-K: item = slice * total_tiles + tile; slice s covers k-blocks [s * kb_per, min(.., kblocks))
+  const int total_items = total_tiles * g.k_slices;
+  const int kb_per = (kblocks + g.k_slices - 1) / g.k_slices;
 
   if (warp == 0) {
     {
@@ -397,10 +414,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       // where this CTA's TMA bytes are accounted: the pair leader's barriers
       const uint32_t full0 = (CG == 2) ? mapa_u32(&full_bar[0], 0) : smem_u32(&full_bar[0]);
-      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      for (int item = worker; item < total_items; item += num_workers) {
+        const int tile = item % total_tiles, slice = item / total_tiles;
         const int m0 = (tile % num_m_tiles) * TM + rank * BM;
         const int n0 = (tile / num_m_tiles) * BN + rank * BNC;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb_end = min(kblocks, (slice + 1) * kb_per);
+        for (int kb = slice * kb_per; kb < kb_end; ++kb) {
           for (int s = 0; s < g.nsplit; ++s) {
             const int a_col = kb * BK + (s == 1 ? g.a_lo_off : 0);
             const int b_col = kb * BK + (s == 2 ? g.b_lo_off : 0);
@@ -452,7 +471,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      for (int item = worker; item < total_items; item += num_workers) {
+        const int slice = item / total_tiles;
+        const int kiters = (min(kblocks, (slice + 1) * kb_per) - slice * kb_per) * g.nsplit;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -496,10 +517,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         (CG == 2) ? mapa_u32(&tempty_bar[1], 0) : smem_u32(&tempty_bar[1])};
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = worker; tile < total_tiles; tile += num_workers) {
+    for (int item = worker; item < total_items; item += num_workers) {
+      const int tile = item % total_tiles, slice = item / total_tiles;
       const int m0 = (tile % num_m_tiles) * TM + rank * BM;
       const int n0 = (tile / num_m_tiles) * BN;
       const int row = m0 + q * 32 + lane;
+      float* const out_f32 = g.out_f32 ? g.out_f32 + (size_t)slice * g.slice_stride : nullptr;
+      // the epilogue's own inputs (residual / pre-activation rows of this warp's half tile) are pulled
+      // into L2 while the tensor pipe is still producing the accumulator
+      if (!g.transpose_out && row < g.M) {
+        const int c0 = n0 + half * (BN / 2);
+        if (g.residual) {
+          const char* p = reinterpret_cast<const char*>(g.residual + (size_t)row * g.ldr + c0);
+#pragma unroll
+          for (int b = 0; b < BN / 2 * 4; b += 128)
+            if (c0 + b / 4 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+        }
+        if (g.aux) {
+          const int esz = g.aux_dtype == HBA_DT_F32 ? 4 : 2;
+          const char* p = static_cast<const char*>(g.aux) + ((size_t)row * g.ld_aux + c0) * esz;
+          for (int b = 0; b < BN / 2 * esz; b += 128)
+            if (c0 + b / esz < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -513,7 +553,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (g.transpose_out) {
           if (row < g.M && col < g.N) epilogue_chunk_transposed(g, r, row, col);
         } else if (m0 + q * 32 < g.M && col < g.N) {  // warp-uniform
-          epilogue_chunk_coalesced<ACT>(g, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
+          epilogue_chunk_coalesced<ACT>(g, out_f32, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
         }
       }
       tc_fence_before();
@@ -530,6 +570,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   } else {
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// out[r, c] = sum_s part[s][r, c]  (split-K reduction, fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float* __restrict__ part, size_t slice_stride, int slices, int rows, int cols,
+                         int ld, float* __restrict__ out, int ld_out) {
+  const int c4 = cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), c = (int)(i % c4) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(part + (size_t)r * ld + c);
+    for (int s = 1; s < slices; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(part + s * slice_stride + (size_t)r * ld + c);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * ld_out + c) = acc;
   }
 }
 
@@ -576,7 +633,7 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   const int tiles = ((p->M + BM * CG - 1) / (BM * CG)) * ((p->N + BN - 1) / BN);
   int workers = num_sms() / CG;
   if (p->max_ctas > 0 && p->max_ctas / CG < workers) workers = p->max_ctas / CG > 0 ? p->max_ctas / CG : 1;
-  if (tiles < workers) workers = tiles;
+  if (tiles * g.k_slices < workers) workers = tiles * g.k_slices;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * CG));
   cfg.blockDim = dim3(kGemmThreads);
@@ -646,6 +703,24 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   g.out_bf16 = static_cast<__nv_bfloat16*>(p->out_bf16), g.ld_bf16 = p->ld_bf16;
   g.out_lo_off = p->out_lo_off, g.transpose_out = p->transpose_out;
   g.a_mn = p->a_mn_major, g.b_mn = p->b_mn_major;
+  g.k_slices = 1, g.slice_stride = 0;
+  const int kblocks_total = (p->K + BK - 1) / BK;
+  int slices = p->k_slices > 1 ? p->k_slices : 1;
+  if (slices > kblocks_total) slices = kblocks_total;
+  if (slices > 1) {
+    HBA_REQUIRE(p->k_workspace && p->out_f32 && !p->out_bf16 && !p->pre_out && !p->bias && !p->residual &&
+                    p->act == HBA_ACT_NONE && !p->transpose_out && p->N % 4 == 0,
+                "hba_gemm_bf16: split-K (k_slices=%d) needs k_workspace, N %% 4 == 0 and a plain out_f32 epilogue",
+                p->k_slices);
+    HBA_REQUIRE(((uintptr_t)p->k_workspace & 15) == 0, "hba_gemm_bf16: k_workspace must be 16-byte aligned");
+    // every slice must own at least one k-block
+    const int kb_per = (kblocks_total + slices - 1) / slices;
+    slices = (kblocks_total + kb_per - 1) / kb_per;
+    g.k_slices = slices;
+    g.slice_stride = (size_t)p->M * p->N;
+    g.out_f32 = p->k_workspace;
+    g.ld_f32 = p->N;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -656,6 +731,16 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool wide = p->N >= 256;
+  if (g.k_slices > 1) {
+    const int rc = wide ? launch_gemm<256, 2, HBA_ACT_NONE>(p, g, s) : launch_gemm<128, 2, HBA_ACT_NONE>(p, g, s);
+    if (rc != HBA_OK) return rc;
+    const size_t n4 = (size_t)p->M * (p->N / 4);
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p->k_workspace, g.slice_stride, g.k_slices, p->M, p->N, p->N,
+                                                p->out_f32, p->ld_f32);
+    return check_launch("splitk_reduce_kernel");
+  }
   if (gemm_cta_group() == 2) {
     switch (p->act) {
 #define HBA_GEMM_CASE(A) \

@@ -33,6 +33,7 @@ class GemmParams(C.Structure):
         ("out_bf16", vp), ("ld_bf16", i32), ("out_lo_off", i32),
         ("transpose_out", i32), ("max_ctas", i32),
         ("a_mn_major", i32), ("b_mn_major", i32),
+        ("k_slices", i32), ("k_workspace", vp),
     ]
 
 

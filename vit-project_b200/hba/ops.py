@@ -75,9 +75,24 @@ class Operand:
         return Operand(self.buf.narrow(0, start, n), n, self.K, self.lo_off)
 
 
+def auto_k_slices(M, N, K, workers=74, max_slices=16):
+    """Split-K factor for a weight-gradient GEMM: minimises rounds-of-work-items / slices (the time of
+    the persistent kernel in units of one full-K tile) plus a small per-slice epilogue / reduction cost."""
+    tiles = -(-M // 256) * -(-N // (256 if N >= 256 else 128))
+    kblocks = -(-K // 64)
+    best, best_cost = 1, None
+    for s in range(1, max_slices + 1):
+        if s > 1 and (kblocks // s < 8 or N % 4):
+            break
+        cost = -(-tiles * s // workers) / s + 0.02 * (s - 1)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
+
+
 def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_ACT_NONE, aux=None,
          pre_out=None, out_f32=None, out: Operand = None, transpose_out=False, alpha=1.0,
-         max_ctas=0, a_mn=False, b_mn=False, K=None):
+         max_ctas=0, a_mn=False, b_mn=False, K=None, k_slices=1, k_workspace=None):
     """C[M,N] = epilogue(A . B^T) on the tcgen05 tensor pipe (hba_gemm_bf16).
     a_mn / b_mn: the operand is stored MN-major, i.e. as [K rows, M resp. N columns] (its Operand
     then has rows = K and K = M resp. N)."""
@@ -115,14 +130,22 @@ def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_AC
     p.transpose_out = 1 if transpose_out else 0
     p.max_ctas = max_ctas
     p.a_mn_major, p.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
+    launches = 1
+    if k_slices == "auto":
+        k_slices = auto_k_slices(M, N, K)
+    if k_slices > 1:
+        assert k_workspace is not None and k_workspace.dtype == torch.float32
+        assert k_workspace.numel() >= k_slices * M * N, "k_workspace too small"
+        p.k_slices, p.k_workspace = k_slices, k_workspace.data_ptr()
+        launches = 2
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16")
+        check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16", launches)
         e1.record()
         GEMM_PROFILE.append((M, N, K, p.nsplit, e0, e1))
         return
-    check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16")
+    check(_lib.load().hba_gemm_bf16(C.byref(p), _stream()), "hba_gemm_bf16", launches)
 
 
 def split_bf16(x, out: Operand, transpose=False):

@@ -240,6 +240,16 @@ class ViTEngine:
         return logits
 
     # ------------------------------------------------------------------ backward
+    def _dw_gemm(self, dy: Operand, x: Operand, K, out):
+        """dW[out, in] = dY^T X (both operands read MN-major, K = rows of the batch).  dW shapes have few
+        output tiles (9 .. 36 of 256 x 256 against 74 CTA pairs): split-K keeps every SM busy."""
+        Mo, No = out.shape
+        s = ops.auto_k_slices(Mo, No, K)
+        ws = self._buf("k_ws", (16 * 768 * 3072,)) if s > 1 else None
+        if ws is not None and ws.numel() < s * Mo * No:
+            s = max(1, ws.numel() // (Mo * No))
+        ops.gemm(dy, x, a_mn=True, b_mn=True, K=K, out_f32=out, k_slices=s, k_workspace=ws if s > 1 else None)
+
     def d_logits_buffer(self, B):
         C = self.m.num_classes
         return self._buf("dl_pad", (B, (C + 3) // 4 * 4), zero=True)[:, :C]
@@ -343,19 +353,19 @@ class ViTEngine:
             att, hid = self._opbuf(tag + "att", M, d), self._opbuf(tag + "hid", M, 4 * d)
             qkv = self._buf(tag + "qkv", (M, 3 * d), adt)
             # fc2 (gy = bf16 of dx and the fc2 bias gradient come from the previous fused LN backward)
-            ops.gemm(gy, hid, a_mn=True, b_mn=True, K=M, out_f32=G(blk.mlp.fc2.weight))
+            self._dw_gemm(gy, hid, M, G(blk.mlp.fc2.weight))
             g_hid = self._opbuf("g_hid", M, 4 * d)
             g_hid_f = self._buf("g_hid_f", (M, 4 * d)) if sp else None
             ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
                      out_f32=g_hid_f)
             # fc1
-            ops.gemm(g_hid, ln2, a_mn=True, b_mn=True, K=M, out_f32=G(blk.mlp.fc1.weight))
+            self._dw_gemm(g_hid, ln2, M, G(blk.mlp.fc1.weight))
             ops.colsum(g_hid_f if sp else g_hid.buf, G(blk.mlp.fc1.bias), cs_ws)
             d_ln = self._buf("d_ln", (M, d))
             ops.gemm(g_hid, self._wops[f"{i}.fc1"], M, b_mn=True, out_f32=d_ln)
             ln_backward(d_ln, x_mid, blk.norm2, gy, G(blk.attn.proj.bias))
             # attention projection
-            ops.gemm(gy, att, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.proj.weight))
+            self._dw_gemm(gy, att, M, G(blk.attn.proj.weight))
             if sp:
                 d_att = self._buf("d_att_f", (M, d))
                 ops.gemm(gy, self._wops[f"{i}.proj"], M, b_mn=True, out_f32=d_att)
@@ -374,7 +384,7 @@ class ViTEngine:
                     ops.attention_bwd_lse(qkv, B, T, H, att.buf, d_att, self._buf(tag + "lse", (B * H * T,)),
                                           g_qkv.buf)
                 ops.colsum(g_qkv.buf, G(blk.attn.qkv.bias), cs_ws)
-            ops.gemm(g_qkv, ln1, a_mn=True, b_mn=True, K=M, out_f32=G(blk.attn.qkv.weight))
+            self._dw_gemm(g_qkv, ln1, M, G(blk.attn.qkv.weight))
             ops.gemm(g_qkv, self._wops[f"{i}.qkv"], M, b_mn=True, out_f32=d_ln)
             ln_backward(d_ln, x_in, blk.norm1, gy, G(m.blocks[i - 1].mlp.fc2.bias) if i > 0 else cs_scratch)
             ready(f"block{i}")
@@ -386,8 +396,7 @@ class ViTEngine:
         gp = self._opbuf("gp", B * npatch, d)
         ops.split_bf16(d_patch, gp)
         patches = self._opbuf("patches", B * npatch, 3 * P * P)
-        ops.gemm(gp, patches, a_mn=True, b_mn=True, K=B * npatch,
-                 out_f32=G(m.patch_embed.proj.weight).view(d, 3 * P * P))
+        self._dw_gemm(gp, patches, B * npatch, G(m.patch_embed.proj.weight).view(d, 3 * P * P))
         ops.colsum(d_patch, G(m.patch_embed.proj.bias), cs_ws)
         ready("embed")
         return self.flat_grad
