@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--model", default="vit_base_patch16_224")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host (no CUDA graph)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     a = ap.parse_args()
@@ -46,7 +47,7 @@ def main():
     hba.set_precision(a.precision)
     torch.manual_seed(0)
     model = vit.create_model(a.model, num_classes=1000).to(dev)
-    tr = vit.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    tr = vit.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4, use_graph=not a.no_graph)
     tr.broadcast_parameters()
     g = torch.Generator(device=dev).manual_seed(rank)
     images = torch.randn(a.batch, 3, 224, 224, device=dev, generator=g)

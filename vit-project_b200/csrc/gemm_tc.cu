@@ -239,11 +239,18 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
       }
     }
   }
+  if (g.alpha == 1.0f) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]) * g.alpha,
-           __uint_as_float(r[4 * j + 1]) * g.alpha, __uint_as_float(r[4 * j + 2]) * g.alpha,
-           __uint_as_float(r[4 * j + 3]) * g.alpha);
+    for (int j = 0; j < 8; ++j)
+      sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]) * g.alpha,
+             __uint_as_float(r[4 * j + 1]) * g.alpha, __uint_as_float(r[4 * j + 2]) * g.alpha,
+             __uint_as_float(r[4 * j + 3]) * g.alpha);
+  }
   __syncwarp();
   if (vec) {
     Vec4 v[8];
@@ -416,8 +423,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t full0 = (CG == 2) ? mapa_u32(&full_bar[0], 0) : smem_u32(&full_bar[0]);
       for (int item = worker; item < total_items; item += num_workers) {
         const int tile = item % total_tiles, slice = item / total_tiles;
-        const int m0 = (tile % num_m_tiles) * TM + rank * BM;
-        const int n0 = (tile / num_m_tiles) * BN + rank * BNC;
+        const int m0 = (tile / num_n_tiles) * TM + rank * BM;
+        const int n0 = (tile % num_n_tiles) * BN + rank * BNC;
         const int kb_end = min(kblocks, (slice + 1) * kb_per);
         for (int kb = slice * kb_per; kb < kb_end; ++kb) {
           for (int s = 0; s < g.nsplit; ++s) {
@@ -517,29 +524,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         (CG == 2) ? mapa_u32(&tempty_bar[1], 0) : smem_u32(&tempty_bar[1])};
     int acc = 0;
     uint32_t acc_phase = 0;
+    // The epilogue's own inputs (residual / pre-activation rows of this warp's half tile) are pulled
+    // into L2 one work item ahead: when the epilogue is the longer stage the accumulator is already
+    // waiting, and loads issued only then paid a full DRAM round trip per 32 x 32 chunk.
+    auto prefetch_inputs = [&](int it) {
+      if (it >= total_items || g.transpose_out || (!g.residual && !g.aux)) return;
+      const int tl = it % total_tiles;
+      const int prow = (tl / num_n_tiles) * TM + rank * BM + q * 32 + lane;
+      if (prow >= g.M) return;
+      const int c0 = (tl % num_n_tiles) * BN + half * (BN / 2);
+      if (g.residual) {
+        const char* p = reinterpret_cast<const char*>(g.residual + (size_t)prow * g.ldr + c0);
+#pragma unroll
+        for (int b = 0; b < BN / 2 * 4; b += 128)
+          if (c0 + b / 4 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+      }
+      if (g.aux) {
+        const int esz = g.aux_dtype == HBA_DT_F32 ? 4 : 2;
+        const char* p = static_cast<const char*>(g.aux) + ((size_t)prow * g.ld_aux + c0) * esz;
+        for (int b = 0; b < BN / 2 * esz; b += 128)
+          if (c0 + b / esz < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+      }
+    };
+    prefetch_inputs(worker);
     for (int item = worker; item < total_items; item += num_workers) {
       const int tile = item % total_tiles, slice = item / total_tiles;
-      const int m0 = (tile % num_m_tiles) * TM + rank * BM;
-      const int n0 = (tile / num_m_tiles) * BN;
+      const int m0 = (tile / num_n_tiles) * TM + rank * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
       const int row = m0 + q * 32 + lane;
       float* const out_f32 = g.out_f32 ? g.out_f32 + (size_t)slice * g.slice_stride : nullptr;
-      // the epilogue's own inputs (residual / pre-activation rows of this warp's half tile) are pulled
-      // into L2 while the tensor pipe is still producing the accumulator
-      if (!g.transpose_out && row < g.M) {
-        const int c0 = n0 + half * (BN / 2);
-        if (g.residual) {
-          const char* p = reinterpret_cast<const char*>(g.residual + (size_t)row * g.ldr + c0);
-#pragma unroll
-          for (int b = 0; b < BN / 2 * 4; b += 128)
-            if (c0 + b / 4 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
-        }
-        if (g.aux) {
-          const int esz = g.aux_dtype == HBA_DT_F32 ? 4 : 2;
-          const char* p = static_cast<const char*>(g.aux) + ((size_t)row * g.ld_aux + c0) * esz;
-          for (int b = 0; b < BN / 2 * esz; b += 128)
-            if (c0 + b / esz < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
-        }
-      }
+      prefetch_inputs(item + num_workers);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1

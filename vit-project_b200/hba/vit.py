@@ -451,8 +451,11 @@ class DataParallelTrainer:
     backward with one async NCCL all-reduce per block bucket, overlapped with the remaining backward
     -> fused multi-tensor SGD.  Works without a process group (world size 1)."""
 
-    def __init__(self, model, lr=0.1, momentum=0.9, weight_decay=1e-4, process_group=None):
+    def __init__(self, model, lr=0.1, momentum=0.9, weight_decay=1e-4, process_group=None, use_graph=False):
         import torch.distributed as dist
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._static = None
         self.model, self.eng = model, get_engine(model)
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = process_group
@@ -469,6 +472,35 @@ class DataParallelTrainer:
                 self.dist.broadcast(p.data, src=0, group=self.group)
 
     def step(self, images, labels):
+        """One training step; returns (loss, top-1 hits) as device tensors.  With use_graph the step's
+        ~400 launches (and the bucketed all-reduces) are captured once per (batch size, lr) into a CUDA
+        graph and replayed: identical kernels and arguments, no per-launch host work or gaps."""
+        if not self.use_graph or self._first:
+            return self._step_eager(images, labels)
+        key = (tuple(images.shape), float(self.param_groups[0]["lr"]))
+        if self._static is None or self._static[0].shape != images.shape:
+            self._static = (torch.empty_like(images), torch.empty_like(labels))
+            self._graphs.clear()
+        s_img, s_lab = self._static
+        s_img.copy_(images, non_blocking=True)
+        s_lab.copy_(labels, non_blocking=True)
+        entry = self._graphs.get(key)
+        if entry is None:
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            c0 = ops.COUNTERS["launches"]
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out = self._step_eager(s_img, s_lab)
+            entry = (graph, out, ops.COUNTERS["launches"] - c0)   # kernels per replay
+            ops.COUNTERS["launches"] = c0
+            if len(self._graphs) >= 4:   # one graph per learning rate: keep the cache small
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = entry
+        entry[0].replay()
+        ops.COUNTERS["launches"] += entry[2]
+        return entry[1]
+
+    def _step_eager(self, images, labels):
         eng, m = self.eng, self.model
         logits = eng.forward(images, save=True)
         B, C = logits.shape
