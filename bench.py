@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-vit", action="store_true")
+    ap.add_argument("--sweep-only", action="store_true", help="debug: measure only the sweep section")
+    ap.add_argument("--vit-batch", type=int, default=256)
     return ap.parse_args()
 
 
@@ -150,6 +153,11 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        try:   # make sure the poller is gone: a live `nvidia-smi -lms` slows every later CUDA call
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            self.proc.wait()
         sm, mx, reasons = [], [], set()
         for row in self.rows:
             parts = [p.strip() for p in row.split(",")]
@@ -224,6 +232,10 @@ def measure_sweep(args, device, world):
             return n_rsa
 
     model, opt = build_gpu_model(args, device)
+    # (the frozen CLIP and its engine are shared per process, functions._pipeline_core.load_clip_to_cpu:
+    # undo the headline measurement's "recompute the text tower every step" switch - the pipeline's own
+    # default caches the constant text trunk, NEW:282)
+    model.clip_model.hba_engine().cache_text = True
     core.enable_trunk_cache(model, n_train + n_test + n_rsa)
     gen = torch.Generator()
     gen.manual_seed(1)
@@ -252,20 +264,72 @@ def measure_sweep(args, device, world):
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    k = 3
+    k = 6
     t_fill = run(0, 1, "fill")          # epoch 1: trunk computed once per image, cache filled
-    t_cached = run(1, 1 + k, "cached")  # epochs 2..k+1: frozen trunk served from HBM
+    t_capture = run(1, 2, "capture")    # epoch 2: first cached epoch, the step / forward graphs are captured
+    t_cached = run(2, 2 + k, "cached")  # epochs 3..k+2: steady state of a 55-epoch condition
     logging.disable(logging.NOTSET)
     sec_epoch = t_cached / k
     imgs_epoch = n_train + n_test + n_rsa
-    return {"conditions_per_hour": world * 3600.0 / (EPOCHS_PER_CONDITION * sec_epoch), "unit": "conditions/h",
+    sec_cond = t_fill + t_capture + (EPOCHS_PER_CONDITION - 2) * sec_epoch
+    return {"conditions_per_hour": world * 3600.0 / sec_cond, "unit": "conditions/h",
             "epochs_per_condition": EPOCHS_PER_CONDITION, "sec_per_epoch_cached": sec_epoch,
-            "sec_first_epoch_cache_fill": t_fill, "images_per_epoch": imgs_epoch,
+            "sec_first_epoch_cache_fill": t_fill, "sec_second_epoch_graph_capture": t_capture,
+            "sec_per_condition": sec_cond,
+            "images_per_epoch": imgs_epoch,
             "blended_images_per_s": world * imgs_epoch / sec_epoch,
             "config": "train_model epochs on 1444/362/48 synthetic HBM-resident images, batch %d, random_target "
-                      "window, per-epoch eval + RSA + CSV + DoRA/random-state checkpoints, frozen-trunk cache; "
-                      "wall clock incl. host" % bs,
+                      "window, per-epoch eval + RSA + CSV + DoRA/random-state checkpoints, frozen-trunk cache, CUDA-graph "
+                      "cached steps; wall clock incl. host; one condition = cache-fill epoch + capture epoch + 53 "
+                      "steady-state epochs" % bs,
             "reference_baseline": "1.52 conditions/h, 43.5 s/epoch on one unnamed GPU (BASELINE.md, derived)"}
+
+
+def measure_vit(args, device, world, dist):
+    """BASELINE.json configs[2]: ViT-B/16 classification training, data parallel (VIT = Training/
+    vit_training/baseline/train_vit_sgd.py): batch 256 per GPU, synthetic 224^2 images / 1000 classes,
+    SGD 0.1 / 0.9 / 1e-4, bf16 tensor-core GEMMs, one NCCL all-reduce per block bucket overlapped with
+    the backward pass, CUDA-graph step.  Whole-job images/s, device-timed, max over ranks."""
+    import torch
+    from hba import ops, vit
+    rank = int(os.environ.get("RANK", "0"))
+    torch.manual_seed(0)
+    model = vit.create_model("vit_base_patch16_224", num_classes=1000).to(device)
+    tr = vit.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4, use_graph=True)
+    tr.broadcast_parameters()
+    batch = args.vit_batch
+    g = torch.Generator(device=device).manual_seed(rank)
+    images = torch.randn(batch, 3, 224, 224, device=device, generator=g)
+    labels = torch.randint(0, 1000, (batch,), device=device, generator=g)
+    for _ in range(3):
+        loss, _ = tr.step(images, labels)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(3, min(args.steps, 10))
+    c0 = ops.COUNTERS["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = tr.step(images, labels)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = world * batch * steps / (ms / 1e3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["bf16_tflops_sustained"] if os.path.exists(peaks_path) else 1400.0
+    tflops = value / world * 105.3e9 / 1e12   # SURVEY 8d: 3 x 35.1 GFLOP per image
+    return {"metric": "ViT-B/16 train imgs/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "ms_per_step": ms / steps, "scaling": "weak", "dtype": "bf16", "global_batch": batch * world,
+            "parallelism": f"dp{world}: batch {batch}/GPU, NCCL gradient all-reduce per block bucket, CUDA-graph step",
+            "loss": float(loss), "gpu_launches": ops.COUNTERS["launches"] - c0,
+            "algorithmic_tflops_per_gpu": tflops, "frac_of_sustained_bf16_peak": tflops / peak}
 
 
 def main():
@@ -288,6 +352,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     hba.set_precision(args.precision)
+    if args.sweep_only:
+        print(json.dumps(measure_sweep(args, device, world)))
+        return
     model, opt = build_gpu_model(args, device)
     eng = model.clip_model.hba_engine()
     eng.cache_text = False  # the reference recomputes the text tower every step (NEW:298)
@@ -389,9 +456,16 @@ def main():
             t = torch.tensor([sw["sec_per_epoch_cached"]], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sw["sec_per_epoch_cached"] = float(t)
-            sw["conditions_per_hour"] = world * 3600.0 / (EPOCHS_PER_CONDITION * float(t))
+            sw["sec_per_condition"] = (sw["sec_first_epoch_cache_fill"] + sw["sec_second_epoch_graph_capture"]
+                                       + (EPOCHS_PER_CONDITION - 2) * float(t))
+            sw["conditions_per_hour"] = world * 3600.0 / sw["sec_per_condition"]
             sw["blended_images_per_s"] = world * sw["images_per_epoch"] / float(t)
         out["sweep"] = sw
+    if not args.no_vit:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        out["vit_b16"] = measure_vit(args, device, world, dist)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -409,7 +483,12 @@ def main():
                                          "text tower recomputed), oracle port in PyTorch fp32"}
     if rank == 0:
         print(json.dumps(out))
+    sys.stdout.flush()
     if dist is not None:
+        if not args.no_vit:
+            # captured graphs hold NCCL kernels of the communicator; tearing the group down with live
+            # graphs hung the ranks at exit (observed at N=2): leave without the teardown
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -195,12 +195,14 @@ int hba_cos_head_bwd(const float* img, const float* txt, int32_t B, int32_t C, i
  * SGD(momentum, weight_decay, dampening 0, no nesterov) of VIT:294-299.
  * ptrs: device array of 4*n pointers (param, grad, exp_avg, exp_avg_sq) resp. 3*n (param, grad,
  * momentum_buf); sizes: device array of n int64.  step is the 1-based step count AFTER this
- * update.  skip_flag (optional, device int32): when *skip_flag != 0 the update is skipped (the
- * NaN/Inf guard of NEW:989-998 evaluated on the device).
+ * update; when step_dev (optional, device int32) is given the count is read from the device instead
+ * (a captured CUDA graph then replays with the right bias corrections).  skip_flag (optional, device
+ * int32): when *skip_flag != 0 the update is skipped (the NaN/Inf guard of NEW:989-998 evaluated on
+ * the device).
  */
 int hba_adamw_multi(void* const* ptrs, const int64_t* sizes, int32_t n, int64_t total,
                     float lr, float beta1, float beta2, float eps, float weight_decay,
-                    int64_t step, const int32_t* skip_flag, void* stream);
+                    int64_t step, const int32_t* step_dev, const int32_t* skip_flag, void* stream);
 int hba_sgd_multi(void* const* ptrs, const int64_t* sizes, int32_t n, int64_t total, float lr,
                   float momentum, float weight_decay, int32_t first_step,
                   const int32_t* skip_flag, void* stream);

@@ -259,3 +259,49 @@ def test_run_behavioral_training_drivers_end_to_end(tiny_checkpoint, tmp_path):
     assert r[1][:5] == rows[1][:5]
     assert r[2][5] == "True" and r[3][5] == "False"              # random targets in epoch 2 only
     assert r == results["plain"]                                 # resident + cached == plain, exactly
+
+
+def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, tmp_path, monkeypatch):
+    """HBA_STEP_GRAPH (CUDA graphs of the trunk-cached training step and of the cached eval / RSA
+    forward) against the same run launched kernel by kernel: a sweep condition resumed from baseline
+    epoch 1, 7 epochs with a 2-epoch random-target window - identical CSV rows, DoRA checkpoints and
+    optimizer step counts."""
+    import hba
+    import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    hba.set_precision("bf16")
+    root = str(tmp_path)
+    img_dir = _write_things_like_dataset(root, n_train=22)
+    common = {"csv_file": f"{root}/train.csv", "img_dir": img_dir, "inference_csv_file": f"{root}/rsa.csv",
+              "RDM48_triplet_dir": f"{root}/RDM48_triplet.mat", "backbone": "ViT-tiny/14", "batch_size": 4,
+              "lr": 3e-4, "random_seed": 1, "vision_layers": 2, "transformer_layers": 1, "rank": 8,
+              "criterion": torch.nn.MSELoss(), "cuda": 0}
+    base_cfg = dict(common, epochs=1, train_portion=0.8, early_stopping_patience=20, logger=None,
+                    checkpoint_path=f"{root}/base/model.pth", training_res_path=f"{root}/base/res.csv",
+                    dora_parameters_path=f"{root}/base/dora", random_state_path=f"{root}/base/rand")
+    BASE.run_behavioral_training(base_cfg)
+    results = {}
+    for tag, flag in (("graph", "1"), ("eager", "0")):
+        monkeypatch.setenv("HBA_STEP_GRAPH", flag)
+        cfg = dict(common, epochs=7, early_stopping_patience=20, hba_resident=True,
+                   checkpoint_path=f"{root}/{tag}/model.pth", training_res_path=f"{root}/{tag}/res.csv",
+                   dora_parameters_path=f"{root}/{tag}/dora", random_state_path=f"{root}/{tag}/rand",
+                   baseline_dora_directory=f"{root}/base/dora", baseline_random_state_path=f"{root}/base/rand",
+                   baseline_split_indices_path=f"{root}/base/rand/dataset_split_indices.pth",
+                   perturb_type="random_target", perturb_length=2, perturb_distribution="target",
+                   perturb_seed=42, training_run=4, resume_from_epoch=1,
+                   previous_training_res_path=f"{root}/base/res.csv")
+        NEW.run_behavioral_training(cfg)
+        rows = list(csv.reader(open(cfg["training_res_path"])))
+        dora = torch.load(f"{root}/{tag}/dora/epoch7_dora_params.pth")
+        rand = torch.load(f"{root}/{tag}/rand/epoch7_random_states.pth", weights_only=False)
+        results[tag] = (rows, dora, rand)
+    g, e = results["graph"], results["eager"]
+    assert len(g[0]) == 8 and g[0] == e[0]
+    assert [r[5] for r in g[0][2:]] == ["False", "False", "True", "True", "False", "False"]   # epochs 2..7
+    assert g[1].keys() == e[1].keys()
+    for k in g[1]:
+        assert torch.equal(g[1][k], e[1][k]), k
+    steps_g = [float(v["step"]) for v in g[2]["optimizer_state_dict"]["state"].values()]
+    steps_e = [float(v["step"]) for v in e[2]["optimizer_state_dict"]["state"].values()]
+    assert steps_g == steps_e and steps_g[0] == 7 * 5   # 17 train images / batch 4 -> 5 steps per epoch, 7 epochs

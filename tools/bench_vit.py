@@ -88,7 +88,12 @@ def main():
                                                  "fused CE, bucketed NCCL gradient all-reduce", "global_batch": a.batch * world},
                           "loss": float(loss), "gpu_launches": ops.COUNTERS["launches"] - c0,
                           "algorithmic_tflops_per_gpu": tflops_per_gpu, "frac_of_sustained_bf16_peak": tflops_per_gpu / peak}))
+    sys.stdout.flush()
     if dist is not None:
+        if not a.no_graph:
+            # a captured graph holds NCCL kernels of the communicator: tearing the process group down
+            # with live graphs hung the ranks at exit (observed at N=2) - leave without the teardown
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -26,14 +26,24 @@ __device__ __forceinline__ int find_tensor(const int64_t* prefix, int n, int64_t
 __global__ void __launch_bounds__(256)
     adamw_multi_kernel(void* const* __restrict__ ptrs, const int64_t* __restrict__ sizes, int n,
                        int64_t total, float lr, float beta1, float beta2, float eps, float wd,
-                       float step_size, float bc2_sqrt, const int* __restrict__ skip_flag) {
+                       float step_size, float bc2_sqrt, const int* __restrict__ step_dev,
+                       const int* __restrict__ skip_flag) {
   if (skip_flag && *skip_flag != 0) return;
   __shared__ int64_t prefix[kOptMaxTensors];
+  __shared__ float s_corr[2];
   if (threadIdx.x == 0) {
     int64_t acc = 0;
     for (int t = 0; t < n; ++t) prefix[t] = acc, acc += sizes[t];
+    if (step_dev) {
+      // step count kept on the device (CUDA-graph replays): same double-precision bias corrections
+      // as the host path / torch.optim.AdamW
+      const double st = (double)*step_dev;
+      s_corr[0] = (float)((double)lr / (1.0 - pow((double)beta1, st)));
+      s_corr[1] = (float)sqrt(1.0 - pow((double)beta2, st));
+    }
   }
   __syncthreads();
+  if (step_dev) step_size = s_corr[0], bc2_sqrt = s_corr[1];
   const int64_t base = (int64_t)blockIdx.x * kOptChunk;
   for (int k = threadIdx.x; k < kOptChunk; k += 256) {
     const int64_t g = base + k;
@@ -89,15 +99,18 @@ using namespace hba;
 
 extern "C" int hba_adamw_multi(void* const* ptrs, const int64_t* sizes, int32_t n, int64_t total,
                                float lr, float beta1, float beta2, float eps, float weight_decay,
-                               int64_t step, const int32_t* skip_flag, void* stream) {
-  HBA_REQUIRE(ptrs && sizes && n > 0 && n <= kOptMaxTensors && total > 0 && step >= 1, "hba_adamw_multi: bad arguments");
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+                               int64_t step, const int32_t* step_dev, const int32_t* skip_flag,
+                               void* stream) {
+  HBA_REQUIRE(ptrs && sizes && n > 0 && n <= kOptMaxTensors && total > 0 && (step >= 1 || step_dev),
+              "hba_adamw_multi: bad arguments");
+  const double hstep = step >= 1 ? (double)step : 1.0;
+  const double bc1 = 1.0 - std::pow((double)beta1, hstep);
+  const double bc2 = 1.0 - std::pow((double)beta2, hstep);
   const float step_size = (float)((double)lr / bc1);
   const float bc2_sqrt = (float)std::sqrt(bc2);
   const unsigned grid = (unsigned)((total + kOptChunk - 1) / kOptChunk);
   adamw_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      ptrs, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, skip_flag);
+      ptrs, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt, step_dev, skip_flag);
   return check_launch("adamw_multi_kernel");
 }
 

@@ -354,6 +354,56 @@ def _announce_ids(model, loader, allowed=True):
         eng.batch_ids = getattr(loader, "last_ids", None) if allowed else None
 
 
+class _CachedForwardGraphs:
+    """CUDA graphs of the no-grad forward on trunk-cached images (evaluation / RSA batches), one per
+    batch size; see _CachedStepGraphs.  __call__ returns a fresh tensor (a copy of the graph's static
+    output)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.eng = _engine_of(model)
+        self.entries = {}
+        self.warm = set()
+
+    @staticmethod
+    def of(model):
+        g = model.__dict__.get("_hba_forward_graphs")
+        if g is None:
+            g = model.__dict__["_hba_forward_graphs"] = _CachedForwardGraphs(model)
+        return g
+
+    def usable(self, loader):
+        eng = self.eng
+        return (os.environ.get("HBA_STEP_GRAPH", "1") != "0" and eng is not None and eng.trunk_cache is not None
+                and getattr(loader, "last_ids_dev", None) is not None and not torch.is_grad_enabled()
+                and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids))
+
+    def __call__(self, images, ids_dev):
+        eng = self.eng
+        key = (tuple(images.shape), eng._stamp, eng.precision)
+        if key not in self.warm:
+            self.warm.add(key)
+            eng.batch_ids = ids_dev
+            return self.model(images)
+        entry = self.entries.get(key)
+        if entry is None:
+            s_img, s_ids = torch.zeros_like(images), ids_dev.clone()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            c0 = ops.COUNTERS["launches"]
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                eng.batch_ids = s_ids
+                out = self.model(s_img)
+            entry = (graph, s_ids, out, ops.COUNTERS["launches"] - c0)
+            ops.COUNTERS["launches"] = c0
+            self.entries[key] = entry
+        graph, s_ids, out, n_launch = entry
+        s_ids.copy_(ids_dev, non_blocking=True)
+        graph.replay()
+        ops.COUNTERS["launches"] += n_launch
+        return out.clone()
+
+
 # ------------------------------------------------------------------------------- evaluation
 def evaluate_model(model, data_loader, device, criterion):
     """NEW:584-602: sample-weighted mean loss; accumulated on the device, one read at the end."""
@@ -364,8 +414,13 @@ def evaluate_model(model, data_loader, device, criterion):
                                        file=sys.stderr):
             images = images.to(device, non_blocking=True)
             targets = targets.to(device, non_blocking=True)
-            _announce_ids(model, data_loader)
-            total += criterion(model(images), targets).double() * images.size(0)
+            fwd = _CachedForwardGraphs.of(model)
+            if fwd.usable(data_loader):
+                predictions = fwd(images, data_loader.last_ids_dev)
+            else:
+                _announce_ids(model, data_loader)
+                predictions = model(images)
+            total += criterion(predictions, targets).double() * images.size(0)
     return float(total) / len(data_loader.dataset)
 
 
@@ -385,8 +440,13 @@ def behavioral_RSA(model, inference_loader, device, logger=None):
     names, chunks = [], []
     with torch.no_grad():
         for image_name, image in inference_loader:
-            _announce_ids(model, inference_loader)
-            chunks.append(model(image.to(device, non_blocking=True)))
+            image = image.to(device, non_blocking=True)
+            fwd = _CachedForwardGraphs.of(model)
+            if fwd.usable(inference_loader):
+                chunks.append(fwd(image, inference_loader.last_ids_dev))
+            else:
+                _announce_ids(model, inference_loader)
+                chunks.append(model(image))
             names.extend(image_name)
     emb = torch.cat(chunks, 0)
     log(f"First 10 image names: {names[:5]}")
@@ -482,14 +542,88 @@ class _BadBatchFlag:
         return self.step
 
 
+class _CachedStepGraphs:
+    """CUDA graphs of the frozen-trunk-cached training step, one per batch size.
+
+    Once every image of a batch is in the trunk cache the step (cache gather -> live blocks -> cosine
+    head -> MSE -> NaN guard -> backward -> DoRA merge backward -> fused AdamW -> loss accumulation)
+    is ~90 small launches of ~0.6 ms GPU time behind ~4 ms of Python: captured once, it replays
+    with the image ids and the (possibly perturbed) targets copied into static buffers.  Same kernels,
+    same arguments, same order as the eager step - results are bit-identical (tests/test_gpu_pipeline.py).
+    Set HBA_STEP_GRAPH=0 to disable."""
+
+    def __init__(self, model, optimizer, criterion, guard, total, device):
+        self.model, self.opt, self.crit, self.guard, self.total = model, optimizer, criterion, guard, total
+        self.device = device
+        self.eng = _engine_of(model)
+        self.entries = {}
+        self.warm = set()
+
+    def usable(self, loader, perturbed_images):
+        eng = self.eng
+        return (os.environ.get("HBA_STEP_GRAPH", "1") != "0" and eng is not None and eng.trunk_cache is not None
+                and not perturbed_images and isinstance(self.opt, FusedAdamW)
+                and getattr(loader, "last_ids_dev", None) is not None
+                and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids))
+
+    def _body(self, images, ids_dev, targets):
+        self.opt.zero_grad()
+        self.eng.batch_ids = ids_dev
+        predictions = self.model(images)
+        loss = self.crit(predictions, targets)
+        bad = self.guard.check(predictions, loss.reshape(1), targets)
+        loss.backward()
+        self.opt.step(skip_flag=bad)
+        self.total += torch.where(bad[0] == 0, loss.detach().double(), torch.zeros_like(self.total)) * images.size(0)
+
+    def step(self, images, ids_dev, targets):
+        B = images.shape[0]
+        key = (B, tuple(images.shape[1:]), self.eng._stamp, self.eng.precision)
+        if key not in self.warm:
+            # first cached step of this shape runs eagerly: it allocates every workspace, gradient and
+            # optimiser-state tensor the captured step will reuse
+            self.warm.add(key)
+            return self._body(images, ids_dev, targets)
+        entry = self.entries.get(key)
+        if entry is None:
+            s_img = torch.zeros_like(images)   # never read on the cached path; carries the shape
+            s_ids, s_tgt = ids_dev.clone(), targets.clone()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            c0 = ops.COUNTERS["launches"]
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._body(s_img, s_ids, s_tgt)
+            entry = (graph, s_ids, s_tgt, ops.COUNTERS["launches"] - c0)
+            ops.COUNTERS["launches"] = c0
+            self.entries[key] = entry
+        graph, s_ids, s_tgt, n_launch = entry
+        s_ids.copy_(ids_dev, non_blocking=True)
+        s_tgt.copy_(targets, non_blocking=True)
+        graph.replay()
+        ops.COUNTERS["launches"] += n_launch
+
+
 def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs, perturb=None,
                     log=print):
     """One pass over train_loader (NEW:873-1004 / BASE:644-659): returns the sample-weighted mean
     loss, read from the device once."""
-    total = torch.zeros((), device=device, dtype=torch.float64)
-    guard = _BadBatchFlag(device)
+    state = model.__dict__.get("_hba_train_state")
+    if state is None or state["optimizer"] is not optimizer or state["criterion"] is not criterion:
+        # persistent per (model, optimizer): the loss accumulator and NaN guard are static inputs of the
+        # captured step graphs, which are reused across epochs
+        total = torch.zeros((), device=device, dtype=torch.float64)
+        guard = _BadBatchFlag(device)
+        state = {"optimizer": optimizer, "criterion": criterion, "total": total, "guard": guard,
+                 "graphs": _CachedStepGraphs(model, optimizer, criterion, guard, total, device)}
+        model.__dict__["_hba_train_state"] = state
+    total, guard, graphs = state["total"], state["guard"], state["graphs"]
+    if graphs.eng is not None and graphs.eng.device is not None:
+        graphs.eng.ensure(graphs.eng.device)   # frozen weights changed since the graphs were captured?
+    total.zero_()
+    guard.total.zero_()
     fused = isinstance(optimizer, FusedAdamW)
     active = perturb is not None and perturb.active(epoch)
+    perturbed_images = active and perturb.kind in IMAGE_PERTURBATIONS
     bar = tqdm(enumerate(train_loader), total=len(train_loader), desc=f"Epoch {epoch + 1}/{epochs}",
                file=sys.stderr)
     for batch_idx, (_, images, targets) in bar:
@@ -497,8 +631,11 @@ def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, ep
         targets = targets.to(device, non_blocking=True)
         if active:
             images, targets = perturb.apply(images, targets, batch_idx, device)
+        if graphs.usable(train_loader, perturbed_images):
+            graphs.step(images, train_loader.last_ids_dev, targets)
+            continue
         optimizer.zero_grad()
-        _announce_ids(model, train_loader, allowed=not (active and perturb.kind in IMAGE_PERTURBATIONS))
+        _announce_ids(model, train_loader, allowed=not perturbed_images)
         predictions = model(images)
         loss = criterion(predictions, targets)
         bad = guard.check(predictions, loss.reshape(1), targets)

@@ -52,6 +52,7 @@ class ResidentStore:
         self.images = images.to(self.device, torch.float32).contiguous()
         self.targets = None if targets is None else targets.to(self.device, torch.float32).contiguous()
         self.ids = [image_id(n) for n in self.names]
+        self.ids_dev = torch.tensor(self.ids, dtype=torch.int64, device=self.device)
 
     def __len__(self):
         return len(self.names)
@@ -70,6 +71,7 @@ class ResidentLoader:
                                         generator=generator)
         self.batch_size = batch_size
         self.last_ids = None
+        self.last_ids_dev = None   # the same ids as a device tensor (no host round trip)
 
     def __len__(self):
         return len(self._index_loader)
@@ -82,10 +84,11 @@ class ResidentLoader:
             host = idx.tolist()
             dev = idx.to(st.device)
             self.last_ids = [st.ids[i] for i in host]
+            self.last_ids_dev = st.ids_dev.index_select(0, dev)
             names = [st.names[i] for i in host]
             images = st.images.index_select(0, dev)
             if st.targets is None:
                 yield names, images
             else:
                 yield names, images, st.targets.index_select(0, dev)
-        self.last_ids = None
+        self.last_ids = self.last_ids_dev = None

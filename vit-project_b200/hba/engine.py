@@ -472,7 +472,10 @@ class Engine:
         if self.trunk_cache is not None and ids is not None and L >= 2 and native:
             if len(ids) != B:
                 raise RuntimeError("libhba: batch_ids does not match the image batch")
-            cache_ctx = self.trunk_cache.lookup(self, ids)
+            if isinstance(ids, torch.Tensor):
+                cache_ctx = self.trunk_cache.lookup_device_ids(self, ids)
+            else:
+                cache_ctx = self.trunk_cache.lookup(self, ids)
         if cache_ctx is not None and cache_ctx["hit"]:
             x, tw = cache_ctx["x"], self.vis
         else:
@@ -610,6 +613,19 @@ class TrunkCache:
             self.a = torch.empty(self.capacity, width, device=eng.device)
             self.present = set()
             self.stamp = stamp
+
+    def all_present(self, ids):
+        return all(int(i) in self.present for i in ids)
+
+    def lookup_device_ids(self, eng, ids_dev):
+        """Hit path with the ids already on the device (the caller has checked `all_present`): no host
+        work, no host->device copy - what a captured CUDA graph of the cached step replays."""
+        self._ensure(eng)
+        B, d = ids_dev.numel(), eng.vis.d
+        x = torch.index_select(self.x, 0, ids_dev, out=eng._buf("v.x", (B, self.x.shape[1])))
+        a = torch.index_select(self.a, 0, ids_dev, out=eng._buf("v.acache", (B, self.x.shape[1])))
+        return {"cache": self, "ids": None, "hit": True, "x": x.view(B * eng.vis.T, d),
+                "a": a.view(B * eng.vis.T, d)}
 
     def lookup(self, eng, ids):
         self._ensure(eng)

@@ -243,9 +243,12 @@ def cos_head_bwd(img, txt, logit_scale, d_img, d_txt, *, d_pred=None, pred=None,
                                        _stream()), "hba_cos_head_bwd")
 
 
-def adamw_multi(ptr_table, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step, skip_flag=None):
+def adamw_multi(ptr_table, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step, skip_flag=None,
+                step_dev=None):
+    """step: host step count (>= 1), or 0 with step_dev = device int32 holding the count."""
     check(_lib.load().hba_adamw_multi(_p(ptr_table), _p(sizes), n, total, lr, beta1, beta2, eps,
-                                      weight_decay, step, _p(skip_flag), _stream()), "hba_adamw_multi")
+                                      weight_decay, step, _p(step_dev), _p(skip_flag), _stream()),
+          "hba_adamw_multi")
 
 
 def sgd_multi(ptr_table, sizes, n, total, lr, momentum, weight_decay, first_step, skip_flag=None):

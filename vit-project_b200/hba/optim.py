@@ -27,8 +27,33 @@ def _check(p):
 
 
 class FusedAdamW(torch.optim.AdamW):
+    """The step count lives on the device (one int32 per param group, advanced only by steps that are
+    not skipped — exactly the reference, whose NaN guard `continue`s before optimizer.step, NEW:989-998)
+    so that a whole training step can be captured into a CUDA graph; torch's per-parameter
+    ``state[p]["step"]`` tensors are refreshed from it whenever the state is read through
+    ``state_dict()`` (what the reference's checkpoints save, NEW:712)."""
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False)
+        self._tables = {}
+        self._step_dev = {}   # group index -> device int32 [1]
+
+    def sync_state(self):
+        """Device step counters -> ``state[p]["step"]`` (one small device read per group)."""
+        for gi, ctr in self._step_dev.items():
+            n = float(int(ctr))
+            for p in self.param_groups[gi]["params"]:
+                st = self.state.get(p)
+                if st is not None and "step" in st:
+                    st["step"] = torch.tensor(n, dtype=torch.float32)
+
+    def state_dict(self):
+        self.sync_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._step_dev = {}
         self._tables = {}
 
     def zero_grad(self, set_to_none=False):
@@ -68,12 +93,17 @@ class FusedAdamW(torch.optim.AdamW):
                 cached = (key, _table([ps, grads, m, v], ps[0].device))
                 self._tables[gi] = cached
             table, sizes, n, total = cached[1]
-            step = int(self.state[ps[0]]["step"]) + 1
-            for p in ps:
-                self.state[p]["step"] += 1
+            ctr = self._step_dev.get(gi)
+            if ctr is None:
+                ctr = torch.tensor([int(self.state[ps[0]]["step"])], dtype=torch.int32, device=ps[0].device)
+                self._step_dev[gi] = ctr
+            if skip_flag is None:
+                ctr += 1
+            else:
+                ctr += (skip_flag.reshape(1) == 0).to(torch.int32)
             b1, b2 = group["betas"]
             ops.adamw_multi(table, sizes, n, total, float(group["lr"]), b1, b2, group["eps"],
-                            group["weight_decay"], step, skip_flag)
+                            group["weight_decay"], 0, skip_flag, step_dev=ctr)
             self._keepalive = grads
         return loss
 
