@@ -427,6 +427,14 @@ def main():
     else:
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    shapes = {}
+    for (M, N, K, ns, a, b) in prof:
+        e = shapes.setdefault((M, N, K), [0, 0.0])
+        e[0] += 1
+        e[1] += a.elapsed_time(b)
+    by_shape = [{"M": M, "N": N, "K": K, "launches_per_step": n / args.steps, "us_per_launch": 1e3 * t / n,
+                 "tflops": 2.0 * M * N * K * n / (t / 1e3) / 1e12}
+                for (M, N, K), (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:12]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tpath):
@@ -446,7 +454,7 @@ def main():
                      "peak_source": peak_src, "gemm_launches_per_step": len(prof) / args.steps,
                      "gemm_flops_per_step": flops / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,
-                     "gemm_share_of_step": gemm_ms / ms},
+                     "gemm_share_of_step": gemm_ms / ms, "by_shape": by_shape},
     }
     if not args.no_sweep:
         del model, opt

@@ -22,6 +22,7 @@ import torch.nn as nn
 
 from . import engine as _engine
 from . import ops
+from .dp import BucketAllReducer, fold_world_size, layout_buckets
 from .ops import (HBA_ACT_GELU_ERF, HBA_ACT_GELU_ERF_GRAD, Operand)
 
 LN_EPS = 1e-6
@@ -264,17 +265,13 @@ class ViTEngine:
         for i in reversed(range(len(m.blocks))):
             groups.append((f"block{i}", list(m.blocks[i].parameters())))
         groups.append(("embed", [m.cls_token, m.pos_embed, m.patch_embed.proj.weight, m.patch_embed.proj.bias]))
-        pad4 = lambda n: (n + 3) // 4 * 4  # every gradient starts 16-byte aligned (GEMM epilogue stores)
-        total = sum(pad4(p.numel()) for _, ps in groups for p in ps)
+        total, offsets, self.bucket_slices = layout_buckets(groups)
         self.flat_grad = torch.zeros(total, device=self.device)
-        self.grad_of, self.bucket_slices = {}, []
-        off = 0
-        for name, ps in groups:
-            start = off
+        self.grad_of = {}
+        for _, ps in groups:
             for p in ps:
-                self.grad_of[id(p)] = self.flat_grad[off:off + p.numel()].view_as(p)
-                off += pad4(p.numel())
-            self.bucket_slices.append((name, start, off))
+                off, n = offsets[id(p)]
+                self.grad_of[id(p)] = self.flat_grad[off:off + n].view_as(p)
 
     def backward(self, d_logits, on_bucket_ready=None):
         """Fills the flat gradient buffer (bucket by bucket, calling `on_bucket_ready(name, flat_slice)`
@@ -459,7 +456,8 @@ class DataParallelTrainer:
         self.model, self.eng = model, get_engine(model)
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
         self.group = process_group
-        self.world = self.dist.get_world_size(process_group) if self.dist else 1
+        self.reducer = BucketAllReducer(self.dist, process_group)
+        self.world = self.reducer.world
         self.lr, self.momentum, self.wd = lr, momentum, weight_decay
         self.param_groups = [{"lr": lr}]  # so that CosineAnnealingLRWithWarmup can drive it
         self._mom = None
@@ -467,9 +465,7 @@ class DataParallelTrainer:
         self._table = None
 
     def broadcast_parameters(self):
-        if self.dist:
-            for p in self.model.parameters():
-                self.dist.broadcast(p.data, src=0, group=self.group)
+        self.reducer.broadcast_parameters(self.model.parameters())
 
     def step(self, images, labels):
         """One training step; returns (loss, top-1 hits) as device tensors.  With use_graph the step's
@@ -509,17 +505,9 @@ class DataParallelTrainer:
         d_logits = eng.d_logits_buffer(B)
         hits = eng._buf("hits", (1,), torch.int32)
         ops.softmax_ce(logits, labels, loss, d_logits, hits, eng._buf("ce_ws", (2 * B,)))
-        if self.world > 1:
-            d_logits.mul_(1.0 / self.world)
-        handles = []
-
-        def on_ready(name, flat):
-            if self.dist:
-                handles.append(self.dist.all_reduce(flat, group=self.group, async_op=True))
-
-        eng.backward(d_logits, on_bucket_ready=on_ready)
-        for h in handles:
-            h.wait()
+        fold_world_size(d_logits, self.world)
+        eng.backward(d_logits, on_bucket_ready=self.reducer.on_bucket_ready)
+        self.reducer.wait()
         self._sgd()
         return loss, hits
 
