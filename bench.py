@@ -97,6 +97,44 @@ def cpu_step_fn(model, n_images):
     return step
 
 
+def eager_gpu_baseline(args, device):
+    import torch
+    model = build_cpu_reference(args.backbone).to(device)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(args.batch, 3, 224, 224, generator=g).to(device)
+    targets = (torch.randn(args.batch, N_CLASSES, generator=g) * 9.5 + 5.75).to(device)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=3e-4)
+    crit = torch.nn.MSELoss()
+    res = {}
+    for tag, ctx in (("fp32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        def step():
+            opt.zero_grad()
+            if ctx is None:
+                loss = crit(model(images), targets)
+            else:
+                with ctx:
+                    loss = crit(model(images).float(), targets)
+            loss.backward()
+            opt.step()
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        res[tag] = {"value": args.batch * reps / (e0.elapsed_time(e1) / 1e3), "unit": UNIT,
+                    "ms_per_step": e0.elapsed_time(e1) / reps}
+    res["what"] = (f"oracle port (oracle/clip_ref.py + dora_ref.py) on cuda, batch {args.batch}, fwd+bwd+AdamW, "
+                   "text tower recomputed; torch eager, allow_tf32 off")
+    del model, opt
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_reference(args):
     """The reference's CPU path (restated: oracle port) on all host cores; one step = a bounded
     sample of `cpu_sample_images` images of the same workload."""
@@ -489,6 +527,13 @@ def main():
                                "kind": "port",
                                "sample": f"{reps} training steps of {n} images (same model, fwd+bwd+AdamW, "
                                          "text tower recomputed), oracle port in PyTorch fp32"}
+        # BASELINE.md 3 "also report": the same oracle port run by PyTorch eager ON THIS B200 (library
+        # kernels: cuBLAS / SDPA), fp32 and bf16 autocast, full batch - the bar a user of the reference
+        # would get from `model.to('cuda')` alone.  A reported baseline, never part of the product path.
+        try:
+            out["cpu_baseline"]["torch_eager_same_gpu"] = eager_gpu_baseline(args, device)
+        except Exception as exc:   # reporting only
+            out["cpu_baseline"]["torch_eager_same_gpu"] = {"error": str(exc)[:200]}
     if rank == 0:
         print(json.dumps(out))
     sys.stdout.flush()

@@ -25,7 +25,13 @@ namespace hba {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, each takes half of the columns
+// Epilogue geometry.  16 warps (four per TMEM lane quarter, each draining a quarter of the tile's
+// columns in 32 x 16 chunks): the fused epilogues (GELU / GELU' / residual / two outputs) are issue- and
+// latency-bound on the CUDA cores, and with 8 warps (2 per scheduler, 45 % issue utilisation) they, not
+// the tensor pipe, set the tile time of every short-K GEMM (K = 768: 11 us epilogue vs 7 us main loop).
+// 18 warps x 32 threads caps the kernel at 112 registers per thread; the 16-column chunk fits.
+constexpr int kEpiWarps = 16;
+constexpr int kChunkCols = 16;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 // CG = CTAs per UMMA (cta_group): with CG == 2 a CTA pair computes a 256 x BN tile, each CTA staging
@@ -38,7 +44,7 @@ struct GemmCfg {
   static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStages = (192 * 1024) / (kABytes + kBBytes) > 8 ? 8 : (192 * 1024) / (kABytes + kBBytes);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kStagingBytes = kEpiWarps * 4096;  // per-warp transposition tiles of the epilogue
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kChunkCols * 4;  // per-warp transposition tiles of the epilogue
   static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + kStagingBytes + 1024 /*align*/ + 256 /*bars*/;
 };
 
@@ -126,7 +132,7 @@ __device__ __forceinline__ float gelu_erf_grad(float a) {
 __device__ __forceinline__ void epilogue_chunk_transposed(const GemmArgs& g, const uint32_t* r, int row,
                                                           int col) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < kChunkCols; ++j) {
     if (col + j < g.N) {
       float v = __uint_as_float(r[j]) * g.alpha;
       if (g.bias) v += __ldg(g.bias + col + j);
@@ -139,6 +145,21 @@ __device__ __forceinline__ void epilogue_chunk_transposed(const GemmArgs& g, con
               __float2bfloat16_rn(v - __bfloat162float(h));
       }
     }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* r) {
+  static_assert(kChunkCols == 16 || kChunkCols == 32, "epilogue chunk is 16 or 32 columns");
+  if constexpr (kChunkCols == 32) {
+    tmem_ld_32x32b_x32(taddr, r);
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
   }
 }
 
@@ -193,31 +214,39 @@ __device__ __forceinline__ float act_runtime(int act, float v, float a) {
   }
 }
 
-// one 32-row x 32-column chunk of the tile; `r` = this thread's accumulator row (lane = row),
-// `stage` = shared-space address of this warp's private 4 KB staging tile.  ACT is a template
-// parameter: each kernel instance carries only its own activation code (the erf variants are long and
-// a kernel with all five thrashed the instruction cache: stall_no_inst was the #2 stall reason)
+// one 32-row x CC-column chunk of the tile (CC = kChunkCols); `r` = this thread's accumulator row
+// (lane = row), `stage` = shared-space address of this warp's private staging tile (32 rows x CC fp32).
+// ACT is a template parameter: each kernel instance carries only its own activation code (the erf
+// variants are long and a kernel with all five thrashed the instruction cache).
+// After the transposition lane l owns the float4 at columns 4*(l % LPR) of rows RPA*i + l / LPR.
 template <int ACT>
 __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, float* __restrict__ out_f32,
                                                          const uint32_t* r, uint32_t stage, int row0,
                                                          int col0, int lane) {
-  const int cq = lane & 7, rsub = lane >> 3;
+  constexpr int CC = kChunkCols;
+  constexpr int LPR = CC / 4;       // lanes (float4 granules) per row
+  constexpr int RPA = 32 / LPR;     // rows covered by one warp-wide access
+  constexpr int NI = 32 / RPA;      // accesses per chunk
+  // 16-byte granule XOR swizzle by the row: conflict-free for the row-per-lane writes and the
+  // RPA-rows-per-access reads (LPR = 8: row & 7;  LPR = 4: (row >> 1) & 3, rows are 64 B apart)
+  auto swz = [](int row) { return LPR == 8 ? (row & 7) : ((row >> 1) & 3); };
+  const int cq = lane % LPR, rsub = lane / LPR;
   const int col = col0 + 4 * cq;
   const int nvalid = g.N - col;  // >= 4: the whole float4 is in range
   const bool vec = nvalid >= 4;
   constexpr bool kGrad = (ACT == HBA_ACT_QUICKGELU_GRAD || ACT == HBA_ACT_GELU_ERF_GRAD);
   // loads that do not depend on the accumulator are issued first (they overlap the transposition)
   Vec4 bias = {{0.f, 0.f, 0.f, 0.f}};
-  Vec4 res[8];
-  Vec4 aux[kGrad ? 8 : 1];
+  Vec4 res[NI];
+  Vec4 aux[kGrad ? NI : 1];
   if (vec) {
     if (g.bias) bias = ld4_f32(g.bias + col);
     if constexpr (kGrad) {
-      // all eight pre-activation vectors in flight at once (one after the other inside the math loop
-      // they cost eight exposed DRAM round trips per chunk: 785 us for the fc2 dX GEMM of ViT-B/16)
+      // all pre-activation vectors of the chunk in flight at once (one after the other inside the math
+      // loop they cost one exposed DRAM round trip each: 785 us for the fc2 dX GEMM of ViT-B/16)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = min(row0 + 4 * i + rsub, g.M - 1);
+      for (int i = 0; i < NI; ++i) {
+        const int row = min(row0 + RPA * i + rsub, g.M - 1);
         if (g.aux_dtype == HBA_DT_F32) {
           const float* p = static_cast<const float*>(g.aux) + (size_t)row * g.ld_aux + col;
           if ((g.ld_aux & 3) == 0) aux[i] = ld4_f32(p);
@@ -232,8 +261,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
     }
     if (g.residual) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4 * i + rsub;
+      for (int i = 0; i < NI; ++i) {
+        const int row = row0 + RPA * i + rsub;
         res[i] = Vec4{{0.f, 0.f, 0.f, 0.f}};
         if (row < g.M) res[i] = ld4_f32(g.residual + (size_t)row * g.ldr + col);
       }
@@ -241,29 +270,29 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
   }
   if (g.alpha == 1.0f) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+    for (int j = 0; j < LPR; ++j)
+      sts128(stage + 16u * (lane * LPR + (j ^ swz(lane))), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(stage + 16u * (lane * 8 + (j ^ (lane & 7))), __uint_as_float(r[4 * j]) * g.alpha,
+    for (int j = 0; j < LPR; ++j)
+      sts128(stage + 16u * (lane * LPR + (j ^ swz(lane))), __uint_as_float(r[4 * j]) * g.alpha,
              __uint_as_float(r[4 * j + 1]) * g.alpha, __uint_as_float(r[4 * j + 2]) * g.alpha,
              __uint_as_float(r[4 * j + 3]) * g.alpha);
   }
   __syncwarp();
   if (vec) {
-    Vec4 v[8];
+    Vec4 v[NI];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + rsub;
-      const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
+    for (int i = 0; i < NI; ++i) {
+      const int rl = RPA * i + rsub;
+      const float4 t = lds128(stage + 16u * (rl * LPR + (cq ^ swz(rl))));
       v[i] = Vec4{{t.x + bias.x[0], t.y + bias.x[1], t.z + bias.x[2], t.w + bias.x[3]}};
     }
     if (g.pre_out) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4 * i + rsub;
+      for (int i = 0; i < NI; ++i) {
+        const int row = row0 + RPA * i + rsub;
         if (row >= g.M) continue;
         if (g.pre_dtype == HBA_DT_F32)
           st4_f32(static_cast<float*>(g.pre_out) + (size_t)row * g.ld_pre + col, v[i]);
@@ -273,38 +302,38 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
     }
     if constexpr (ACT == HBA_ACT_QUICKGELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[i].x[e] = quickgelu(v[i].x[e]);
     } else if constexpr (ACT == HBA_ACT_GELU_ERF) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[i].x[e] = gelu_erf(v[i].x[e]);
     } else if constexpr (kGrad) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           v[i].x[e] *= (ACT == HBA_ACT_QUICKGELU_GRAD) ? quickgelu_grad(aux[i].x[e]) : gelu_erf_grad(aux[i].x[e]);
     }
     if (g.residual) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < NI; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[i].x[e] += res[i].x[e];
     }
     if (out_f32) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4 * i + rsub;
+      for (int i = 0; i < NI; ++i) {
+        const int row = row0 + RPA * i + rsub;
         if (row < g.M) st4_f32(out_f32 + (size_t)row * g.ld_f32 + col, v[i]);
       }
     }
     if (g.out_bf16) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + 4 * i + rsub;
+      for (int i = 0; i < NI; ++i) {
+        const int row = row0 + RPA * i + rsub;
         if (row >= g.M) continue;
         __nv_bfloat16* p = g.out_bf16 + (size_t)row * g.ld_bf16 + col;
         st4_bf16(p, v[i]);
@@ -320,11 +349,11 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
   } else if (nvalid > 0) {
     // ragged last columns (N % 4 != 0): element-wise, not unrolled (cold path)
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + rsub;
+    for (int i = 0; i < NI; ++i) {
+      const int rl = RPA * i + rsub;
       const int row = row0 + rl;
       if (row >= g.M) continue;
-      const float4 t = lds128(stage + 16u * (rl * 8 + (cq ^ (rl & 7))));
+      const float4 t = lds128(stage + 16u * (rl * LPR + (cq ^ swz(rl))));
       const float tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll 1
       for (int e = 0; e < nvalid; ++e) {
@@ -517,8 +546,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
-    constexpr int kChunksPerWarp = BN / 32 / (kEpiWarps / 4);
+    const int part = (warp - 2) >> 2;  // which 1 / (kEpiWarps / 4) of the tile's columns this warp drains
+    constexpr int kParts = kEpiWarps / 4;
+    constexpr int kChunksPerWarp = BN / kChunkCols / kParts;
     const uint32_t tempty_addr[2] = {
         (CG == 2) ? mapa_u32(&tempty_bar[0], 0) : smem_u32(&tempty_bar[0]),
         (CG == 2) ? mapa_u32(&tempty_bar[1], 0) : smem_u32(&tempty_bar[1])};
@@ -532,17 +562,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const int tl = it % total_tiles;
       const int prow = (tl / num_n_tiles) * TM + rank * BM + q * 32 + lane;
       if (prow >= g.M) return;
-      const int c0 = (tl % num_n_tiles) * BN + half * (BN / 2);
+      const int c0 = (tl % num_n_tiles) * BN + part * (BN / kParts);
       if (g.residual) {
         const char* p = reinterpret_cast<const char*>(g.residual + (size_t)prow * g.ldr + c0);
 #pragma unroll
-        for (int b = 0; b < BN / 2 * 4; b += 128)
+        for (int b = 0; b < BN / kParts * 4; b += 128)
           if (c0 + b / 4 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
       }
       if (g.aux) {
         const int esz = g.aux_dtype == HBA_DT_F32 ? 4 : 2;
         const char* p = static_cast<const char*>(g.aux) + ((size_t)prow * g.ld_aux + c0) * esz;
-        for (int b = 0; b < BN / 2 * esz; b += 128)
+        for (int b = 0; b < BN / kParts * esz; b += 128)
           if (c0 + b / esz < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
       }
     };
@@ -557,17 +587,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half * kChunksPerWarp; c < (half + 1) * kChunksPerWarp; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32;
-        tmem_ld_32x32b_x32(taddr, r);
+      for (int c = part * kChunksPerWarp; c < (part + 1) * kChunksPerWarp; ++c) {
+        uint32_t r[kChunkCols];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * kChunkCols;
+        tmem_ld_chunk(taddr, r);
         tmem_ld_wait();
-        const int col = n0 + c * 32;
+        const int col = n0 + c * kChunkCols;
         if (g.debug & 1) continue;
         if (g.transpose_out) {
           if (row < g.M && col < g.N) epilogue_chunk_transposed(g, r, row, col);
         } else if (m0 + q * 32 < g.M && col < g.N) {  // warp-uniform
-          epilogue_chunk_coalesced<ACT>(g, out_f32, r, smem_u32(sStage) + (warp - 2) * 4096, m0 + q * 32, col, lane);
+          epilogue_chunk_coalesced<ACT>(g, out_f32, r, smem_u32(sStage) + (warp - 2) * (32 * kChunkCols * 4), m0 + q * 32, col, lane);
         }
       }
       tc_fence_before();
