@@ -403,21 +403,21 @@ def main():
     host_targets = (torch.randn(B, N_CLASSES, generator=g) * 9.5 + 5.75).pin_memory()
     dev_images, dev_targets = host_images.to(device), host_targets.to(device)
 
+    # functions._pipeline_core.TrainStep is the step `train_model` itself runs for every batch
+    # (NEW:985-1003: zero_grad, CLIPHBA forward, MSE, NaN guard, backward, AdamW): no trunk-cache ids are
+    # passed, so it is the full-trunk step, replayed as a CUDA graph after its first two calls
+    import functions._pipeline_core as core
+    train_step = core.TrainStep.of(model, opt, crit, device)
+
     def step_resident():
-        opt.zero_grad()
-        loss = crit(model(dev_images), dev_targets)
-        loss.backward()
-        opt.step()
-        return loss
+        train_step(dev_images, dev_targets)
+        return train_step.last_loss
 
     def step_e2e():
-        images = host_images.to(device, non_blocking=True)
+        images = host_images.to(device, non_blocking=True)    # pinned host -> device, inside the timed region
         targets = host_targets.to(device, non_blocking=True)
-        opt.zero_grad()
-        loss = crit(model(images), targets)
-        loss.backward()
-        opt.step()
-        return float(loss)  # device -> host read of the step's result
+        train_step(images, targets)
+        return float(train_step.last_loss)  # device -> host read of the step's result
 
     def barrier():
         if dist is not None:
@@ -448,8 +448,13 @@ def main():
         step_resident()
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches, prof = timed(step_resident, args.steps, profile_gemm=True)
+    ms, launches, _ = timed(step_resident, args.steps)
     clocks = sampler.stop()
+    # roofline of the dominant kernel: CUDA events around every GEMM launch, which needs the launches to
+    # come from the host - the same K steps once more with graph replay switched off (identical kernels)
+    os.environ["HBA_STEP_GRAPH"] = "0"
+    ms_eager, _, prof = timed(step_resident, args.steps, profile_gemm=True)
+    os.environ.pop("HBA_STEP_GRAPH")
     loss_val = float(step_resident())
     for _ in range(2):
         step_e2e()
@@ -492,7 +497,10 @@ def main():
                      "peak_source": peak_src, "gemm_launches_per_step": len(prof) / args.steps,
                      "gemm_flops_per_step": flops / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,
-                     "gemm_share_of_step": gemm_ms / ms, "by_shape": by_shape},
+                     "gemm_share_of_step": gemm_ms / ms_eager, "eager_ms_per_step": ms_eager / args.steps,
+                     "how": "CUDA events around every gemm_tc_kernel launch over K host-launched steps of the "
+                            "same workload, run right after the timed (graph-replayed) region",
+                     "by_shape": by_shape},
     }
     if not args.no_sweep:
         del model, opt

@@ -356,7 +356,7 @@ def _announce_ids(model, loader, allowed=True):
 
 class _CachedForwardGraphs:
     """CUDA graphs of the no-grad forward on trunk-cached images (evaluation / RSA batches), one per
-    batch size; see _CachedStepGraphs.  __call__ returns a fresh tensor (a copy of the graph's static
+    batch size; see TrainStep.  __call__ returns a fresh tensor (a copy of the graph's static
     output)."""
 
     def __init__(self, model):
@@ -542,62 +542,98 @@ class _BadBatchFlag:
         return self.step
 
 
-class _CachedStepGraphs:
-    """CUDA graphs of the frozen-trunk-cached training step, one per batch size.
+class TrainStep:
+    """One optimisation step of NEW:985-1003 (zero_grad -> forward -> MSE -> NaN guard -> backward ->
+    AdamW -> loss accumulation), launched either kernel by kernel or as a replayed CUDA graph.
 
-    Once every image of a batch is in the trunk cache the step (cache gather -> live blocks -> cosine
-    head -> MSE -> NaN guard -> backward -> DoRA merge backward -> fused AdamW -> loss accumulation)
-    is ~90 small launches of ~0.6 ms GPU time behind ~4 ms of Python: captured once, it replays
-    with the image ids and the (possibly perturbed) targets copied into static buffers.  Same kernels,
-    same arguments, same order as the eager step - results are bit-identical (tests/test_gpu_pipeline.py).
-    Set HBA_STEP_GRAPH=0 to disable."""
+    Three ways to run the SAME kernels with the same arguments in the same order:
+      * eager          - non-fused optimiser, HBA_STEP_GRAPH=0, the first step of a shape (it allocates
+                         every workspace / gradient / optimiser-state tensor the graphs reuse), and steps
+                         that FILL the frozen-trunk cache (host-side bookkeeping of the filled ids);
+      * "cached" graph - every image of the batch is in the trunk cache: ~90 launches / 1.5 ms of GPU
+                         time behind ~4 ms of Python; static inputs are the image ids and the targets;
+      * "full" graph   - no cache for this batch (image perturbations, cache disabled): the ~335
+                         launches of the whole trunk + text tower step; static inputs are the images
+                         and the targets.
+    Target perturbations (random targets / label shuffle, Philox streams of NEW:918-959) are applied by
+    the caller before the step.  Graph replay is bit-identical to the eager step
+    (tests/test_gpu_pipeline.py::test_captured_step_graphs_are_bit_identical_to_eager_steps).
+    `total` accumulates loss * batch over un-skipped steps, `last_loss` holds the last step's loss,
+    `guard.total` counts skipped (NaN/Inf) batches - all on the device, read once per epoch."""
 
-    def __init__(self, model, optimizer, criterion, guard, total, device):
-        self.model, self.opt, self.crit, self.guard, self.total = model, optimizer, criterion, guard, total
-        self.device = device
+    def __init__(self, model, optimizer, criterion, device):
+        self.model, self.opt, self.crit, self.device = model, optimizer, criterion, device
+        self.total = torch.zeros((), device=device, dtype=torch.float64)
+        self.last_loss = torch.zeros((), device=device, dtype=torch.float32)
+        self.guard = _BadBatchFlag(device)
         self.eng = _engine_of(model)
+        self.fused = isinstance(optimizer, FusedAdamW)
         self.entries = {}
         self.warm = set()
 
-    def usable(self, loader, perturbed_images):
-        eng = self.eng
-        return (os.environ.get("HBA_STEP_GRAPH", "1") != "0" and eng is not None and eng.trunk_cache is not None
-                and not perturbed_images and isinstance(self.opt, FusedAdamW)
-                and getattr(loader, "last_ids_dev", None) is not None
-                and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids))
+    @staticmethod
+    def of(model, optimizer, criterion, device):
+        st = model.__dict__.get("_hba_train_step")
+        if st is None or st.opt is not optimizer or st.crit is not criterion:
+            st = model.__dict__["_hba_train_step"] = TrainStep(model, optimizer, criterion, device)
+        return st
 
-    def _body(self, images, ids_dev, targets):
+    def start_epoch(self):
+        if self.eng is not None and self.eng.device is not None:
+            self.eng.ensure(self.eng.device)   # frozen weights changed since the graphs were captured?
+        self.total.zero_()
+        self.guard.total.zero_()
+
+    def _graphs_on(self):
+        return os.environ.get("HBA_STEP_GRAPH", "1") != "0" and self.eng is not None and self.fused
+
+    def _body(self, images, ids, targets):
         self.opt.zero_grad()
-        self.eng.batch_ids = ids_dev
+        if self.eng is not None:
+            self.eng.batch_ids = ids
         predictions = self.model(images)
         loss = self.crit(predictions, targets)
         bad = self.guard.check(predictions, loss.reshape(1), targets)
         loss.backward()
-        self.opt.step(skip_flag=bad)
+        if self.fused:
+            self.opt.step(skip_flag=bad)
+        elif int(bad) == 0:
+            self.opt.step()
+        self.last_loss.copy_(loss.detach())
         self.total += torch.where(bad[0] == 0, loss.detach().double(), torch.zeros_like(self.total)) * images.size(0)
 
-    def step(self, images, ids_dev, targets):
-        B = images.shape[0]
-        key = (B, tuple(images.shape[1:]), self.eng._stamp, self.eng.precision)
+    def __call__(self, images, targets, ids_host=None, ids_dev=None):
+        """ids_host / ids_dev: trunk-cache ids of the batch (None for perturbed images / no cache)."""
+        eng = self.eng
+        cache = eng.trunk_cache if eng is not None else None
+        have_ids = cache is not None and ids_host is not None
+        cached = have_ids and ids_dev is not None and cache.x is not None and cache.all_present(ids_host)
+        if not self._graphs_on() or (have_ids and not cached):
+            return self._body(images, ids_host if have_ids else None, targets)
+        mode = "cached" if cached else "full"
+        key = (mode, tuple(images.shape), eng._stamp, eng.precision, eng.cache_text)
         if key not in self.warm:
-            # first cached step of this shape runs eagerly: it allocates every workspace, gradient and
-            # optimiser-state tensor the captured step will reuse
             self.warm.add(key)
-            return self._body(images, ids_dev, targets)
+            return self._body(images, ids_dev if cached else None, targets)
         entry = self.entries.get(key)
         if entry is None:
-            s_img = torch.zeros_like(images)   # never read on the cached path; carries the shape
-            s_ids, s_tgt = ids_dev.clone(), targets.clone()
+            # (the cached path never reads the images: a zero tensor carries the shape)
+            s_img = torch.zeros_like(images) if cached else images.clone()
+            s_ids = ids_dev.clone() if cached else None
+            s_tgt = targets.clone()
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             c0 = ops.COUNTERS["launches"]
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 self._body(s_img, s_ids, s_tgt)
-            entry = (graph, s_ids, s_tgt, ops.COUNTERS["launches"] - c0)
+            entry = (graph, s_img, s_ids, s_tgt, ops.COUNTERS["launches"] - c0)
             ops.COUNTERS["launches"] = c0
             self.entries[key] = entry
-        graph, s_ids, s_tgt, n_launch = entry
-        s_ids.copy_(ids_dev, non_blocking=True)
+        graph, s_img, s_ids, s_tgt, n_launch = entry
+        if cached:
+            s_ids.copy_(ids_dev, non_blocking=True)
+        else:
+            s_img.copy_(images, non_blocking=True)
         s_tgt.copy_(targets, non_blocking=True)
         graph.replay()
         ops.COUNTERS["launches"] += n_launch
@@ -607,21 +643,8 @@ def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, ep
                     log=print):
     """One pass over train_loader (NEW:873-1004 / BASE:644-659): returns the sample-weighted mean
     loss, read from the device once."""
-    state = model.__dict__.get("_hba_train_state")
-    if state is None or state["optimizer"] is not optimizer or state["criterion"] is not criterion:
-        # persistent per (model, optimizer): the loss accumulator and NaN guard are static inputs of the
-        # captured step graphs, which are reused across epochs
-        total = torch.zeros((), device=device, dtype=torch.float64)
-        guard = _BadBatchFlag(device)
-        state = {"optimizer": optimizer, "criterion": criterion, "total": total, "guard": guard,
-                 "graphs": _CachedStepGraphs(model, optimizer, criterion, guard, total, device)}
-        model.__dict__["_hba_train_state"] = state
-    total, guard, graphs = state["total"], state["guard"], state["graphs"]
-    if graphs.eng is not None and graphs.eng.device is not None:
-        graphs.eng.ensure(graphs.eng.device)   # frozen weights changed since the graphs were captured?
-    total.zero_()
-    guard.total.zero_()
-    fused = isinstance(optimizer, FusedAdamW)
+    step = TrainStep.of(model, optimizer, criterion, device)
+    step.start_epoch()
     active = perturb is not None and perturb.active(epoch)
     perturbed_images = active and perturb.kind in IMAGE_PERTURBATIONS
     bar = tqdm(enumerate(train_loader), total=len(train_loader), desc=f"Epoch {epoch + 1}/{epochs}",
@@ -631,24 +654,15 @@ def train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, ep
         targets = targets.to(device, non_blocking=True)
         if active:
             images, targets = perturb.apply(images, targets, batch_idx, device)
-        if graphs.usable(train_loader, perturbed_images):
-            graphs.step(images, train_loader.last_ids_dev, targets)
-            continue
-        optimizer.zero_grad()
-        _announce_ids(model, train_loader, allowed=not perturbed_images)
-        predictions = model(images)
-        loss = criterion(predictions, targets)
-        bad = guard.check(predictions, loss.reshape(1), targets)
-        loss.backward()
-        if fused:
-            optimizer.step(skip_flag=bad)
-        elif int(bad) == 0:
-            optimizer.step()
-        total += torch.where(bad[0] == 0, loss.detach().double(), torch.zeros_like(total)) * images.size(0)
-    n_bad = int(guard.total)
+        if perturbed_images:   # never cache (or serve from the cache) a perturbed image
+            step(images, targets)
+        else:
+            step(images, targets, getattr(train_loader, "last_ids", None),
+                 getattr(train_loader, "last_ids_dev", None))
+    n_bad = int(step.guard.total)
     if n_bad:
         log(f"ERROR: NaN/Inf detected in {n_bad} batch(es) of epoch {epoch + 1}; they were skipped")
-    return float(total) / len(train_loader.dataset)
+    return float(step.total) / len(train_loader.dataset)
 
 
 def select_device(cuda_flag):
