@@ -388,6 +388,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/WARN) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     hba.set_precision(args.precision)
     if args.sweep_only:

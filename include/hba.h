@@ -94,6 +94,9 @@ typedef struct hba_gemm_params {
                          every (tile, K slice) is a work item; the slices are summed in a fixed order
                          (deterministic).  Needs k_workspace and a plain out_f32 epilogue, N % 4 == 0 */
   float* k_workspace; /* >= k_slices * M * N floats, 16-byte aligned */
+  float* colsum_partial; /* or NULL: [ceil(M / 32), N] fp32 receiving, per 32-row group, the column sums
+                            of the bf16 output (hi part) - the bias gradient of the previous Linear fused
+                            into the GEMM that produces its dY (VIT:143); sum the groups with hba_colsum */
 } hba_gemm_params;
 
 int hba_gemm_bf16(const hba_gemm_params* p, void* stream);

@@ -120,6 +120,31 @@ def test_gemm_split_k(M, N, K, slices, split):
     assert rel_err(outs[0], ref) < 2e-6 * math.sqrt(K)   # same products, different fp32 summation order
 
 
+@pytest.mark.parametrize("M,N,K", [(333, 512, 128), (1000, 3072, 256), (70, 256, 64)])
+def test_gemm_fused_bias_gradient_column_sums(M, N, K):
+    """colsum_partial: per 32-row group column sums of the bf16 output, emitted by the GELU'-epilogue
+    GEMM that produces dY (the fc1 bias gradient of the ViT backward); summed with hba_colsum."""
+    hba, ops = _imports()
+    from hba._lib import HBA_ACT_GELU_ERF_GRAD
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = (torch.randn(N, K, generator=g) * 0.2).to(DEV)
+    aux = torch.randn(M, N, generator=g).to(DEV).to(torch.bfloat16)
+    A, B = make_operand(ops, a, False), make_operand(ops, b, False)
+    out = ops.Operand.empty(M, N, False, DEV)
+    groups = (M + 31) // 32
+    part = torch.full((groups, N), float("nan"), device=DEV)
+    ops.gemm(A, B, M, act=HBA_ACT_GELU_ERF_GRAD, aux=aux, out=out, colsum_partial=part)
+    torch.cuda.synchronize()
+    got_out = out.buf[:, :N].float()
+    assert torch.isfinite(part).all()
+    want_part = torch.stack([got_out[32 * i:32 * i + 32].double().sum(0) for i in range(groups)])
+    assert float((part.double() - want_part).abs().max()) < 1e-4 * float(got_out.abs().max()) * 32
+    total = torch.empty(N, device=DEV)
+    ops.colsum(part, total, torch.empty(128 * N + 64, device=DEV))
+    assert rel_err(total, got_out.double().sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("rows,cols", [(1, 128), (777, 768), (5000, 1000), (50432, 768)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_colsum(rows, cols, dtype):

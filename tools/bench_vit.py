@@ -43,6 +43,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     hba.set_precision(a.precision)
     torch.manual_seed(0)

@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-nvidia-smi -L
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/bench_vit.py --batch 256 --steps 5 --warmup 3 > gpurun_out/vit_n2.json 2> gpurun_out/vit_n2.err; echo "vit n2 rc=$?"; cat gpurun_out/vit_n2.json; tail -5 gpurun_out/vit_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/bench_vit.py --batch 256 --steps 5 --warmup 3 --no-graph > gpurun_out/vit_n2_nograph.json 2> gpurun_out/vit_n2_nograph.err; echo "vit n2 nograph rc=$?"; cat gpurun_out/vit_n2_nograph.json; tail -5 gpurun_out/vit_n2_nograph.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"; cat gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-timeout 300 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench_n2.json')); print(d['n_gpus'], d['value'], d['e2e']['value'], d['sweep']['conditions_per_hour'], d['vit_b16']['value'], d['vit_b16']['ms_per_step'])"; tail -4 gpurun_out/bench_n2.err
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err; echo "ref n2 rc=$?"; cut -c1-300 gpurun_out/bench_ref_n2.json

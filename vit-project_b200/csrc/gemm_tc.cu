@@ -80,6 +80,7 @@ struct GemmArgs {
   int ld_bf16, out_lo_off;
   int transpose_out;
   int a_mn, b_mn;  // operand stored MN-major: [K rows, M (resp. N) columns]
+  float* colsum;   // optional [ceil(M / 32), N]: column sums of the bf16 output per 32-row group
   int k_slices;    // split-K: work item = (tile, K slice); slice s writes out_f32 + s * slice_stride
   size_t slice_stride;
   int debug;       // HBA_GEMM_DEBUG (measurement only): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA loads
@@ -329,6 +330,30 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
         const int row = row0 + RPA * i + rsub;
         if (row < g.M) st4_f32(out_f32 + (size_t)row * g.ld_f32 + col, v[i]);
       }
+    }
+    if (g.colsum) {
+      // bias gradient fused into the GEMM that produces dY: column sums of the bf16-rounded outputs of
+      // this 32-row x CC-column chunk; every (row group, column) is written by exactly one warp, the
+      // row groups are summed afterwards in a fixed order (hba_colsum) - deterministic
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if (row0 + RPA * i + rsub < g.M) {
+          s0 += __bfloat162float(__float2bfloat16_rn(v[i].x[0]));
+          s1 += __bfloat162float(__float2bfloat16_rn(v[i].x[1]));
+          s2 += __bfloat162float(__float2bfloat16_rn(v[i].x[2]));
+          s3 += __bfloat162float(__float2bfloat16_rn(v[i].x[3]));
+        }
+      }
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+      }
+      if (rsub == 0)
+        *reinterpret_cast<float4*>(g.colsum + (size_t)(row0 >> 5) * g.N + col) = make_float4(s0, s1, s2, s3);
     }
     if (g.out_bf16) {
 #pragma unroll
@@ -747,6 +772,10 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   g.out_bf16 = static_cast<__nv_bfloat16*>(p->out_bf16), g.ld_bf16 = p->ld_bf16;
   g.out_lo_off = p->out_lo_off, g.transpose_out = p->transpose_out;
   g.a_mn = p->a_mn_major, g.b_mn = p->b_mn_major;
+  g.colsum = p->colsum_partial;
+  if (p->colsum_partial)
+    HBA_REQUIRE(p->out_bf16 && !p->transpose_out && p->N % 4 == 0 && ((uintptr_t)p->colsum_partial & 15) == 0,
+                "hba_gemm_bf16: colsum_partial needs a bf16 output, N %% 4 == 0 and a 16-byte aligned buffer");
   g.k_slices = 1, g.slice_stride = 0;
   const int kblocks_total = (p->K + BK - 1) / BK;
   int slices = p->k_slices > 1 ? p->k_slices : 1;

@@ -34,6 +34,7 @@ class GemmParams(C.Structure):
         ("transpose_out", i32), ("max_ctas", i32),
         ("a_mn_major", i32), ("b_mn_major", i32),
         ("k_slices", i32), ("k_workspace", vp),
+        ("colsum_partial", vp),
     ]
 
 

@@ -92,7 +92,7 @@ def auto_k_slices(M, N, K, workers=74, max_slices=16):
 
 def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_ACT_NONE, aux=None,
          pre_out=None, out_f32=None, out: Operand = None, transpose_out=False, alpha=1.0,
-         max_ctas=0, a_mn=False, b_mn=False, K=None, k_slices=1, k_workspace=None):
+         max_ctas=0, a_mn=False, b_mn=False, K=None, k_slices=1, k_workspace=None, colsum_partial=None):
     """C[M,N] = epilogue(A . B^T) on the tcgen05 tensor pipe (hba_gemm_bf16).
     a_mn / b_mn: the operand is stored MN-major, i.e. as [K rows, M resp. N columns] (its Operand
     then has rows = K and K = M resp. N)."""
@@ -131,6 +131,9 @@ def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_AC
     p.max_ctas = max_ctas
     p.a_mn_major, p.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
     launches = 1
+    if colsum_partial is not None:
+        assert colsum_partial.dtype == torch.float32 and colsum_partial.numel() >= (M + 31) // 32 * N
+        p.colsum_partial = colsum_partial.data_ptr()
     if k_slices == "auto":
         k_slices = auto_k_slices(M, N, K)
     if k_slices > 1:

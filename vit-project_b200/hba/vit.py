@@ -353,11 +353,18 @@ class ViTEngine:
             self._dw_gemm(gy, hid, M, G(blk.mlp.fc2.weight))
             g_hid = self._opbuf("g_hid", M, 4 * d)
             g_hid_f = self._buf("g_hid_f", (M, 4 * d)) if sp else None
-            ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
-                     out_f32=g_hid_f)
+            if sp:
+                ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
+                         out_f32=g_hid_f)
+                ops.colsum(g_hid_f, G(blk.mlp.fc1.bias), cs_ws)
+            else:   # the fc1 bias gradient = colsum(g_hid) comes out of the same epilogue, per 32-row group
+                groups = (M + 31) // 32
+                cs_part = self._buf("cs_part", (groups, 4 * d))
+                ops.gemm(gy, self._wops[f"{i}.fc2"], M, b_mn=True, act=HBA_ACT_GELU_ERF_GRAD, aux=pre, out=g_hid,
+                         colsum_partial=cs_part)
+                ops.colsum(cs_part, G(blk.mlp.fc1.bias), cs_ws)
             # fc1
             self._dw_gemm(g_hid, ln2, M, G(blk.mlp.fc1.weight))
-            ops.colsum(g_hid_f if sp else g_hid.buf, G(blk.mlp.fc1.bias), cs_ws)
             d_ln = self._buf("d_ln", (M, d))
             ops.gemm(g_hid, self._wops[f"{i}.fc1"], M, b_mn=True, out_f32=d_ln)
             ln_backward(d_ln, x_mid, blk.norm2, gy, G(blk.attn.proj.bias))
