@@ -527,24 +527,33 @@ def main():
                             "same workload, run right after the timed (graph-replayed) region",
                      "by_shape": by_shape},
     }
+    out["host_cpus"] = os.cpu_count()
+    # The secondary sections must never cost the headline line: a failure is recorded and reported.
     if not args.no_sweep:
-        del model, opt
+        del model, opt, train_step
         torch.cuda.empty_cache()
-        sw = measure_sweep(args, device, world)
+        try:
+            sw = measure_sweep(args, device, world)
+        except Exception as exc:
+            sw = {"error": f"{type(exc).__name__}: {exc}"[:300], "sec_per_epoch_cached": float("nan")}
         if dist is not None:
             t = torch.tensor([sw["sec_per_epoch_cached"]], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sw["sec_per_epoch_cached"] = float(t)
-            sw["sec_per_condition"] = (sw["sec_first_epoch_cache_fill"] + sw["sec_second_epoch_graph_capture"]
-                                       + (EPOCHS_PER_CONDITION - 2) * float(t))
-            sw["conditions_per_hour"] = world * 3600.0 / sw["sec_per_condition"]
-            sw["blended_images_per_s"] = world * sw["images_per_epoch"] / float(t)
+            if "error" not in sw:
+                sw["sec_per_epoch_cached"] = float(t)
+                sw["sec_per_condition"] = (sw["sec_first_epoch_cache_fill"] + sw["sec_second_epoch_graph_capture"]
+                                           + (EPOCHS_PER_CONDITION - 2) * float(t))
+                sw["conditions_per_hour"] = world * 3600.0 / sw["sec_per_condition"]
+                sw["blended_images_per_s"] = world * sw["images_per_epoch"] / float(t)
         out["sweep"] = sw
     if not args.no_vit:
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        out["vit_b16"] = measure_vit(args, device, world, dist)
+        try:
+            out["vit_b16"] = measure_vit(args, device, world, dist)
+        except Exception as exc:
+            out["vit_b16"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
