@@ -472,9 +472,12 @@ def main():
     ms, launches, _ = timed(step_resident, args.steps)
     # roofline of the dominant kernel: CUDA events around every GEMM launch, which needs the launches to
     # come from the host - the same K steps once more with graph replay switched off (identical kernels)
+    # (and with the text tower on the main stream: overlapped kernels would stretch each other's events)
     os.environ["HBA_STEP_GRAPH"] = "0"
+    os.environ["HBA_TEXT_STREAM"] = "0"
     ms_eager, _, prof = timed(step_resident, args.steps, profile_gemm=True)
     os.environ.pop("HBA_STEP_GRAPH")
+    os.environ.pop("HBA_TEXT_STREAM")
     loss_val = float(step_resident())
     for _ in range(2):
         step_e2e()
@@ -523,8 +526,9 @@ def main():
                      "gemm_flops_per_step": flops / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,
                      "gemm_share_of_step": gemm_ms / ms_eager, "eager_ms_per_step": ms_eager / args.steps,
-                     "how": "CUDA events around every gemm_tc_kernel launch over K host-launched steps of the "
-                            "same workload, run right after the timed (graph-replayed) region",
+                     "how": "CUDA events around every gemm_tc_kernel launch over K host-launched, single-stream steps "
+                            "of the same workload, run right after the timed region (which replays the step as a "
+                            "CUDA graph with the text tower on a parallel branch)",
                      "by_shape": by_shape},
     }
     out["host_cpus"] = os.cpu_count()

@@ -7,6 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "vit-project_b200")]
 
+os.environ.setdefault("HBA_TEXT_STREAM", "0")  # serialised kernels: clean per-kernel durations under ncu
 import torch  # noqa: E402
 
 import bench  # noqa: E402

@@ -430,11 +430,13 @@ class Engine:
             a_all = self._buf("t.a_f32", (M, d))
             ops.attention_fwd(qkv, S, T, H, causal=True, out_f32=a_all)
             eot = (tokens.argmax(dim=-1) + torch.arange(S, device=tokens.device) * T).contiguous()
-            a_eot = torch.empty(S, d, device=self.device)
-            x_eot = torch.empty(S, d, device=self.device)
+            # (persistent buffers, not fresh tensors: they are produced on the side stream and read by
+            # the backward pass on the main stream - nothing here may be recycled by the caching allocator)
+            a_eot = self._buf("t.a_eot", (S, d))
+            x_eot = self._buf("t.x_eot", (S, d))
             ops.gather_rows(a_all, eot, d, a_eot)
             ops.gather_rows(x, eot, d, x_eot)
-            a_op = Operand.empty(max(S, 128), d, self.split, self.device, zero=True)
+            a_op = self._opbuf("t.a_op", max(S, 128), d, zero=True)
             ops.split_bf16(a_eot, a_op)
             self.launches += 6
             cache = {"key": key, "a_eot": a_eot, "x_eot": x_eot, "a_op": a_op}
@@ -462,6 +464,12 @@ class Engine:
         self.launches += 2
         return feat, {"S": S, "trainZ": trainZ, "keepZ": keepZ}
 
+    def _side_stream(self):
+        st = self.__dict__.get("_side")
+        if st is None or st.device != self.device:
+            st = self.__dict__["_side"] = torch.cuda.Stream(device=self.device)
+        return st
+
     def run_forward(self, images, tokens, pos_embedding, v_adapters, t_adapters, need_grad):
         """-> (pred [B, S] fp32 (fresh tensor), saved state for run_backward)."""
         self.ensure(images.device)
@@ -483,12 +491,27 @@ class Engine:
                 cache_ctx = self.trunk_cache.lookup_device_ids(self, ids)
             else:
                 cache_ctx = self.trunk_cache.lookup(self, ids)
+        # The two towers are independent until the cosine head: the text tower (small persistent kernels,
+        # 2.4 waves of tiles per GEMM at 66 x 77 rows) is enqueued on a side stream so that its kernels
+        # fill the SMs the vision tower's kernel tails leave idle, and vice versa.  Same kernels, same
+        # arguments: results are unchanged.  Fork / join are stream events, so the pair is captured into a
+        # CUDA graph as two parallel branches.  HBA_TEXT_STREAM=0 keeps everything on one stream.
+        side = None
+        if os.environ.get("HBA_TEXT_STREAM", "1") != "0":
+            main = torch.cuda.current_stream(self.device)
+            side = self._side_stream()
+            side.wait_stream(main)    # fork: the adapters' merged weights were produced on the main stream
+            with torch.cuda.stream(side):
+                txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
         if cache_ctx is not None and cache_ctx["hit"]:
             x, tw = cache_ctx["x"], self.vis
         else:
             x, tw = self.vision_trunk(images, max(L - 2, 0))
         img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad, cache_ctx)
-        txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
+        if side is None:
+            txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
+        else:
+            main.wait_stream(side)   # join: the cosine head needs both towers
         pred = torch.empty(B, txt_feat.shape[0], device=self.device)
         ops.cos_head_fwd(img_feat, txt_feat, self.logit_scale, pred)
         self.launches += 1
