@@ -477,7 +477,18 @@ def main():
     os.environ["HBA_TEXT_STREAM"] = "0"
     ms_eager, _, prof = timed(step_resident, args.steps, profile_gemm=True)
     os.environ.pop("HBA_STEP_GRAPH")
+    # the kernel's SHARE of the step: every libhba launch of a few host-launched steps bracketed by events the
+    # same way (numerator and denominator then carry the same launch-latency bias)
+    os.environ["HBA_STEP_GRAPH"] = "0"
+    with ops.EventProfile() as ep:
+        for _ in range(3):
+            step_resident()
+        torch.cuda.synchronize()
+    os.environ.pop("HBA_STEP_GRAPH")
     os.environ.pop("HBA_TEXT_STREAM")
+    per_entry = ep.totals_ms()
+    all_ms = sum(per_entry.values())
+    shares = {k: round(v / all_ms, 4) for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1])[:6]}
     loss_val = float(step_resident())
     for _ in range(2):
         step_e2e()
@@ -525,10 +536,12 @@ def main():
                      "peak_source": peak_src, "gemm_launches_per_step": len(prof) / args.steps,
                      "gemm_flops_per_step": flops / args.steps,
                      "gemm_ms_per_step": gemm_ms / args.steps,
-                     "gemm_share_of_step": gemm_ms / ms_eager, "eager_ms_per_step": ms_eager / args.steps,
+                     "gemm_share_of_step": per_entry.get("hba_gemm_bf16", 0.0) / all_ms,
+                     "kernel_time_shares": shares, "eager_ms_per_step": ms_eager / args.steps,
                      "how": "CUDA events around every gemm_tc_kernel launch over K host-launched, single-stream steps "
                             "of the same workload, run right after the timed region (which replays the step as a "
-                            "CUDA graph with the text tower on a parallel branch)",
+                            "CUDA graph with the text tower on a parallel branch); shares = event time per C-ABI entry "
+                            "point / event time of all libhba launches of 3 further host-launched steps",
                      "by_shape": by_shape},
     }
     out["host_cpus"] = os.cpu_count()

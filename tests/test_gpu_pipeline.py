@@ -261,11 +261,12 @@ def test_run_behavioral_training_drivers_end_to_end(tiny_checkpoint, tmp_path):
     assert r == results["plain"]                                 # resident + cached == plain, exactly
 
 
-def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, tmp_path, monkeypatch):
-    """HBA_STEP_GRAPH (CUDA graphs of the trunk-cached training step and of the cached eval / RSA
-    forward) against the same run launched kernel by kernel: a sweep condition resumed from baseline
-    epoch 1, 7 epochs with a 2-epoch random-target window - identical CSV rows, DoRA checkpoints and
-    optimizer step counts."""
+@pytest.mark.parametrize("perturb_type", ["random_target", "uniform_images"])
+def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, tmp_path, monkeypatch, perturb_type):
+    """HBA_STEP_GRAPH (CUDA graphs of the trunk-cached training step, of the full-trunk step used under
+    image perturbations, and of the cached eval / RSA forward) against the same run launched kernel by
+    kernel: a sweep condition resumed from baseline epoch 1, 7 epochs with a 2-epoch perturbation window -
+    identical CSV rows, DoRA checkpoints and optimizer step counts."""
     import hba
     import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
     import functions.new_cvpr_train_behavior_things_pipeline as NEW
@@ -288,7 +289,7 @@ def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, 
                    dora_parameters_path=f"{root}/{tag}/dora", random_state_path=f"{root}/{tag}/rand",
                    baseline_dora_directory=f"{root}/base/dora", baseline_random_state_path=f"{root}/base/rand",
                    baseline_split_indices_path=f"{root}/base/rand/dataset_split_indices.pth",
-                   perturb_type="random_target", perturb_length=2, perturb_distribution="target",
+                   perturb_type=perturb_type, perturb_length=2, perturb_distribution="target",
                    perturb_seed=42, training_run=4, resume_from_epoch=1,
                    previous_training_res_path=f"{root}/base/res.csv")
         NEW.run_behavioral_training(cfg)
@@ -298,7 +299,8 @@ def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, 
         results[tag] = (rows, dora, rand)
     g, e = results["graph"], results["eager"]
     assert len(g[0]) == 8 and g[0] == e[0]
-    assert [r[5] for r in g[0][2:]] == ["False", "False", "True", "True", "False", "False"]   # epochs 2..7
+    col = {"random_target": 5, "uniform_images": 7}[perturb_type]   # used_random_targets / used_uniform_images
+    assert [r[col] for r in g[0][2:]] == ["False", "False", "True", "True", "False", "False"]   # epochs 2..7
     assert g[1].keys() == e[1].keys()
     for k in g[1]:
         assert torch.equal(g[1][k], e[1][k]), k

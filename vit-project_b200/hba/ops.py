@@ -22,6 +22,57 @@ _KERNELS_PER_CALL = {"hba_dora_merge_bwd": 2, "hba_pearson_f64": 3, "hba_softmax
 GEMM_PROFILE = None
 
 
+class EventProfile:
+    """Context manager: every C-ABI launch made through this module is bracketed by CUDA events on the
+    launching stream; `.records` holds (entry point, start, end).  Used by bench.py for the kernel-time
+    shares of a step (a measurement aid - the events add host work, never use it in a timed region)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _lib
+        real, records = _lib, self.records
+
+        class _Lib:
+            def __getattr__(self, name):
+                fn = getattr(real.load(), name)
+                if not name.startswith("hba_") or name in ("hba_last_error", "hba_rank_workspace_bytes"):
+                    return fn
+
+                def bracketed(*args):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = fn(*args)
+                    e1.record()
+                    records.append((name, e0, e1))
+                    return rc
+                return bracketed
+
+        class _Shim:
+            def __getattr__(self, name):
+                return getattr(real, name)
+
+            @staticmethod
+            def load():
+                return _Lib()
+
+        self._real = real
+        _lib = _Shim()
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._real
+        return False
+
+    def totals_ms(self):
+        out = {}
+        for name, e0, e1 in self.records:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
 def check(rc, what, kernels=None):
     _check(rc, what)
     COUNTERS["calls"] += 1
