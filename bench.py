@@ -390,7 +390,17 @@ def main():
         import torch.distributed as dist
         # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION/WARN) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)             # (the banner is a plain printf at communicator creation)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     hba.set_precision(args.precision)
     if args.sweep_only:
         print(json.dumps(measure_sweep(args, device, world)))
