@@ -41,12 +41,15 @@ class _DoraMerge(torch.autograd.Function):
         ctx.save_for_backward(D, A, Bm, m)
         ctx.scale = scale
         ctx.mark_non_differentiable(w.buf, wt.buf)
+        ctx.set_materialize_grads(False)   # no zero tensors for the two bf16 operand outputs in backward
         return w_t, w.buf, wt.buf
 
     @staticmethod
     def backward(ctx, g_wt, _g1, _g2):
         D, A, Bm, m = ctx.saved_tensors
         in_f, out_f = D.shape
+        if g_wt is None:
+            return None, None, None, None, None
         G = g_wt.t()  # dL/dW in [out, in] layout
         if not G.is_contiguous():
             G = G.contiguous()

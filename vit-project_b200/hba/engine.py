@@ -541,14 +541,17 @@ class Engine:
         self.launches += 3
 
     def _dw(self, tag, dY, a_f32, R, d_out, d_in):
-        """dW[out, in] = sum_r dY[r, out] a[r, in] as a GEMM with K = rows (zero padded to 64)."""
-        kp = _roundup(R, 64)
-        # the buffers are keyed by R: their zero K-padding [R, kp) must never hold stale rows
-        A = self._grad_operand(f"{tag}.dyT{R}", dY, R, d_out, transpose=True, k_pad=kp)
-        Bo = self._grad_operand(f"{tag}.aT{R}", a_f32, R, d_in, transpose=True, k_pad=kp)
+        """dW[out, in] = sum_r dY[r, out] a[r, in]: both operands are read MN-major (as [K = rows, M / N]
+        matrices, no transposition pass; rows beyond R are zero-filled by TMA) and the K = R rows are split
+        into slices when the 16 output tiles of a 1024 x 1024 gradient would leave 58 of 74 CTA pairs idle."""
+        A = self._grad_operand(f"{tag}.dy{R}", dY, R, d_out)
+        Bo = self._grad_operand(f"{tag}.a{R}", a_f32, R, d_in)
         dW = torch.empty(d_out, d_in, device=self.device)
-        ops.gemm(A, Bo, d_out, out_f32=dW)
-        self.launches += 1
+        s = ops.auto_k_slices(d_out, d_in, R)
+        ws = self._buf("b.k_ws", (s * d_out * d_in,)) if s > 1 else None
+        ops.gemm(Operand(A.buf, R, d_out, A.lo_off), Operand(Bo.buf, R, d_in, Bo.lo_off), a_mn=True, b_mn=True,
+                 K=R, out_f32=dW, k_slices=s, k_workspace=ws)
+        self.launches += 2 if s > 1 else 1
         return dW
 
     def run_backward(self, saved, d_pred):
