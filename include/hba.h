@@ -209,6 +209,13 @@ int hba_adamw_multi(void* const* ptrs, const int64_t* sizes, int32_t n, int64_t 
 int hba_sgd_multi(void* const* ptrs, const int64_t* sizes, int32_t n, int64_t total, float lr,
                   float momentum, float weight_decay, int32_t first_step,
                   const int32_t* skip_flag, void* stream);
+/* Vectorised SGD of the fully trained ViT-B/16 with the bf16 GEMM operand of each weight refreshed in the
+ * same pass.  ptrs: device array of 4*n pointers (param, grad, momentum_buf, bf16 copy or NULL), all 16-byte
+ * aligned (the bf16 copy 8-byte), every tensor's element count a multiple of 4; prefix4: device array of n
+ * int64 = exclusive prefix of the element counts / 4; total4 = sum of the element counts / 4. */
+int hba_sgd_staged(void* const* ptrs, const int64_t* prefix4, int32_t n, int64_t total4, float lr,
+                   float momentum, float weight_decay, int32_t first_step,
+                   const int32_t* skip_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RSA evaluation (behavioral_RSA tail, NEW:625-652; ViT variant MEAS:298-355):

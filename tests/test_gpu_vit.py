@@ -339,9 +339,12 @@ def test_vit_trainer_steps_match_oracle_sgd():
         hba.set_precision("bf16")
 
 
-def test_vit_trainer_cuda_graph_replay_is_bit_identical_to_eager_steps():
+@pytest.mark.parametrize("num_classes", [10, 12])
+def test_vit_trainer_cuda_graph_replay_is_bit_identical_to_eager_steps(num_classes):
     """The captured step (one graph per batch shape and learning rate) replays exactly the eager step's
-    kernels: 5 steps incl. a learning-rate change give bit-identical losses and parameters."""
+    kernels: 5 steps incl. a learning-rate change give bit-identical losses and parameters.  12 classes:
+    every tensor size is a multiple of 4, i.e. the vectorised SGD that also refreshes the bf16 operands
+    (no staging pass in the graph); 10 classes: the generic SGD + per-step staging."""
     hba, ops = _imports()
     from hba import vit
     g = torch.Generator().manual_seed(11)
@@ -350,7 +353,7 @@ def test_vit_trainer_cuda_graph_replay_is_bit_identical_to_eager_steps():
     results = []
     for use_graph in (False, True):
         torch.manual_seed(3)
-        model = vit.create_model("vit_tiny_test", num_classes=10).to(DEV)
+        model = vit.create_model("vit_tiny_test", num_classes=num_classes).to(DEV)
         tr = vit.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4, use_graph=use_graph)
         losses = []
         for i, (images, labels) in enumerate(batches):
@@ -358,6 +361,32 @@ def test_vit_trainer_cuda_graph_replay_is_bit_identical_to_eager_steps():
                 tr.param_groups[0]["lr"] = 0.05
             loss, hits = tr.step(images, labels)
             losses.append(float(loss))
+        results.append((losses, [p.detach().clone() for p in model.parameters()]))
+    assert results[0][0] == results[1][0]
+    for a, b in zip(results[0][1], results[1][1]):
+        assert torch.equal(a, b)
+
+
+def test_operand_refreshing_sgd_equals_sgd_plus_staging(monkeypatch):
+    """hba_sgd_staged (vectorised, bf16 operands refreshed in the same pass) against hba_sgd_multi followed by
+    the per-step staging pass: bit-identical losses and parameters over 4 steps."""
+    hba, ops = _imports()
+    from hba import vit
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(4, 3, 224, 224, generator=g).to(DEV), torch.randint(0, 12, (4,), generator=g).to(DEV))
+               for _ in range(4)]
+    results = []
+    for fused in (True, False):
+        torch.manual_seed(3)
+        model = vit.create_model("vit_tiny_test", num_classes=12).to(DEV)
+        tr = vit.DataParallelTrainer(model, lr=0.1, momentum=0.9, weight_decay=1e-4)
+        losses = []
+        for images, labels in batches:
+            loss, _ = tr.step(images, labels)
+            losses.append(float(loss))
+            if not fused:   # drop to the generic kernel from the second step on
+                tr._staged = None
+        assert (tr._staged is not None) == fused
         results.append((losses, [p.detach().clone() for p in model.parameters()]))
     assert results[0][0] == results[1][0]
     for a, b in zip(results[0][1], results[1][1]):

@@ -60,6 +60,7 @@ SIGNATURES = {
     "hba_cos_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "hba_adamw_multi": (i32, [vp, vp, i32, i64, f32, f32, f32, f32, f32, i64, vp, vp, vp]),
     "hba_sgd_multi": (i32, [vp, vp, i32, i64, f32, f32, f32, i32, vp, vp]),
+    "hba_sgd_staged": (i32, [vp, vp, i32, i64, f32, f32, f32, i32, vp, vp]),
     "hba_rdm_f64": (i32, [vp, i32, i32, vp, vp, vp]),
     "hba_rank_workspace_bytes": (i64, [i64]),
     "hba_rank_avg_f64": (i32, [vp, i64, vp, vp, i64, vp]),

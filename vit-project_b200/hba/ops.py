@@ -310,6 +310,11 @@ def sgd_multi(ptr_table, sizes, n, total, lr, momentum, weight_decay, first_step
                                     1 if first_step else 0, _p(skip_flag), _stream()), "hba_sgd_multi")
 
 
+def sgd_staged(ptr_table, prefix4, n, total4, lr, momentum, weight_decay, first_step, skip_flag=None):
+    check(_lib.load().hba_sgd_staged(_p(ptr_table), _p(prefix4), n, total4, lr, momentum, weight_decay,
+                                     1 if first_step else 0, _p(skip_flag), _stream()), "hba_sgd_staged")
+
+
 def rdm_f64(E, rdm=None, tri=None):
     N, Dm = E.shape
     assert E.dtype == torch.float32 and E.is_contiguous()

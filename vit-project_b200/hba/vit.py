@@ -167,27 +167,49 @@ class ViTEngine:
             self.device, self.precision = device, prec
             self._bufs.clear()
             self._wops.clear()
+            self._wops_gen = self.__dict__.get("_wops_gen", 0) + 1   # optimiser tables pointing into them are stale
             self._grads_for = None
+
+    def _weight_matrices(self):
+        m = self.m
+        mats = {"conv": m.patch_embed.proj.weight, "head": m.head.weight}
+        for i, blk in enumerate(m.blocks):
+            mats[f"{i}.qkv"], mats[f"{i}.proj"] = blk.attn.qkv.weight, blk.attn.proj.weight
+            mats[f"{i}.fc1"], mats[f"{i}.fc2"] = blk.mlp.fc1.weight, blk.mlp.fc2.weight
+        return mats
+
+    def _weights_key(self):
+        return (self.precision, str(self.device), tuple(p._version for p in self._weight_matrices().values()))
 
     def stage_weights(self):
         """bf16 (hi[/lo]) operands of every weight matrix, refreshed from the fp32 masters."""
-        m = self.m
-        mats = {"conv": m.patch_embed.proj.weight.detach().reshape(m.embed_dim, -1), "head": m.head.weight.detach()}
-        for i, blk in enumerate(m.blocks):
-            mats[f"{i}.qkv"], mats[f"{i}.proj"] = blk.attn.qkv.weight.detach(), blk.attn.proj.weight.detach()
-            mats[f"{i}.fc1"], mats[f"{i}.fc2"] = blk.mlp.fc1.weight.detach(), blk.mlp.fc2.weight.detach()
-        for k, w in mats.items():
+        for k, p in self._weight_matrices().items():
+            w = p.detach()
+            w = w.reshape(w.shape[0], -1)
             op = self._wops.get(k)
             if op is None:
                 op = Operand.empty(w.shape[0], w.shape[1], self.split, self.device)
                 self._wops[k] = op
             ops.split_bf16(w if w.is_contiguous() else w.contiguous(), op)
+        self._staged_key = self._weights_key()
+
+    def staged_operand_of(self):
+        """id(parameter) -> its bf16 operand (bf16 mode: a plain [out, in] bf16 matrix the optimiser may keep
+        in step with the fp32 master, see DataParallelTrainer._sgd)."""
+        return {id(p): self._wops[k] for k, p in self._weight_matrices().items() if k in self._wops}
+
+    def weights_in_sync(self):
+        """True when whoever updated the parameters last also refreshed the bf16 operands (fused SGD) and
+        nothing has touched the masters through torch since (their version counters are unchanged)."""
+        return bool(self.__dict__.get("_operands_vouched")) and self.__dict__.get("_staged_key") == self._weights_key()
 
     # ------------------------------------------------------------------ forward
     def forward(self, images, save=True):
         m = self.m
         self._setup(images.device)
-        self.stage_weights()
+        if not self.weights_in_sync():
+            self.stage_weights()
+        self._operands_vouched = False   # any other optimiser updates the masters through raw pointers
         B, P, d, H = images.shape[0], m.patch_size, m.embed_dim, m.blocks[0].attn.num_heads
         grid = images.shape[2] // P
         if images.shape[2] != m.img_size or images.shape[3] != m.img_size:
@@ -487,6 +509,13 @@ class DataParallelTrainer:
         s_img, s_lab = self._static
         s_img.copy_(images, non_blocking=True)
         s_lab.copy_(labels, non_blocking=True)
+        fused_staging = self.__dict__.get("_staged") is not None and self._staged[4]
+        if fused_staging and not self.eng.weights_in_sync():
+            # (with the operand-refreshing SGD the captured step holds no staging pass: parameters loaded /
+            # edited through torch since the last step are re-staged here, outside the graph; without it
+            # the staging pass stays inside every captured step)
+            self.eng.stage_weights()
+            self.eng._operands_vouched = True
         entry = self._graphs.get(key)
         if entry is None:
             graph = torch.cuda.CUDAGraph()
@@ -520,7 +549,11 @@ class DataParallelTrainer:
 
     def _sgd(self):
         eng = self.eng
+        if self._mom is not None and self.__dict__.get("_tables_gen") != eng.__dict__.get("_wops_gen", 0):
+            raise RuntimeError("hba.vit: precision mode / device changed under a live DataParallelTrainer; "
+                               "create a new trainer")
         if self._mom is None:
+            self._tables_gen = eng.__dict__.get("_wops_gen", 0)
             self._mom = torch.zeros_like(eng.flat_grad)
             ps = eng.param_list()
             for p in ps:
@@ -537,7 +570,28 @@ class DataParallelTrainer:
             self._table = (torch.tensor(flat, dtype=torch.int64, device=eng.device),
                            torch.tensor([p.numel() for p in ps], dtype=torch.int64, device=eng.device),
                            len(ps), sum(p.numel() for p in ps))
-        table, sizes, n, total = self._table
-        ops.sgd_multi(table, sizes, n, total, float(self.param_groups[0]["lr"]), self.momentum, self.wd,
-                      self._first)
+            # vectorised variant that also refreshes the bf16 GEMM operands (bf16 mode, all sizes % 4 == 0)
+            self._staged = None
+            if not eng.split and all(p.numel() % 4 == 0 and p.data_ptr() % 16 == 0 for p in ps):
+                wop = eng.staged_operand_of()
+                flat4, prefix, acc = [], [], 0
+                for p in ps:
+                    g = eng.grad_of[id(p)]
+                    op = wop.get(id(p))
+                    ok16 = op is not None and op.lo_off == 0 and op.buf.is_contiguous() and op.buf.numel() == p.numel()
+                    flat4 += [p.data_ptr(), g.data_ptr(), base_m + (g.data_ptr() - base_g),
+                              op.buf.data_ptr() if ok16 else 0]
+                    prefix.append(acc)
+                    acc += p.numel() // 4
+                self._staged = (torch.tensor(flat4, dtype=torch.int64, device=eng.device),
+                                torch.tensor(prefix, dtype=torch.int64, device=eng.device), len(ps), acc,
+                                all(wop.get(id(p)) is not None for p in eng._weight_matrices().values()))
+        lr = float(self.param_groups[0]["lr"])
+        if self._staged is not None:
+            table4, prefix4, n, total4, all_staged = self._staged
+            ops.sgd_staged(table4, prefix4, n, total4, lr, self.momentum, self.wd, self._first)
+            eng._operands_vouched = all_staged   # the operands were refreshed together with the masters
+        else:
+            table, sizes, n, total = self._table
+            ops.sgd_multi(table, sizes, n, total, lr, self.momentum, self.wd, self._first)
         self._first = False
