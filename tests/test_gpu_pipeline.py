@@ -183,6 +183,42 @@ def test_trunk_cache_is_bit_identical(tiny_checkpoint):
     hba.set_precision("bf16")
 
 
+@pytest.mark.parametrize("B", [1, 3, 5])
+def test_trunk_cache_hit_is_independent_of_the_batch_that_filled_it(tiny_checkpoint, B):
+    """A sweep worker fills the cache once and serves later conditions (other batch compositions, a last
+    batch of one image) from it: a hit on B images cached as part of an 8-image batch equals recomputation
+    bit for bit - predictions and DoRA gradients."""
+    import hba
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    from hba.engine import TrunkCache
+    from oracle.synth import synthetic_problem
+    hba.set_precision("bf16")
+    prob = synthetic_problem()
+    xall = prob["train_images"][:8].to(DEV)
+    y = torch.randn(8, 6, generator=torch.Generator().manual_seed(3)).to(DEV)
+    model = build_model(NEW).to(DEV)
+    eng = model.clip_model.hba_engine()
+    crit = torch.nn.MSELoss()
+
+    def run(x, t, ids):
+        for p in model.parameters():
+            p.grad = None
+        eng.batch_ids = ids
+        pred = model(x)
+        crit(pred, t).backward()
+        return pred.detach().clone(), [p.grad.clone() for p in model.parameters() if p.requires_grad]
+
+    eng.trunk_cache = None
+    base = run(xall[:B], y[:B], None)
+    eng.trunk_cache = TrunkCache(16)
+    run(xall, y, list(range(8)))                 # fill: all 8 images in one batch
+    hit = run(xall[:B], y[:B], list(range(B)))
+    assert torch.equal(base[0], hit[0])
+    for a, b in zip(base[1], hit[1]):
+        assert torch.equal(a, b)
+    eng.trunk_cache = None
+
+
 def _write_things_like_dataset(root, n_train=12, n_rsa=8, seed=0):
     """A THINGS-shaped dataset on disk: PNG images, the SPoSE csv layout (index, image name, 66 target
     columns; NEW:191-202), the 48-image-style inference csv and RDM48_triplet.mat."""

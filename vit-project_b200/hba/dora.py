@@ -71,11 +71,17 @@ class DoRALayer(nn.Module):
         self.dora_alpha = dora_alpha
         self.dora_dropout = nn.Dropout(p=dora_dropout)
         with torch.no_grad():
-            Wt = original_layer.weight.data.clone().T      # [in, out]
+            # The reference builds its adapters while the model is still on the CPU (NEW:1133-1152, .to(device)
+            # comes at NEW:1178), so S and D are CPU fp32 results.  A sweep worker re-adapts a frozen CLIP
+            # that already lives on the GPU: computing the decomposition there would change S / D in the
+            # last bit from condition to condition (tests/test_gpu_sweep.py found exactly that), so it is
+            # always done on the CPU and moved to wherever the wrapped layer lives.
+            dev = original_layer.weight.device
+            Wt = original_layer.weight.data.detach().to("cpu", torch.float32).clone().T      # [in, out]
             S = torch.norm(Wt, dim=0)                      # column magnitudes [out]
             D = Wt / S                                     # unit-norm columns
-        self.m = nn.Parameter(S)
-        self.register_buffer("D", D.contiguous())
+        self.m = nn.Parameter(S.to(dev))
+        self.register_buffer("D", D.contiguous().to(dev))
         self.delta_D_A = nn.Parameter(torch.zeros(self.r, original_layer.out_features))
         self.delta_D_B = nn.Parameter(torch.zeros(original_layer.in_features, self.r))
         self.scaling = self.dora_alpha / self.r
