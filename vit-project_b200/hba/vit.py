@@ -107,6 +107,17 @@ class VisionTransformer(nn.Module):
             return eng.forward(x, save=False).clone()
 
 
+    global_pool = "token"   # timm's default for vit_base_patch16_224: compute_rsa_score takes features[:, 0] (MEAS:315-322)
+
+    def forward_features(self, x):
+        """[B,3,H,W] -> final-LayerNorm token features [B, T, embed_dim] fp32 (timm's forward_features as
+        used by compute_rsa_score, MEAS:308-322); inference only."""
+        if not x.is_cuda:
+            raise RuntimeError("hba.vit has no CPU path: move the model and the images to a CUDA device")
+        with torch.no_grad():
+            return get_engine(self).forward(x, save=False, features=True).clone()
+
+
 def create_model(name="vit_base_patch16_224", pretrained=False, num_classes=1000, **kw):
     """timm.create_model stand-in for the one architecture the reference trains (VIT:283)."""
     if pretrained:
@@ -204,7 +215,7 @@ class ViTEngine:
         return bool(self.__dict__.get("_operands_vouched")) and self.__dict__.get("_staged_key") == self._weights_key()
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images, save=True):
+    def forward(self, images, save=True, features=False):
         m = self.m
         self._setup(images.device)
         if not self.weights_in_sync():
@@ -253,6 +264,10 @@ class ViTEngine:
             x_out = self._buf(tag + "xout", (M, d))
             ops.gemm(hid, self._wops[f"{i}.fc2"], M, bias=blk.mlp.fc2.bias.detach(), residual=x_mid, out_f32=x_out)
             x = x_out
+        if features:   # every token through the final LayerNorm, fp32 (forward_features)
+            feat = self._buf("features", (M, d))
+            ops.layernorm_fwd(x, M, d, m.norm.weight.detach(), m.norm.bias.detach(), LN_EPS, y_f32=feat)
+            return feat.view(B, T, d)
         cls_n = self._opbuf("clsn", max(B, 128), d, zero=True)
         ops.layernorm_fwd(x, B, d, m.norm.weight.detach(), m.norm.bias.detach(), LN_EPS, row_step=T, y=cls_n)
         logits = self._buf("logits", (B, (m.num_classes + 3) // 4 * 4))[:, :m.num_classes]  # 16-byte rows
@@ -491,6 +506,8 @@ class DataParallelTrainer:
         self.param_groups = [{"lr": lr}]  # so that CosineAnnealingLRWithWarmup can drive it
         self._mom = None
         self._first = True
+        self._mom_valid = False     # False: the next SGD step initialises the momentum buffers (buf = grad)
+        self._pending_mom = None    # momentum buffers of a loaded checkpoint, until the flat buffer exists
         self._table = None
 
     def broadcast_parameters(self):
@@ -531,6 +548,75 @@ class DataParallelTrainer:
         entry[0].replay()
         ops.COUNTERS["launches"] += entry[2]
         return entry[1]
+
+    # ------------------------------------------------------------------ evaluation (VIT:167-204)
+    def evaluate(self, images, labels):
+        """No-grad forward + fused softmax-CE of one validation batch: (mean CE loss, top-1 hits) as
+        device tensors (`outputs.max(1)` / `cross_entropy` of VIT:178-187).  The returned tensors are
+        workspaces: accumulate them before the next call."""
+        eng = self.eng
+        with torch.no_grad():
+            logits = eng.forward(images, save=False)
+            B = logits.shape[0]
+            loss = eng._buf("val_loss", (1,))
+            hits = eng._buf("val_hits", (1,), torch.int32)
+            ops.softmax_ce(logits, labels, loss, eng.d_logits_buffer(B), hits, eng._buf("ce_ws", (2 * B,)))
+        return loss, hits
+
+    # ------------------------------------------------------------------ optimizer state (VIT:98-100, 321)
+    def momentum_of(self, p):
+        """View of a parameter's momentum buffer inside the flat momentum buffer (which mirrors the
+        flat gradient layout)."""
+        eng = self.eng
+        g = eng.grad_of[id(p)]
+        off = (g.data_ptr() - eng.flat_grad.data_ptr()) // 4
+        return self._mom[off:off + p.numel()].view_as(p)
+
+    def state_dict(self):
+        """`torch.optim.SGD.state_dict()` layout, parameters indexed in `model.parameters()` order (the
+        order of timm's vit_base_patch16_224), so that 'optimizer_state_dict' of a checkpoint written here
+        loads into the reference's optimizer and vice versa (VIT:98-100, 321; MEAS:507)."""
+        ps = list(self.model.parameters())
+        if self._pending_mom is not None:
+            state = {i: {"momentum_buffer": b.clone()} for i, b in self._pending_mom.items()}
+        elif self._mom is not None and self._mom_valid:
+            state = {i: {"momentum_buffer": self.momentum_of(p).clone()} for i, p in enumerate(ps)}
+        else:
+            state = {}
+        group = {"lr": float(self.param_groups[0]["lr"]), "momentum": self.momentum, "dampening": 0,
+                 "weight_decay": self.wd, "nesterov": False, "maximize": False, "foreach": None,
+                 "differentiable": False, "fused": None, "params": list(range(len(ps)))}
+        if "initial_lr" in self.param_groups[0]:
+            group["initial_lr"] = self.param_groups[0]["initial_lr"]
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        if group.get("nesterov") or group.get("dampening", 0) != 0 or group.get("maximize"):
+            raise NotImplementedError("hba.vit: plain SGD with momentum only (VIT:294-299)")
+        ps = list(self.model.parameters())
+        if len(group["params"]) != len(ps):
+            raise ValueError(f"optimizer state covers {len(group['params'])} parameters, the model has {len(ps)}")
+        self.param_groups[0]["lr"] = float(group["lr"])
+        self.momentum, self.wd = float(group["momentum"]), float(group["weight_decay"])
+        state = sd.get("state", {})
+        bufs = {i: state[k]["momentum_buffer"] for i, k in enumerate(group["params"])
+                if k in state and state[k].get("momentum_buffer") is not None}
+        if bufs and len(bufs) != len(ps):
+            raise ValueError("optimizer state holds momentum buffers for some parameters only")
+        for i, b in bufs.items():
+            if tuple(b.shape) != tuple(ps[i].shape):
+                raise ValueError(f"momentum buffer {i} has shape {tuple(b.shape)}, parameter {tuple(ps[i].shape)}")
+        self._graphs.clear()        # captured steps hold the old learning rate / first-step flag
+        self._first = True          # next step host-launched
+        if not bufs:
+            self._pending_mom, self._mom_valid = None, False
+        elif self._mom is not None:
+            for i, p in enumerate(ps):
+                self.momentum_of(p).copy_(bufs[i])
+            self._pending_mom, self._mom_valid = None, True
+        else:
+            self._pending_mom, self._mom_valid = {i: b.detach().float() for i, b in bufs.items()}, False
 
     def _step_eager(self, images, labels):
         eng, m = self.eng, self.model
@@ -586,12 +672,18 @@ class DataParallelTrainer:
                 self._staged = (torch.tensor(flat4, dtype=torch.int64, device=eng.device),
                                 torch.tensor(prefix, dtype=torch.int64, device=eng.device), len(ps), acc,
                                 all(wop.get(id(p)) is not None for p in eng._weight_matrices().values()))
+        if self._pending_mom is not None:   # momentum buffers of a checkpoint loaded before the first step
+            for i, p in enumerate(self.model.parameters()):
+                self.momentum_of(p).copy_(self._pending_mom[i])
+            self._pending_mom, self._mom_valid = None, True
         lr = float(self.param_groups[0]["lr"])
+        init_mom = not self._mom_valid
         if self._staged is not None:
             table4, prefix4, n, total4, all_staged = self._staged
-            ops.sgd_staged(table4, prefix4, n, total4, lr, self.momentum, self.wd, self._first)
+            ops.sgd_staged(table4, prefix4, n, total4, lr, self.momentum, self.wd, init_mom)
             eng._operands_vouched = all_staged   # the operands were refreshed together with the masters
         else:
             table, sizes, n, total = self._table
-            ops.sgd_multi(table, sizes, n, total, lr, self.momentum, self.wd, self._first)
+            ops.sgd_multi(table, sizes, n, total, lr, self.momentum, self.wd, init_mom)
         self._first = False
+        self._mom_valid = True
