@@ -415,3 +415,65 @@ def test_collective_tails_on_gloo_world_2(tmp_path):
     assert r0["rsa_quirk"][0] == pytest.approx(ref.compute_rsa_score_ref(model, things, rdm, 2, dataset_order=False)[0], abs=1e-12)
     assert abs(r0["rsa_quirk"][0] - one_rank[0]) > 1e-6                        # the interleave does change rho
     assert r1["rsa_fixed"] == (None, None) and r1["rsa_quirk"] == (None, None)  # MEAS:335-336
+
+
+# ------------------------------------------------------------------------------- optimizer state (host logic)
+def test_trainer_optimizer_state_layout_on_host(monkeypatch):
+    """DataParallelTrainer.state_dict / load_state_dict / momentum_of: the bookkeeping between the flat
+    momentum buffer (bucket order) and torch.optim.SGD's per-parameter state (model.parameters() order),
+    with the SGD kernels stubbed out (their numerics are GPU-tested)."""
+    from hba import ops, vit
+    torch.manual_seed(0)
+    model = vit.create_model("vit_tiny_test", num_classes=10)
+    ps = list(model.parameters())
+    # torch's own optimizer gives the layout to match
+    opt = torch.optim.SGD(ps, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    for p in ps:
+        p.grad = torch.full_like(p, 0.5)
+    opt.step()
+    want = opt.state_dict()
+
+    calls = []
+    monkeypatch.setattr(ops, "sgd_multi", lambda *a, **k: calls.append(("multi", a[-1])))
+    monkeypatch.setattr(ops, "sgd_staged", lambda *a, **k: calls.append(("staged", a[-1])))
+    tr = vit.DataParallelTrainer(model, lr=0.3, momentum=0.5, weight_decay=0.0)
+    assert tr.state_dict()["state"] == {} and sorted(tr.state_dict()["param_groups"][0]) == sorted(want["param_groups"][0])
+    eng = tr.eng
+    eng.device, eng.precision = torch.device("cpu"), "fp32"       # host stand-in for ViTEngine._setup
+    eng._ensure_grads()
+    # checkpoint loaded before the first step: kept pending, handed back unchanged, applied by the first SGD call
+    tr.load_state_dict(want)
+    assert (tr.param_groups[0]["lr"], tr.momentum, tr.wd) == (0.1, 0.9, 1e-4) and tr._first
+    back = tr.state_dict()
+    assert all(torch.equal(back["state"][i]["momentum_buffer"], want["state"][i]["momentum_buffer"]) for i in want["state"])
+    tr._sgd()
+    assert calls == [("multi", False)]                             # momentum buffers are NOT re-initialised
+    assert tr._pending_mom is None and tr._mom_valid and not tr._first
+    for i, p in enumerate(ps):
+        view = tr.momentum_of(p)
+        assert view.shape == p.shape and torch.equal(view, want["state"][i]["momentum_buffer"])
+        g = eng.grad_of[id(p)]
+        assert view.data_ptr() - tr._mom.data_ptr() == g.data_ptr() - eng.flat_grad.data_ptr()
+    got = tr.state_dict()
+    assert sorted(got["state"]) == sorted(want["state"]) and got["param_groups"][0]["params"] == want["param_groups"][0]["params"]
+    # loading into a trainer whose flat buffer exists writes through immediately and forces a host-launched step
+    doubled = {"state": {i: {"momentum_buffer": v["momentum_buffer"] * 2} for i, v in want["state"].items()},
+               "param_groups": [dict(want["param_groups"][0], lr=0.02)]}
+    tr._graphs["stale"] = object()
+    tr.load_state_dict(doubled)
+    assert tr._graphs == {} and tr._first and tr._mom_valid and tr.param_groups[0]["lr"] == 0.02
+    assert torch.equal(tr.momentum_of(ps[3]), want["state"][3]["momentum_buffer"] * 2)
+    # a state without momentum buffers (fresh optimizer): the next step initialises them
+    tr.load_state_dict({"state": {}, "param_groups": want["param_groups"]})
+    tr._sgd()
+    assert calls[-1] == ("multi", True) and tr.state_dict()["state"] != {}
+    fresh = vit.DataParallelTrainer(vit.create_model("vit_tiny_test", num_classes=10))
+    fresh.eng.device, fresh.eng.precision = torch.device("cpu"), "fp32"
+    fresh.eng._ensure_grads()
+    fresh._sgd()
+    assert calls[-1] == ("multi", True)                            # first step of a new run: buf = grad
+    with pytest.raises(ValueError):
+        tr.load_state_dict({"state": {0: want["state"][0]}, "param_groups": want["param_groups"]})
+    with pytest.raises(ValueError):
+        bad = {i: {"momentum_buffer": torch.zeros(3)} for i in want["state"]}
+        tr.load_state_dict({"state": bad, "param_groups": want["param_groups"]})

@@ -397,7 +397,7 @@ def compute_rsa_score(model, things_loader, rdm, local_rank=0, world_size=1, dat
     if evaluator is None:
         from .rsa import RSAEvaluator
         evaluator = RSAEvaluator(reference, emb.device)
-    rho, p_value, _ = evaluator(emb, want_rdm=False)
+    rho, p_value, _ = evaluator(emb)
     return rho, p_value
 
 
