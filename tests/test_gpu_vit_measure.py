@@ -133,7 +133,8 @@ def test_optimizer_state_round_trip_and_exchange_with_torch_sgd():
         lo = F.cross_entropy(ref(batches[2][0]), batches[2][1])
         lo.backward()
         opt.step()
-        assert abs(float(lc) - float(lo)) < 1e-3 * abs(float(lo))
+        lo = float(lo.detach())
+        assert abs(float(lc) - lo) < 1e-3 * abs(lo)
         for (n, a), (_, b) in zip(prod_c.named_parameters(), ref.named_parameters()):
             assert rel_err(a.detach(), b.detach()) < 2e-3, (n, rel_err(a.detach(), b.detach()))
         # (iii) the product's state into a torch optimizer (the reference side loading our checkpoint)
