@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(kDoraThreads)
 // The CTA stages 32 rank rows of A (all out_f columns, <= 2048) in shared memory once; a warp owns
 // one row i, its lanes split the columns (coalesced reads of dV, 32 loads in flight), every lane keeps
 // 32 partial sums (one per rank index) and the warp reduces them with shuffles at the end.
-constexpr int kDbMaxCols = 1024;
 __global__ void __launch_bounds__(256)
     dora_merge_bwd_rows_kernel(const float* __restrict__ dV, const float* __restrict__ A, int in_f,
                                int out_f, int r, float scale, float* __restrict__ dB) {
