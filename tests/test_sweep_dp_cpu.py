@@ -134,3 +134,139 @@ def test_reference_arm_under_torchrun_two_ranks(tmp_path):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["unit"] == "images/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ------------------------------------------------------------------------------- LEN's resume chain
+def test_find_previous_run_dir_and_last_completed_epoch(tmp_path):
+    """LEN:139-160 and LEN:188-221 (the reference keeps both inside `main()`; restated in hba.sweep)."""
+    from hba import sweep
+    base = str(tmp_path)
+    for name in ("random_target_e1_l2", "random_target_e1_l10", "random_target_e1_l30", "random_target_e10_l5",
+                 "label_shuffle_e1_l5", "random_target_e1_lx", "random_target_e11_l2"):
+        os.makedirs(os.path.join(base, name))
+    open(os.path.join(base, "random_target_e1_l20"), "w").close()          # a file, not a run directory
+    find = sweep.find_previous_run_dir
+    assert find(base, "random_target", 1, 20) == (os.path.join(base, "random_target_e1_l10"), 10)
+    assert find(base, "random_target", 1, 50) == (os.path.join(base, "random_target_e1_l30"), 30)
+    assert find(base, "random_target", 1, 2) == (None, None)                 # nothing shorter
+    assert find(base, "random_target", 10, 50) == (os.path.join(base, "random_target_e10_l5"), 5)   # e1_ != e10_
+    assert find(base, "label_shuffle", 1, 50) == (os.path.join(base, "label_shuffle_e1_l5"), 5)    # prefix must match
+    assert find(base, "random_target", 2, 50) == (None, None)
+    assert find(os.path.join(base, "missing"), "random_target", 1, 50) == (None, None)
+    csv = os.path.join(base, "training_res.csv")
+    assert sweep.last_completed_epoch(csv) == -1
+    with open(csv, "w") as f:
+        f.write("epoch,train_loss,test_loss,behavioral_rsa_rho,behavioral_rsa_p_value\n1,2.0,2.1,0.3,0.0\n"
+                "2,1.9,2.0,0.31,0.0\n\nnot-a-number,1,1,1,1\n7,1.5,1.6,0.4,0.0\n")
+    assert sweep.last_completed_epoch(csv) == 6                              # 1-indexed in the file
+
+
+def test_apply_length_resume_branches(tmp_path):
+    from hba import sweep
+    base = {"output_base_directory": str(tmp_path), "perturb_type": "random_target"}
+    logs = []
+    # (3) nothing there: baseline epoch e-1
+    cfg = sweep.condition_config(base, {"training_run": 8, "perturb_length": 5}, "length")
+    assert sweep.apply_length_resume(cfg, logs.append) == "baseline" and cfg["resume_from_epoch"] == 7
+    assert "resume_dora_parameters_path" not in cfg
+    # a shorter neighbour directory WITHOUT the needed checkpoint (failed / still running): still baseline
+    cfg10 = sweep.condition_config(base, {"training_run": 8, "perturb_length": 10}, "length")
+    assert sweep.apply_length_resume(cfg10, logs.append) == "baseline" and cfg10["resume_from_epoch"] == 7
+    assert "has no checkpoint of epoch 12" in logs[-1] and "shorter" in logs[-1]
+    # (2) the shorter run finished its window: resume from its end, last_epoch = (e-1) + prev_length  (LEN:239-244)
+    prev = os.path.join(str(tmp_path), "random_target_e8_l5")
+    os.makedirs(os.path.join(prev, "dora_params_8"))
+    open(os.path.join(prev, "dora_params_8", "epoch12_dora_params.pth"), "w").close()
+    cfg10 = sweep.condition_config(base, {"training_run": 8, "perturb_length": 10}, "length")
+    assert sweep.apply_length_resume(cfg10, logs.append) == "chain"
+    assert cfg10["resume_from_epoch"] == 12 and cfg10["perturb_length"] == 10 and cfg10["training_run"] == 8
+    assert cfg10["previous_training_res_path"] == os.path.join(prev, "training_res.csv")
+    assert cfg10["resume_random_state_path"] == os.path.join(prev, "random_states_8")
+    assert cfg10["resume_dora_parameters_path"] == os.path.join(prev, "dora_params_8")
+    assert "resuming from epoch 13" in logs[-1]
+    # (1) the run's own CSV exists: continue it from its own checkpoints  (LEN:229-236)
+    with open(cfg10["training_res_path"], "w") as f:
+        f.write("epoch,train_loss\n13,1.0\n14,0.9\n")
+    cfg10 = sweep.condition_config(base, {"training_run": 8, "perturb_length": 10}, "length")
+    assert sweep.apply_length_resume(cfg10) == "existing" and cfg10["resume_from_epoch"] == 14
+    assert cfg10["previous_training_res_path"] == cfg10["training_res_path"]
+    assert cfg10["resume_dora_parameters_path"] == cfg10["dora_parameters_path"]
+    assert cfg10["resume_random_state_path"] == cfg10["random_state_path"]
+    # first epoch: max(0, e-1)
+    cfg = sweep.condition_config(base, {"training_run": 0, "perturb_length": 2}, "length")
+    assert cfg["resume_from_epoch"] == 0
+
+
+def test_chain_groups_and_costs():
+    from hba import sweep
+    grid = sweep.length_grid_conditions()
+    groups = sweep.chain_groups(grid)
+    assert len(groups) == 21 and sum(len(g) for g in groups) == 136
+    for g in groups:
+        assert len({c["training_run"] for c in g}) == 1
+        lengths = [c["perturb_length"] for c in g]
+        assert lengths == sorted(lengths)
+    g1 = next(g for g in groups if g[0]["training_run"] == 1)
+    indep = sum(sweep.expected_epochs(c) for c in g1)
+    assert sweep.chain_cost(g1) == indep - (2 + 5 + 10 + 20 + 30 + 40)      # every window but the last is skipped once
+    total_chain = sum(sweep.chain_cost(g) for g in groups)
+    total_indep = sum(sweep.expected_epochs(c) for c in grid)
+    assert total_chain < 0.86 * total_indep
+    plan, loads = sweep.lpt_assign(groups, 8, cost=sweep.chain_cost)
+    assert sum(len(p) for p in plan) == 21 and max(loads) < 1.1 * sum(loads) / 8
+
+
+def _fake_length_condition(cfg):
+    """Stand-in for run_behavioral_training on the 'length' layout: writes what a finished run leaves behind
+    (result CSV rows and per-epoch DoRA checkpoints from the resume epoch to the end of the window + 2) and
+    records how it was asked to resume."""
+    e, length = cfg["training_run"], cfg["perturb_length"]
+    if (e, length) == (3, 5):
+        raise RuntimeError("condition (3, 5) fails")
+    os.makedirs(cfg["dora_parameters_path"], exist_ok=True)
+    first = cfg["resume_from_epoch"] + 1
+    last = max(0, e - 1) + length + 2
+    with open(cfg["training_res_path"], "a") as f:
+        if f.tell() == 0:
+            f.write("epoch,train_loss\n")
+        for ep in range(first, last + 1):
+            f.write(f"{ep},1.0\n")
+            open(os.path.join(cfg["dora_parameters_path"], f"epoch{ep}_dora_params.pth"), "w").close()
+    with open(os.path.join(cfg["output_dir"], "how.json"), "w") as f:
+        json.dump({"pid": os.getpid(), "kind": cfg.get("hba_resume_kind"), "resume_from_epoch": cfg["resume_from_epoch"],
+                   "resume_dora": cfg.get("resume_dora_parameters_path"), "t": __import__("time").time()}, f)
+
+
+def test_chained_length_sweep_on_two_workers(tmp_path):
+    from hba import sweep
+    conds = [{"training_run": s, "perturb_length": l} for s in (1, 3, 7) for l in (2, 5, 10)]
+    base = {"output_base_directory": str(tmp_path), "perturb_type": "random_target", "perturb_length": 1}
+    logs = []
+    res = sweep.run_sweep(base, conds, [None, None], layout="length", run_fn=_fake_length_condition, log=logs.append,
+                          chain=True)
+    assert [r["ok"] for r in res] == [not (c["training_run"] == 3 and c["perturb_length"] == 5) for c in conds]
+    assert "8 successful, 1 failed" in logs[-1]
+    how = {}
+    for c in conds:
+        p = os.path.join(str(tmp_path), f"random_target_e{c['training_run']}_l{c['perturb_length']}", "how.json")
+        if os.path.exists(p):
+            how[(c["training_run"], c["perturb_length"])] = json.load(open(p))
+    for s in (1, 3, 7):
+        chain = [how[(s, l)] for l in (2, 5, 10) if (s, l) in how]
+        assert len({h["pid"] for h in chain}) == 1                            # one start epoch = one worker
+        assert [h["t"] for h in chain] == sorted(h["t"] for h in chain)       # in increasing window length
+    assert how[(1, 2)]["kind"] == "baseline" and how[(1, 2)]["resume_from_epoch"] == 0
+    assert how[(1, 5)]["kind"] == "chain" and how[(1, 5)]["resume_from_epoch"] == 0 + 2
+    assert how[(1, 10)]["kind"] == "chain" and how[(1, 10)]["resume_from_epoch"] == 0 + 5
+    assert how[(7, 10)]["resume_from_epoch"] == 6 + 5
+    assert how[(7, 10)]["resume_dora"].endswith(os.path.join("random_target_e7_l5", "dora_params_7"))
+    # (3, 5) failed before writing anything: (3, 10) chains from the last FINISHED shorter window, (3, 2)
+    assert how[(3, 10)]["kind"] == "chain" and how[(3, 10)]["resume_from_epoch"] == 2 + 2
+    # independent mode keeps every condition on the baseline checkpoint
+    res = sweep.run_sweep(dict(base, output_base_directory=os.path.join(str(tmp_path), "indep")), conds[:3], [None],
+                          layout="length", run_fn=_fake_length_condition, log=logs.append)
+    assert all(r["ok"] for r in res)
+    h = json.load(open(os.path.join(str(tmp_path), "indep", "random_target_e1_l10", "how.json")))
+    assert h["kind"] is None and h["resume_from_epoch"] == 0
+    with pytest.raises(ValueError):
+        sweep.run_sweep(base, conds, [None], layout="sweep", run_fn=_fake_length_condition, chain=True)

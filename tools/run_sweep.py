@@ -7,6 +7,7 @@ longest-first, each condition = the unmodified run_behavioral_training(config).
       --csv-file ... --img-dir ... --inference-csv-file ... --rdm ...
   python tools/run_sweep.py --kind grid ...        # the 136-condition (start, length) grid
   python tools/run_sweep.py --kind grid --plan --gpus 0,1,2,3,4,5,6,7     # print the LPT plan only
+  python tools/run_sweep.py --kind grid --chain ...  # LEN's resume chain: a start epoch's windows in increasing length
 """
 import argparse
 import os
@@ -23,6 +24,8 @@ def main():
     ap.add_argument("--end", type=int, default=98)
     ap.add_argument("--gpus", default="0")
     ap.add_argument("--plan", action="store_true")
+    ap.add_argument("--chain", action="store_true",
+                    help="grid only: LEN's shorter -> longer resume chain, one start epoch per worker at a time")
     ap.add_argument("--perturb-type", default="random_target")
     ap.add_argument("--perturb-distribution", default="target")
     ap.add_argument("--perturb-seed", type=int, default=42)
@@ -39,6 +42,16 @@ def main():
     from hba import sweep
     conds = sweep.single_epoch_conditions(a.start, a.end) if a.kind == "single" else sweep.length_grid_conditions()
     devices = [int(x) for x in a.gpus.split(",")]
+    if a.plan and a.chain:
+        groups = sweep.chain_groups(conds)
+        plan, loads = sweep.lpt_assign(groups, len(devices), cost=sweep.chain_cost)
+        for w, (p, load) in enumerate(zip(plan, loads)):
+            print(f"worker {w} (GPU {devices[w]}): {len(p)} start epochs, {load} expected epochs: "
+                  + " ".join(f"e{g[0]['training_run']}x{len(g)}" for g in p))
+        indep = sum(sweep.expected_epochs(c) for c in conds)
+        print(f"{len(conds)} conditions in {len(groups)} chains; {sum(loads)} epochs (independent: {indep}); "
+              f"makespan {max(loads)} vs ideal {sum(loads) / len(devices):.1f} epochs")
+        return
     if a.plan:
         plan, loads = sweep.lpt_assign(conds, len(devices))
         for w, (p, load) in enumerate(zip(plan, loads)):
@@ -56,7 +69,8 @@ def main():
             "baseline_split_indices_path": os.path.join(a.baseline_dir, "random_states", "dataset_split_indices.pth"),
             "perturb_type": a.perturb_type, "perturb_length": 1, "perturb_distribution": a.perturb_distribution,
             "perturb_seed": a.perturb_seed, "output_base_directory": a.output}
-    results = sweep.run_sweep(base, conds, devices, layout="sweep" if a.kind == "single" else "length")
+    results = sweep.run_sweep(base, conds, devices, layout="sweep" if a.kind == "single" else "length",
+                              chain=a.chain and a.kind == "grid")
     sys.exit(0 if all(r["ok"] for r in results) else 1)
 
 

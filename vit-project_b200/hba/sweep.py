@@ -99,12 +99,113 @@ def condition_config(base_config, cond, layout="sweep"):
     return cfg
 
 
+def last_completed_epoch(training_res_path):
+    """LEN:139-160: the largest (1-indexed) epoch value in an existing result CSV, as a 0-indexed epoch;
+    -1 when there is no usable row."""
+    import csv
+    last = -1
+    if not os.path.exists(training_res_path):
+        return last
+    try:
+        with open(training_res_path, "r") as f:
+            reader = csv.reader(f)
+            next(reader, None)
+            for row in reader:
+                if row:
+                    try:
+                        last = max(last, int(row[0]) - 1)
+                    except (ValueError, IndexError):
+                        continue
+    except OSError:
+        return -1
+    return last
+
+
+def find_previous_run_dir(base_dir, perturb_type, start_epoch, current_length):
+    """LEN:188-221: among the run directories under `base_dir` with the same start epoch token `e{start}_`
+    (and the same perturbation prefix), the one with the largest window length `_l{n}` below
+    `current_length` -> (path, length) or (None, None)."""
+    if not os.path.isdir(base_dir):
+        return None, None
+    candidates = []
+    for name in os.listdir(base_dir):
+        full = os.path.join(base_dir, name)
+        if not os.path.isdir(full) or f"e{start_epoch}_" not in name:
+            continue
+        if perturb_type in ("random_target", "label_shuffle") and not name.startswith(perturb_type):
+            continue
+        length = next((int(p[1:]) for p in name.split("_") if p.startswith("l") and p[1:].isdigit()), None)
+        if length is not None and length < current_length:
+            candidates.append((length, full))
+    if not candidates:
+        return None, None
+    length, path = max(candidates, key=lambda t: t[0])
+    return path, length
+
+
+def apply_length_resume(cfg, log=None):
+    """The resume decisions of LEN:222-253 on a 'length'-layout config, in the reference's order:
+    (1) the run's own result CSV exists -> continue after its last completed epoch from its own
+        checkpoints; (2) a finished run with the same start epoch and a shorter window exists -> resume from
+        the end of THAT window (both runs are identical up to there), `last_epoch = max(0, e-1) + prev_length`;
+    (3) otherwise from the baseline checkpoint of epoch e-1 (what `condition_config` set).
+    Beyond the reference, (2) only accepts a shorter run that really holds the DoRA checkpoint of `last_epoch`
+    (a failed or still-running neighbour is stepped over: next shorter window, finally (3)).  Returns 'existing' | 'chain' |
+    'baseline'."""
+    say = log or (lambda *_: None)
+    e, length = int(cfg["training_run"]), int(cfg["perturb_length"])
+    done = last_completed_epoch(cfg["training_res_path"])
+    if done >= 0:
+        cfg["resume_from_epoch"] = done + 1
+        cfg["previous_training_res_path"] = cfg["training_res_path"]
+        cfg["resume_random_state_path"] = cfg["random_state_path"]
+        cfg["resume_dora_parameters_path"] = cfg["dora_parameters_path"]
+        say(f"Detected existing training run. Resuming from epoch {done + 2}")
+        return "existing"
+    below = length
+    while True:   # the reference takes the longest shorter window; step down past neighbours without a checkpoint
+        prev_dir, prev_length = find_previous_run_dir(cfg["output_base_directory"], cfg.get("perturb_type"), e, below)
+        if prev_dir is None:
+            break
+        last_epoch = max(0, e - 1) + prev_length
+        dora = os.path.join(prev_dir, f"dora_params_{e}", f"epoch{last_epoch}_dora_params.pth")
+        if os.path.exists(dora):
+            cfg["resume_from_epoch"] = last_epoch
+            cfg["previous_training_res_path"] = os.path.join(prev_dir, "training_res.csv")
+            cfg["resume_random_state_path"] = os.path.join(prev_dir, f"random_states_{e}")
+            cfg["resume_dora_parameters_path"] = os.path.join(prev_dir, f"dora_params_{e}")
+            say(f"Detected previous run at '{prev_dir}' with length {prev_length}; resuming from epoch {last_epoch + 1}")
+            return "chain"
+        say(f"Previous run at '{prev_dir}' has no checkpoint of epoch {last_epoch}; looking for a shorter one")
+        below = prev_length
+    return "baseline"
+
+
+def chain_groups(conditions):
+    """Conditions of the length grid grouped by start epoch, each group in increasing window length: the
+    order in which LEN's shorter -> longer resume chain (LEN:188-253) can be used.  A group runs on ONE worker."""
+    groups = {}
+    for c in conditions:
+        groups.setdefault(int(c["training_run"]), []).append(c)
+    return [sorted(g, key=lambda c: int(c.get("perturb_length", 1))) for _, g in sorted(groups.items())]
+
+
+def chain_cost(group, cost=None):
+    """Expected epochs of a chained group: every member but the first skips the window of its predecessor."""
+    cost = cost or expected_epochs
+    total, prev = 0, None
+    for c in group:
+        total += cost(c) - (int(prev.get("perturb_length", 1)) if prev is not None else 0)
+        prev = c
+    return total
+
+
 def _default_run_fn(config):
     from functions.new_cvpr_train_behavior_things_pipeline import run_behavioral_training
     return run_behavioral_training(config)
 
 
-def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn):
+def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn, chain=False):
     # pin the GPU before anything initialises CUDA in this process
     if device_id is not None:
         os.environ["CUDA_VISIBLE_DEVICES"] = str(device_id)
@@ -113,33 +214,48 @@ def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn):
         item = tasks.get()
         if item is None:
             break
-        idx, cond = item
-        t0 = time.time()
-        try:
-            cfg = condition_config(base_config, cond, layout)
-            if device_id is not None:
-                cfg["cuda"] = 0   # the only visible device (NEW:1137-1144)
-            run_fn(cfg)
-            results.put((idx, worker_id, True, time.time() - t0, ""))
-        except Exception as exc:  # SWEEP:215-223: log, count, continue with the next condition
-            results.put((idx, worker_id, False, time.time() - t0, f"{exc}\n{traceback.format_exc()}"))
+        for idx, cond in item:      # one condition, or one resume chain in increasing window length
+            t0 = time.time()
+            try:
+                cfg = condition_config(base_config, cond, layout)
+                if chain:
+                    cfg["hba_resume_kind"] = apply_length_resume(cfg)
+                if device_id is not None:
+                    cfg["cuda"] = 0   # the only visible device (NEW:1137-1144)
+                run_fn(cfg)
+                results.put((idx, worker_id, True, time.time() - t0, ""))
+            except Exception as exc:  # SWEEP:215-223: log, count, continue with the next condition
+                results.put((idx, worker_id, False, time.time() - t0, f"{exc}\n{traceback.format_exc()}"))
 
 
-def run_sweep(base_config, conditions, devices, layout="sweep", run_fn=None, cost=expected_epochs, log=print):
+def run_sweep(base_config, conditions, devices, layout="sweep", run_fn=None, cost=expected_epochs, log=print,
+              chain=False):
     """Runs `conditions` on one worker process per entry of `devices` (CUDA device indices; None
     entries run without pinning, for CPU tests).  Returns a list of result dicts in condition order:
-    {condition, worker, ok, seconds, error}."""
+    {condition, worker, ok, seconds, error}.
+
+    `chain=True` ('length' layout only) schedules LEN's resume chain (LEN:188-253): the conditions of one start
+    epoch form one task, run on one worker in increasing window length, each resuming from the end of the
+    previous, shorter window instead of recomputing it from the baseline epoch (`apply_length_resume`); the
+    groups are handed out longest-first.  `chain=False`: every condition is its own task and resumes from
+    the baseline checkpoint (independent conditions, best balance)."""
     import multiprocessing as mp
+    if chain and layout != "length":
+        raise ValueError("chain=True needs layout='length' (the single-epoch sweep has one window per start epoch)")
     ctx = mp.get_context("spawn")
     tasks, results = ctx.Queue(), ctx.Queue()
-    order = lpt_order(list(conditions), cost)
     index_of = {id(c): i for i, c in enumerate(conditions)}
-    for c in order:
-        tasks.put((index_of[id(c)], c))
+    if chain:
+        groups = chain_groups(list(conditions))
+        for _, _, g in sorted(((-chain_cost(g, cost), i, g) for i, g in enumerate(groups))):
+            tasks.put([(index_of[id(c)], c) for c in g])
+    else:
+        for c in lpt_order(list(conditions), cost):
+            tasks.put([(index_of[id(c)], c)])
     for _ in devices:
         tasks.put(None)
-    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn), daemon=False)
-             for w, dev in enumerate(devices)]
+    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn, chain),
+                         daemon=False) for w, dev in enumerate(devices)]
     t0 = time.time()
     for p in procs:
         p.start()
