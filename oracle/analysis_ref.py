@@ -55,3 +55,54 @@ def recovery_table(baseline_df, runs):
                      "epochs_to_recovery": None if recovery_epoch is None else recovery_epoch - perturbation_end,
                      "recovered": recovery_epoch is not None})
     return pd.DataFrame(rows).sort_values(["start_epoch", "length"]).reset_index(drop=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# FIG2 = Figures/fig2 (Effects of Different Perturbations)/fig2.ipynb
+# ------------------------------------------------------------------------------------------------
+FIG2_TARGET_EPOCHS = [5, 15, 25, 35, 45, 70, 98]          # FIG2 cell 7
+
+
+def fig2_type_deviations(baseline_df, runs_by_type, target_epochs=FIG2_TARGET_EPOCHS):
+    """FIG2 cells 5-7, row by row.  `runs_by_type`: {perturbation name: {run number: DataFrame}} (each type's
+    directory holds flat `training_res_run{e}.csv` files); `baseline_df` trimmed at its minimum test loss
+    (cell 3).  -> {name: {"test_loss": [...], "behavioral_rsa_rho": [...]}} with NaN where the run, the run's
+    row at epoch e, or the baseline row at epoch e is missing."""
+    import math
+    out = {}
+    for name, runs in runs_by_type.items():
+        d_loss, d_ba = [], []
+        for ep in target_epochs:
+            df = runs.get(ep)
+            base_row = baseline_df[baseline_df["epoch"] == ep]
+            # cell 7 compute_deltas -> cell 5 load_run_epoch_value / baseline_epoch_loss
+            run_loss = None
+            if df is not None and "epoch" in df.columns:
+                row = df[df["epoch"] == ep]
+                if len(row) > 0:
+                    run_loss = float(row.iloc[0]["test_loss"])
+            base_loss = float(base_row["test_loss"].iloc[0]) if len(base_row) > 0 else None
+            d_loss.append(math.nan if run_loss is None or base_loss is None else run_loss - base_loss)
+            # cell 5 compute_ba_from_dict
+            if df is None:
+                d_ba.append(math.nan)
+                continue
+            row = df[df["epoch"] == ep]
+            if len(row) == 0 or len(base_row) == 0:
+                d_ba.append(math.nan)
+                continue
+            d_ba.append(float(row.iloc[0]["behavioral_rsa_rho"]) - float(base_row.iloc[0]["behavioral_rsa_rho"]))
+        out[name] = {"test_loss": d_loss, "behavioral_rsa_rho": d_ba}
+    return out
+
+
+def vit_summary_table(effects_df):
+    """Data/vit_results/perturbation_summary_table.csv from perturbation_effects.csv: the six summary columns,
+    rows ordered by (perturb_epoch, perturbation_type), values rounded to 4 decimals (verified cell by cell
+    against the shipped table by oracle/make_analysis_golden.py)."""
+    cols = ["perturb_epoch", "perturbation_type", "delta_loss", "delta_rsa", "baseline_loss", "baseline_rsa"]
+    rows = sorted(effects_df[cols].to_dict("records"), key=lambda r: (r["perturb_epoch"], r["perturbation_type"]))
+    for r in rows:
+        for c in cols[2:]:
+            r[c] = round(float(r[c]), 4)
+    return rows

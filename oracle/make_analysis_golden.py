@@ -23,6 +23,41 @@ SWEEP_DIR = os.path.join(DATA, "single_sweep_experiments")
 COLS = ["epoch", "test_loss", "behavioral_rsa_rho"]
 
 
+FIG2_DIRS = {"image_noise": "image_noise", "blank_image": "uniform_target", "label_shuffle": "label_shuffle",
+             "target_noise": "target_noise"}          # FIG2 cell 7: name -> directory under Data/clip_results
+
+
+def fig2_golden(base):
+    """FIG2: the four perturbation-type directories (flat training_res_run{e}.csv files) against the trimmed
+    baseline, and the ViT summary table against the shipped Data/vit_results/perturbation_summary_table.csv."""
+    runs_by_type, excerpt = {}, {}
+    for name, d in FIG2_DIRS.items():
+        runs_by_type[name] = {}
+        for f in sorted(os.listdir(os.path.join(DATA, d))):
+            if f.startswith("training_res_run") and f.endswith(".csv"):
+                e = int(f[len("training_res_run"):-4])
+                df = pd.read_csv(os.path.join(DATA, d, f))
+                runs_by_type[name][e] = df
+        # excerpt: per run, the rows around its perturbed epoch are all the cells read
+        excerpt[name] = {str(e): [[int(r.epoch), float(r.test_loss), float(r.behavioral_rsa_rho)]
+                                  for r in df[(df["epoch"] >= e - 1) & (df["epoch"] <= e + 1)].itertuples()]
+                         for e, df in runs_by_type[name].items()}
+    dev = ref.fig2_type_deviations(base, runs_by_type)
+    vit_dir = "/root/reference/Data/vit_results"
+    eff = pd.read_csv(os.path.join(vit_dir, "perturbation_effects.csv"))
+    shipped = pd.read_csv(os.path.join(vit_dir, "perturbation_summary_table.csv"))
+    table = ref.vit_summary_table(eff)
+    assert list(shipped.columns) == list(table[0].keys()) and len(shipped) == len(table)
+    for want, got in zip(shipped.to_dict("records"), table):      # the restatement reproduces the shipped table
+        assert want == got, (want, got)
+    nan_to_none = lambda xs: [None if v != v else float(v) for v in xs]
+    return {"fig2_target_epochs": ref.FIG2_TARGET_EPOCHS,
+            "fig2_runs": excerpt,
+            "fig2_expected": {n: {k: nan_to_none(v) for k, v in d.items()} for n, d in dev.items()},
+            "vit_effects_rows": eff.to_dict("records"),
+            "vit_summary_csv": open(os.path.join(vit_dir, "perturbation_summary_table.csv")).read()}
+
+
 def main():
     base_raw = pd.read_csv(os.path.join(DATA, "baseline_clip_results_seed1.csv"))
     base = ref.trim_at_min_test_loss(base_raw)
@@ -77,6 +112,7 @@ def main():
                          "sum_delta_test_loss": float(sum(v for _, v in d_loss)),
                          "sum_delta_rsa": float(sum(v for _, v in d_rsa))},
     }
+    out.update(fig2_golden(base))
     path = os.path.join(ROOT, "tests", "golden", "analysis.json")
     json.dump(out, open(path, "w"))
     print(path, os.path.getsize(path), "bytes;", out["full_summary"])

@@ -132,3 +132,97 @@ def test_full_reference_result_set_summary():
     assert len(s) == f["n_single_with_deviation"]
     assert abs(float(s["delta_test_loss"].sum()) - f["sum_delta_test_loss"]) < 1e-9
     assert abs(float(s["delta_behavioral_rsa_rho"].sum()) - f["sum_delta_rsa"]) < 1e-9
+
+
+# ------------------------------------------------------------------------------- FIG2
+def _fig2_runs():
+    return {name: {int(e): frame(rows) for e, rows in runs.items()} for name, runs in GOLD["fig2_runs"].items()}
+
+
+def test_perturbation_type_comparison_matches_reference_golden():
+    """FIG2 cells 5-9 on the excerpt of the reference's shipped Data/clip_results/{image_noise, uniform_target,
+    label_shuffle, target_noise}: the deltas the notebook plots, and the row-by-row restatement."""
+    base = trimmed_baseline()
+    runs = _fig2_runs()
+    got = analysis.perturbation_type_comparison(base, runs)
+    assert list(analysis.FIG2_TARGET_EPOCHS) == GOLD["fig2_target_epochs"] == ref.FIG2_TARGET_EPOCHS
+    assert list(got.columns) == ["perturbation", "epoch", "delta_test_loss", "delta_behavioral_rsa_rho"]
+    assert len(got) == 4 * 7 and list(got["perturbation"].unique()) == ["image_noise", "blank_image", "label_shuffle", "target_noise"]
+    again = ref.fig2_type_deviations(base, runs)
+    for name, want in GOLD["fig2_expected"].items():
+        sub = got[got["perturbation"] == name]
+        assert list(sub["epoch"]) == GOLD["fig2_target_epochs"]
+        for col, key in (("delta_test_loss", "test_loss"), ("delta_behavioral_rsa_rho", "behavioral_rsa_rho")):
+            w = np.array([np.nan if v is None else v for v in want[key]])
+            assert np.array_equal(sub[col].to_numpy(), w, equal_nan=True)
+            assert np.array_equal(np.array(again[name][key]), w, equal_nan=True)
+    # the qualitative finding of the figure: every perturbation hurts more the later it comes
+    ls = got[got["perturbation"] == "label_shuffle"]["delta_test_loss"].to_numpy()
+    assert (np.diff(ls) > 0).all()
+
+
+def test_perturbation_type_comparison_missing_pieces(tmp_path):
+    base = pd.DataFrame({"epoch": [1, 2, 3], "test_loss": [9.0, 8.0, 7.0], "behavioral_rsa_rho": [0.1, 0.2, 0.3]})
+    run2 = pd.DataFrame({"epoch": [1, 2, 3], "test_loss": [9.0, 8.5, 7.0], "behavioral_rsa_rho": [0.1, 0.15, 0.3]})
+    run3_no_row = pd.DataFrame({"epoch": [1, 2], "test_loss": [9.0, 8.0], "behavioral_rsa_rho": [0.1, 0.2]})
+    runs = {"a": {2: run2, 3: run3_no_row, 5: run2}, "b": {}}
+    got = analysis.perturbation_type_comparison(base, runs, target_epochs=(2, 3, 5))
+    want = ref.fig2_type_deviations(base, runs, target_epochs=[2, 3, 5])
+    a = got[got["perturbation"] == "a"]
+    assert a["delta_test_loss"].tolist()[0] == 0.5 and np.isnan(a["delta_test_loss"].tolist()[1:]).all()
+    assert abs(a["delta_behavioral_rsa_rho"].tolist()[0] + 0.05) < 1e-15
+    assert got[got["perturbation"] == "b"][["delta_test_loss", "delta_behavioral_rsa_rho"]].isna().all().all()
+    for name in ("a", "b"):
+        sub = got[got["perturbation"] == name]
+        assert np.array_equal(sub["delta_test_loss"].to_numpy(), np.array(want[name]["test_loss"]), equal_nan=True)
+        assert np.array_equal(sub["delta_behavioral_rsa_rho"].to_numpy(), np.array(want[name]["behavioral_rsa_rho"]), equal_nan=True)
+    # directory form + CLI
+    root = tmp_path / "results"
+    for d in ("label_shuffle", "image_noise"):
+        (root / d).mkdir(parents=True)
+        run2.to_csv(root / d / "training_res_run2.csv", index=False)
+    (root / "label_shuffle" / "notes.txt").write_text("x")
+    bcsv = tmp_path / "baseline.csv"
+    pd.concat([base, pd.DataFrame({"epoch": [4], "test_loss": [7.5], "behavioral_rsa_rho": [0.3]})]).to_csv(bcsv, index=False)
+    t = analysis.perturbation_type_summary(str(bcsv), str(root), target_epochs=(2,))
+    by = dict(zip(t["perturbation"], t["delta_test_loss"]))
+    assert by["label_shuffle"] == 0.5 and by["image_noise"] == 0.5 and np.isnan(by["blank_image"]) and np.isnan(by["target_noise"])
+
+
+def test_vit_summary_table_reproduces_the_shipped_csv(tmp_path):
+    """Data/vit_results/perturbation_effects.csv -> perturbation_summary_table.csv, text for text."""
+    eff = pd.DataFrame(GOLD["vit_effects_rows"])
+    got = analysis.vit_perturbation_summary(eff)
+    assert got.to_csv(index=False) == GOLD["vit_summary_csv"]
+    assert got.to_dict("records") == ref.vit_summary_table(eff)
+    src = tmp_path / "effects.csv"
+    eff.to_csv(src, index=False)
+    out = tmp_path / "summary.csv"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "analyze_sweep.py"), "--kind", "vit-summary", "--effects",
+                        str(src), "--out", str(out)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert out.read_text() == GOLD["vit_summary_csv"]
+    # the columns are the ones hba.vit_train writes
+    from hba import vit_train
+    assert set(analysis.VIT_SUMMARY_COLUMNS) <= set(vit_train.RESULT_COLUMNS)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Data/clip_results"), reason="reference not mounted")
+def test_fig2_tables_from_the_reference_tree_directly(tmp_path):
+    """The directory-level entry points on the reference's own Data/ tree (only where it is mounted)."""
+    data = "/root/reference/Data"
+    t = analysis.perturbation_type_summary(os.path.join(data, "clip_results", "baseline_clip_results_seed1.csv"),
+                                           os.path.join(data, "clip_results"))
+    for name, want in GOLD["fig2_expected"].items():
+        sub = t[t["perturbation"] == name]
+        assert np.array_equal(sub["delta_test_loss"].to_numpy(), np.array(want["test_loss"], dtype=np.float64), equal_nan=True)
+        assert np.array_equal(sub["delta_behavioral_rsa_rho"].to_numpy(),
+                              np.array(want["behavioral_rsa_rho"], dtype=np.float64), equal_nan=True)
+    out = tmp_path / "fig2.csv"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "analyze_sweep.py"), "--kind", "types", "--baseline",
+                        os.path.join(data, "clip_results", "baseline_clip_results_seed1.csv"), "--sweep-dir",
+                        os.path.join(data, "clip_results"), "--out", str(out)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert len(pd.read_csv(out)) == 28
+    shipped = open(os.path.join(data, "vit_results", "perturbation_summary_table.csv")).read()
+    assert analysis.vit_perturbation_summary(os.path.join(data, "vit_results", "perturbation_effects.csv")).to_csv(index=False) == shipped

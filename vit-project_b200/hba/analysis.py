@@ -99,3 +99,62 @@ def single_sweep_summary(baseline_csv, sweep_root):
 def length_grid_summary(baseline_csv, base_dir, prefix="random_target"):
     """One row per (start, length) condition of the variable-length grid: the recovery table of FIG4."""
     return recovery_table(load_baseline(baseline_csv), discover_length_runs(base_dir, prefix))
+
+
+# ------------------------------------------------------------------------------------------------
+# FIG2 = Figures/fig2 (Effects of Different Perturbations)/fig2.ipynb: the four perturbation types side by side
+# (CLIP-HBA, cells 3-9) and the ViT measurement table (cells 12-14, Data/vit_results)
+# ------------------------------------------------------------------------------------------------
+FIG2_TARGET_EPOCHS = (5, 15, 25, 35, 45, 70, 98)          # FIG2 cell 7
+FIG2_TYPE_DIRS = {"image_noise": "image_noise", "blank_image": "uniform_target", "label_shuffle": "label_shuffle",
+                  "target_noise": "target_noise"}         # FIG2 cell 7: plotted name -> directory of the runs
+VIT_SUMMARY_COLUMNS = ["perturb_epoch", "perturbation_type", "delta_loss", "delta_rsa", "baseline_loss", "baseline_rsa"]
+
+
+def discover_flat_runs(root):
+    """{run number: DataFrame} from the flat `training_res_run{e}.csv` files of one perturbation type
+    (FIG2 cell 5 `load_all_run_data`)."""
+    runs = {}
+    if not os.path.isdir(root):
+        return runs
+    for name in sorted(os.listdir(root)):
+        m = re.fullmatch(r"training_res_run(\d+)\.csv", name)
+        if m:
+            runs[int(m.group(1))] = pd.read_csv(os.path.join(root, name))
+    return runs
+
+
+def perturbation_type_comparison(baseline_df, runs_by_type, target_epochs=FIG2_TARGET_EPOCHS):
+    """FIG2 cells 5-9 as one long table: for every perturbation type and target epoch e, the run
+    `training_res_run{e}`'s test loss / behavioural alignment AT epoch e minus the (trimmed) baseline's; NaN
+    where the run, its row, or the baseline row is missing.  Columns: perturbation, epoch, delta_test_loss,
+    delta_behavioral_rsa_rho."""
+    base = baseline_df.drop_duplicates("epoch").set_index("epoch")
+    rows = []
+    for name, runs in runs_by_type.items():
+        for e in target_epochs:
+            d_loss = d_ba = np.nan
+            df = runs.get(e)
+            if df is not None and "epoch" in df.columns and e in base.index:
+                hit = df[df["epoch"] == e]
+                if len(hit) > 0:
+                    d_loss = float(hit.iloc[0]["test_loss"]) - float(base.at[e, "test_loss"])
+                    d_ba = float(hit.iloc[0]["behavioral_rsa_rho"]) - float(base.at[e, "behavioral_rsa_rho"])
+            rows.append((name, e, d_loss, d_ba))
+    return pd.DataFrame(rows, columns=["perturbation", "epoch", "delta_test_loss", "delta_behavioral_rsa_rho"])
+
+
+def perturbation_type_summary(baseline_csv, results_root, type_dirs=None, target_epochs=FIG2_TARGET_EPOCHS):
+    """The FIG2 (A)/(B) table from a results tree laid out like the reference's Data/clip_results."""
+    type_dirs = type_dirs or FIG2_TYPE_DIRS
+    runs = {name: discover_flat_runs(os.path.join(results_root, d)) for name, d in type_dirs.items()}
+    return perturbation_type_comparison(load_baseline(baseline_csv), runs, target_epochs)
+
+
+def vit_perturbation_summary(effects):
+    """Data/vit_results/perturbation_summary_table.csv from the rows `hba.vit_train.measure_all` (reference
+    MEAS:653-657) writes: the six summary columns, ordered by (perturb_epoch, perturbation_type), rounded to
+    4 decimals.  `effects`: CSV path or DataFrame."""
+    df = pd.read_csv(effects) if isinstance(effects, (str, os.PathLike)) else effects
+    out = df.sort_values(["perturb_epoch", "perturbation_type"], kind="stable")[VIT_SUMMARY_COLUMNS]
+    return out.round(4).reset_index(drop=True)
