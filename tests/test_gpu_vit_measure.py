@@ -286,9 +286,15 @@ def test_drop_in_scripts_end_to_end_on_synthetic_data(tmp_path):
     assert ck["scheduler_state_dict"]["current_epoch"] == 2
     assert ck["optimizer_state_dict"]["param_groups"][0]["lr"] == pytest.approx(0.1 * 2 / 5)
     assert len(ck["optimizer_state_dict"]["state"]) == len(ck["model_state_dict"])
-    m["rsa_score"] = [0.1, 0.2, 0.3]
-    base_csv = os.path.join(out, "with_rsa.csv")
-    m.to_csv(base_csv, index=False)
+    # RSA of every checkpoint -> the measurement's baseline CSV (schema of the shipped rsa_results_final.csv)
+    from hba import vit_train as vt
+    things, rdm = vt.synthetic_things(DEV)
+    base_csv = os.path.join(out, "rsa_results.csv")
+    rows = vt.rsa_over_checkpoints(out, things, rdm, base_csv, model_name="vit_tiny_test", num_classes=CLASSES, log=None)
+    b = pd.read_csv(base_csv)
+    assert list(b.columns) == ["checkpoint", "epoch", "train_loss", "val_loss", "val_acc", "rsa_score"]
+    assert b["epoch"].tolist() == [0, 1, 2] and np.isfinite(b["rsa_score"].to_numpy()).all()
+    assert np.allclose(b["val_loss"], m["val_loss"], atol=1e-6) and len(rows) == 3
     res_csv = os.path.join(str(tmp_path), "effects.csv")
     measure_script.main(["--baseline_checkpoint_dir", out, "--baseline_metrics_csv", base_csv, "--data_path",
                          f"synthetic:16:8:{CLASSES}", "--output_csv", res_csv, "--things_csv", "synthetic",
@@ -299,4 +305,5 @@ def test_drop_in_scripts_end_to_end_on_synthetic_data(tmp_path):
                                 "perturbed_rsa", "delta_loss", "delta_rsa"]
     assert df["perturb_epoch"].tolist() == [2, 2] and df["perturbation_type"].tolist() == ["label_shuffle", "uniform_gray"]
     assert np.isfinite(df[["perturbed_loss", "perturbed_rsa"]].to_numpy()).all()
+    assert np.allclose(df["baseline_rsa"], b["rsa_score"][2], rtol=1e-12) and np.allclose(df["baseline_loss"], b["val_loss"][2], rtol=1e-12)
     assert (df["delta_loss"] - (df["perturbed_loss"] - df["baseline_loss"])).abs().max() < 1e-9

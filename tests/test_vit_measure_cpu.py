@@ -477,3 +477,50 @@ def test_trainer_optimizer_state_layout_on_host(monkeypatch):
     with pytest.raises(ValueError):
         bad = {i: {"momentum_buffer": torch.zeros(3)} for i in want["state"]}
         tr.load_state_dict({"state": bad, "param_groups": want["param_groups"]})
+
+
+# ------------------------------------------------------------------------------- RSA over checkpoints
+def _rsa_ckpt_worker(rank, world, port, ckdir, out_csv):
+    import torch.distributed as dist
+    from hba import vit, vit_train as vt
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    _, _, things, rdm = _tiny_problem(seed=6)
+    factory = _tiny_factory()
+    vit.create_model = lambda name, pretrained=False, num_classes=1000: factory()
+    vt.rsa_over_checkpoints(ckdir, vt.ResidentImageSet(things), rdm, out_csv, rank=rank, world_size=world,
+                            evaluator=_ScipyEvaluator(rdm), log=None)
+    dist.destroy_process_group()
+
+
+def test_rsa_over_checkpoints_schema_sharding_and_values(tmp_path, monkeypatch):
+    """One row per checkpoint in the shipped rsa_results_final.csv schema; checkpoints sharded over a world-2
+    `gloo` group give the single-process table; every rho equals the oracle's on that checkpoint's weights."""
+    import pandas as pd
+    import torch.multiprocessing as mp
+    from hba import vit
+    from oracle import vit_measure_ref as ref
+    vt = _vt()
+    train, val, things, rdm = _tiny_problem(seed=6)
+    factory = _tiny_factory()
+    ckdir, _ = _write_baseline(tmp_path, factory, train, val, epochs=3)
+    monkeypatch.setattr(vit, "create_model", lambda name, pretrained=False, num_classes=1000: factory())
+    out1 = os.path.join(str(tmp_path), "rsa1.csv")
+    rows = vt.rsa_over_checkpoints(ckdir, vt.ResidentImageSet(things), rdm, out1, evaluator=_ScipyEvaluator(rdm), log=None)
+    df = pd.read_csv(out1)
+    assert list(df.columns) == ["checkpoint", "epoch", "train_loss", "val_loss", "val_acc", "rsa_score"]   # shipped schema
+    assert df["checkpoint"].tolist() == [f"checkpoint_epoch_{e:03d}" for e in range(3)] and df["epoch"].tolist() == [0, 1, 2]
+    metrics = pd.read_csv(os.path.join(ckdir, "training_metrics.csv"))
+    assert np.allclose(df["val_loss"], metrics["val_loss"], atol=1e-6)          # the CSV keeps 6 decimals
+    for r in rows:
+        ck = torch.load(os.path.join(ckdir, r["checkpoint"] + ".pth"), weights_only=False)
+        m = factory()
+        m.load_state_dict(ck["model_state_dict"])
+        assert r["rsa_score"] == ref.compute_rsa_score_ref(m, things, rdm)[0]
+        assert r["val_loss"] == ck["val_loss"]
+    # usable as the measurement's baseline CSV (MEAS:421-433)
+    assert vt.baseline_row(out1, 2) == pytest.approx((rows[2]["val_loss"], rows[2]["rsa_score"]), rel=1e-14)
+    out2 = os.path.join(str(tmp_path), "rsa2.csv")
+    mp.spawn(_rsa_ckpt_worker, args=(2, 29250 + os.getpid() % 200, ckdir, out2), nprocs=2, join=True)
+    assert open(out2).read() == open(out1).read()
+    with pytest.raises(FileNotFoundError):
+        vt.rsa_over_checkpoints(str(tmp_path / "empty"), vt.ResidentImageSet(things), rdm, evaluator=_ScipyEvaluator(rdm))

@@ -597,3 +597,59 @@ def synthetic_things(device, n=48, dim=66, seed=2, img_size=224):
     rdm = 1.0 - np.corrcoef(human)
     np.fill_diagonal(rdm, 0.0)
     return ResidentImageSet(images.to(device)), rdm
+
+
+# ------------------------------------------------------------------------------------------------
+# RSA of every checkpoint of a baseline run -> the `baseline_metrics_csv` the measurement reads
+# ------------------------------------------------------------------------------------------------
+RSA_RESULTS_COLUMNS = ("checkpoint", "epoch", "train_loss", "val_loss", "val_acc", "rsa_score")
+
+
+def rsa_over_checkpoints(checkpoint_dir, things_data, things_rdm, output_csv=None, model_name="vit_base_patch16_224",
+                         num_classes=1000, rank=0, world_size=1, dataset_order=True, evaluator=None, log=print):
+    """The table shipped as Data/vit_results/rsa_results_final.csv (`checkpoint, epoch, train_loss, val_loss,
+    val_acc, rsa_score`, one row per `checkpoint_epoch_XXX.pth` of a `train_vit_sgd.py` run): what
+    `measure_perturbation_effect` reads as `baseline_metrics_csv` (MEAS:421-433 needs `epoch`, `val_loss`,
+    `rsa_score`).  The reference ships the table but not the script that made it; the per-checkpoint
+    computation is `compute_rsa_score` (MEAS:298-355) on the checkpoint's weights.
+
+    Checkpoints are independent ("RSA at scale"): rank r evaluates the files r, r+W, ... on ALL
+    RSA images, no data-path collective; the rows are gathered on rank 0, which writes the CSV.  Returns the
+    rows (rank 0) or None."""
+    import glob
+    from . import vit
+    files = sorted(glob.glob(os.path.join(checkpoint_dir, "checkpoint_epoch_*.pth")))
+    if not files:
+        raise FileNotFoundError(f"no checkpoint_epoch_*.pth under {checkpoint_dir}")
+    device = things_data.images.device
+    model = vit.create_model(model_name, pretrained=False, num_classes=num_classes).to(device)
+    loader = ShardedLoader(things_data, 8, 1, 0, shuffle=False, with_names=True)
+    if evaluator is None:
+        from .rsa import RSAEvaluator
+        evaluator = RSAEvaluator(load_reference_rdm(things_rdm), device)
+    rows = []
+    for path in files[rank::world_size]:
+        ck = torch.load(path, map_location=device, weights_only=False)
+        model.load_state_dict(ck["model_state_dict"])
+        rho, _ = compute_rsa_score(model, loader, things_rdm, 0, 1, dataset_order=dataset_order, evaluator=evaluator)
+        rows.append({"checkpoint": os.path.splitext(os.path.basename(path))[0], "epoch": int(ck["epoch"]),
+                     "train_loss": float(ck.get("train_loss", float("nan"))),
+                     "val_loss": float(ck.get("val_loss", float("nan"))),
+                     "val_acc": float(ck.get("val_acc", float("nan"))), "rsa_score": float(rho)})
+        if log is not None:
+            log(f"[rank {rank}] {rows[-1]['checkpoint']}: RSA {rho:.4f}")
+    if world_size > 1:
+        d = _dist()
+        if d is None:
+            raise RuntimeError("world_size > 1 needs an initialised process group")
+        gathered = [None] * world_size
+        d.all_gather_object(gathered, rows)
+        rows = [r for part in gathered for r in part]
+    if rank != 0:
+        return None
+    rows.sort(key=lambda r: (r["epoch"], r["checkpoint"]))
+    if output_csv:
+        import pandas as pd
+        os.makedirs(os.path.dirname(os.path.abspath(output_csv)), exist_ok=True)
+        pd.DataFrame(rows, columns=list(RSA_RESULTS_COLUMNS)).to_csv(output_csv, index=False)
+    return rows
