@@ -524,3 +524,86 @@ def test_rsa_over_checkpoints_schema_sharding_and_values(tmp_path, monkeypatch):
     assert open(out2).read() == open(out1).read()
     with pytest.raises(FileNotFoundError):
         vt.rsa_over_checkpoints(str(tmp_path / "empty"), vt.ResidentImageSet(things), rdm, evaluator=_ScipyEvaluator(rdm))
+
+
+# ------------------------------------------------------------------------------- streamed ImageFolder data
+def _image_tree(root, classes=3, per_class=4, val_per_class=2, size=40):
+    from PIL import Image
+    rng = np.random.RandomState(0)
+    for split, n in (("train", per_class), ("val", val_per_class)):
+        for c in range(classes):
+            d = os.path.join(root, split, f"class{c}")
+            os.makedirs(d)
+            for i in range(n):
+                Image.fromarray(rng.randint(0, 255, (size, size + 8, 3), dtype=np.uint8)).save(os.path.join(d, f"{i}.jpg"))
+    return root
+
+
+@pytest.mark.parametrize("kind", [None, "label_shuffle", "target_noise", "uniform_gray", "gaussian"])
+def test_streamed_imagefolder_loaders_follow_the_reference_pipeline(tmp_path, kind):
+    """imagenet_loaders (VIT:29-87 / MEAS:139-227) on a tiny JPEG tree: batch shapes, the label stream of a rank
+    (sampler order x label perturbation) and the image perturbations; against the reference's own
+    get_dataloaders where /root/reference is mounted."""
+    vt = _vt()
+    root = _image_tree(str(tmp_path / "data"))
+    tl, vl, sampler = vt.imagenet_loaders(root, 4, 1, 2, 1, torch.device("cpu"), perturbation_type=kind, epsilon=0.1)
+    assert tl.sampler is sampler
+    sampler.set_epoch(3)
+    got = [(x.shape, y.tolist(), float(x.abs().max()), float(x.std())) for x, y in tl]
+    assert [g[0] for g in got] == [torch.Size([4, 3, 224, 224]), torch.Size([2, 3, 224, 224])]       # 12 images / 2 ranks
+    if kind == "uniform_gray":
+        assert all(g[2] == 0.0 for g in got)
+    elif kind == "gaussian":
+        assert all(abs(g[3] - 0.1) < 0.01 for g in got)
+    else:
+        assert all(g[2] > 1.0 for g in got)                       # normalised natural-range pixels
+    vals = [(x.shape[0], y.tolist()) for x, y in vl]
+    assert sum(n for n, _ in vals) == 3 and all(x.dtype == torch.float32 for x, _ in vl)   # 6 val images / 2 ranks
+    if os.path.isdir("/root/reference/Training/vit_training"):
+        from oracle import make_vit_measure_golden as mk
+        MEAS, _ = mk.load_reference_scripts()
+        rtl, rvl, rsampler = MEAS.get_dataloaders(root, 4, 1, 2, 1, perturbation_type=kind, epsilon=0.1, shuffle_seed=42)
+        rsampler.set_epoch(3)
+        want = [y.tolist() for _, y in rtl]
+        assert [g[1] for g in got] == want
+        assert [y for _, y in vals] == [y.tolist() for _, y in rvl]
+
+
+def test_measurement_streams_an_imagefolder_tree(tmp_path, monkeypatch):
+    """measure_perturbation_effect(train_data=None, data_path=<ImageFolder root>): the reference's real-data
+    invocation (MEAS:512-517), with the device trainer replaced by the CPU stand-in."""
+    from hba import vit
+    from oracle import vit_ref
+    vt = _vt()
+    root = _image_tree(str(tmp_path / "data"))
+    factory = lambda: vit_ref.VisionTransformerRef(img_size=224, patch_size=16, embed_dim=64, depth=1, num_heads=1,
+                                                   num_classes=1000)
+    monkeypatch.setattr(vit, "create_model", lambda name, pretrained=False, num_classes=1000: factory())
+    monkeypatch.setattr(vit, "DataParallelTrainer", _TorchTrainer)
+    # a one-epoch baseline on the same tree, through the same loaders
+    torch.manual_seed(0)
+    model = factory()
+    tr = _TorchTrainer(model, lr=0.01)
+    sched = vit.CosineAnnealingLRWithWarmup(tr, 5, 100)
+    tl, vl, sampler = vt.imagenet_loaders(root, 4, 1, 1, 0, torch.device("cpu"))
+    ckdir = str(tmp_path / "baseline")
+    for epoch in range(2):
+        sampler.set_epoch(epoch)
+        a = vt.train_one_epoch(tr, tl, epoch, log=None)
+        sched.step()
+        b, c = vt.validate(tr, vl)
+        vt.save_checkpoint(epoch, model, tr, sched, a, b, c, ckdir)
+    g = torch.Generator().manual_seed(0)
+    things = torch.randn(12, 3, 224, 224, generator=g)
+    rdm = 1 - np.corrcoef(torch.randn(12, 9, generator=g).double().numpy())
+    np.fill_diagonal(rdm, 0)
+    csv = os.path.join(ckdir, "rsa.csv")
+    vt.rsa_over_checkpoints(ckdir, vt.ResidentImageSet(things), rdm, csv, evaluator=_ScipyEvaluator(rdm), log=None)
+    got = vt.measure_perturbation_effect(1, "label_shuffle", ckdir, csv, None, None, vt.ResidentImageSet(things), rdm,
+                                         batch_size=4, evaluator=_ScipyEvaluator(rdm), log=None, data_path=root,
+                                         num_workers=1)
+    assert list(got) == list(vt.RESULT_COLUMNS) and np.isfinite(got["perturbed_loss"]) and np.isfinite(got["perturbed_rsa"])
+    assert got["delta_loss"] == got["perturbed_loss"] - got["baseline_loss"]
+    with pytest.raises(ValueError):
+        vt.measure_perturbation_effect(1, "label_shuffle", ckdir, csv, None, None, vt.ResidentImageSet(things), rdm,
+                                       evaluator=_ScipyEvaluator(rdm), log=None)

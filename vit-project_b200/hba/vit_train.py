@@ -430,7 +430,7 @@ def measure_perturbation_effect(perturb_epoch, perturbation_type, baseline_check
                                 lr=0.1, momentum=0.9, weight_decay=1e-4, warmup_epochs=5, total_epochs=100,
                                 rank=0, world_size=1, local_rank=0, model_name="vit_base_patch16_224",
                                 num_classes=1000, use_graph=True, dataset_order=True, noise_seed=None,
-                                evaluator=None, log=print):
+                                evaluator=None, log=print, data_path=None, num_workers=8):
     """MEAS:403-555.  Loads the baseline checkpoint of epoch N-1 (model, SGD momentum, scheduler), trains
     ONLY epoch N on the perturbed training data, evaluates on the clean validation data, computes the RSA
     of the CLS features on the THINGS images and returns the row of `RESULT_COLUMNS` (None when the baseline
@@ -439,7 +439,9 @@ def measure_perturbation_effect(perturb_epoch, perturbation_type, baseline_check
     `train_data` / `val_data` / `things_data`: `ResidentImageSet`s on this rank's device (the reference
     builds ImageFolder loaders from `data_path`; the resident sets are the whole dataset, each rank reads its
     `DistributedSampler` share).  `noise_seed` seeds the device generator of the 'gaussian' perturbation
-    (the reference's noise comes from unseeded worker processes)."""
+    (the reference's noise comes from unseeded worker processes).  With `train_data is None` and a
+    `data_path`, the epoch streams a real ImageFolder tree through the reference's own torchvision pipeline and
+    dataset wrappers instead (`imagenet_loaders`, MEAS:139-227; ImageNet does not fit in HBM)."""
     from . import vit
     say = log if (rank == 0 and log is not None) else (lambda *_: None)
     say(f"\n{'=' * 80}\nMeasuring: {perturbation_type} @ epoch {perturb_epoch}\n{'=' * 80}")
@@ -454,7 +456,7 @@ def measure_perturbation_effect(perturb_epoch, perturbation_type, baseline_check
         say(f"Checkpoint not found: {checkpoint_path}")
         return None
 
-    device = train_data.images.device
+    device = train_data.images.device if train_data is not None else things_data.images.device
     model = vit.create_model(model_name, pretrained=False, num_classes=num_classes).to(device)
     trainer = vit.DataParallelTrainer(model, lr=lr, momentum=momentum, weight_decay=weight_decay,
                                       use_graph=use_graph)
@@ -462,13 +464,20 @@ def measure_perturbation_effect(perturb_epoch, perturbation_type, baseline_check
                                                 eta_min=0)
     load_checkpoint(checkpoint_path, model, trainer, scheduler, device)
 
-    gen = None
-    if perturbation_type == "gaussian" and noise_seed is not None:
-        gen = torch.Generator(device=device).manual_seed(noise_seed + rank)
-    train_loader = ShardedLoader(train_data, batch_size, world_size, rank, shuffle=True,
-                                 perturbation_type=perturbation_type, epsilon=epsilon, shuffle_seed=42,
-                                 num_classes=num_classes, noise_generator=gen)
-    val_loader = ShardedLoader(val_data, batch_size, world_size, rank, shuffle=False)
+    if train_data is None:
+        if data_path is None:
+            raise ValueError("measure_perturbation_effect: pass resident train_data / val_data or a data_path")
+        train_loader, val_loader, _ = imagenet_loaders(data_path, batch_size, num_workers, world_size, rank, device,
+                                                       perturbation_type=perturbation_type, epsilon=epsilon,
+                                                       shuffle_seed=42)
+    else:
+        gen = None
+        if perturbation_type == "gaussian" and noise_seed is not None:
+            gen = torch.Generator(device=device).manual_seed(noise_seed + rank)
+        train_loader = ShardedLoader(train_data, batch_size, world_size, rank, shuffle=True,
+                                     perturbation_type=perturbation_type, epsilon=epsilon, shuffle_seed=42,
+                                     num_classes=num_classes, noise_generator=gen)
+        val_loader = ShardedLoader(val_data, batch_size, world_size, rank, shuffle=False)
     things_loader = ShardedLoader(things_data, 8, world_size, rank, shuffle=False, with_names=True)  # MEAS:458-464
     train_loader.sampler.set_epoch(perturb_epoch)                                                     # MEAS:519
 

@@ -64,7 +64,7 @@ def build_parser():
     p = argparse.ArgumentParser(description="Measure single-epoch perturbation effects on ViT")
     p.add_argument("--baseline_checkpoint_dir", type=str, required=True, help="Directory containing baseline checkpoints")
     p.add_argument("--baseline_metrics_csv", type=str, required=True, help="Baseline metrics CSV (epoch, val_loss, rsa_score)")
-    p.add_argument("--data_path", type=str, required=True, help="synthetic:NTRAIN:NVAL[:C] (HBM-resident synthetic data)")
+    p.add_argument("--data_path", type=str, required=True, help="Path to ImageNet data, or synthetic:NTRAIN:NVAL[:C]")
     p.add_argument("--output_csv", type=str, required=True, help="Output CSV file for results")
     p.add_argument("--things_csv", type=str, required=True, help="THINGS inference CSV, or 'synthetic'")
     p.add_argument("--things_img_dir", type=str, default="", help="Directory containing THINGS images")
@@ -97,12 +97,14 @@ def main(argv=None):
     if world_size > 1:
         dist.barrier()
     syn = vt.parse_synthetic(args.data_path)
-    if syn is None:
-        raise SystemExit("measure: an ImageFolder tree cannot be kept resident; pass --data_path synthetic:NTRAIN:NVAL[:C] "
-                         "(hba.vit_train.imagenet_loaders streams a real tree for train_vit_sgd.py)")
-    n_train, n_val, classes = syn
-    train = vt.synthetic_imagenet(n_train, classes, seed=0, device=device)
-    val = vt.synthetic_imagenet(n_val, classes, seed=1, device=device)
+    if syn is None:      # a real ImageFolder tree: streamed through the reference's torchvision pipeline (MEAS:139-227)
+        train = val = None
+        classes, data_path = 1000, args.data_path
+    else:                # synthetic stand-ins, kept resident in HBM
+        n_train, n_val, classes = syn
+        train = vt.synthetic_imagenet(n_train, classes, seed=0, device=device)
+        val = vt.synthetic_imagenet(n_val, classes, seed=1, device=device)
+        data_path = None
     things, rdm = load_things(args.things_csv, args.things_img_dir, args.things_rdm_path, device)
     from hba.rsa import RSAEvaluator
     evaluator = RSAEvaluator(rdm, device) if rank == 0 else None
@@ -113,7 +115,8 @@ def main(argv=None):
         batch_size=args.batch_size, lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay,
         warmup_epochs=args.warmup_epochs, total_epochs=args.total_epochs, world_size=world_size,
         local_rank=local_rank, model_name=args.model, num_classes=classes,
-        dataset_order=not args.reference_row_order, noise_seed=args.noise_seed, evaluator=evaluator)
+        dataset_order=not args.reference_row_order, noise_seed=args.noise_seed, evaluator=evaluator,
+        data_path=data_path, num_workers=args.num_workers)
     if rank == 0:
         import pandas as pd
         print(f"\nSaved results to {args.output_csv}\n\nResults summary:")
