@@ -49,3 +49,23 @@ vt.compute_rsa_score(model, tl, rdm); torch.cuda.synchronize(); out["rsa_48_imag
 print(json.dumps(out))
 PY
 echo "measure epoch timing rc=$?"; cat gpurun_out/vit_measure_epoch.json
+#   4. N1 probe: does a second / third sweep worker PROCESS on the same GPU raise conditions/hour (the cached sweep
+#      epoch leaves the GPU idle during its host phases: CSV, checkpoints, RSA read-back)?  Sum of the per-process
+#      conditions/h of k concurrent `bench.py --sweep-only` runs against k = 1.
+for k in 1 2 3; do
+  pids=""
+  for i in $(seq 1 $k); do
+    timeout 400 python bench.py --sweep-only > gpurun_out/sweep_k${k}_p${i}.json 2> gpurun_out/sweep_k${k}_p${i}.err &
+    pids="$pids $!"
+  done
+  for p in $pids; do wait $p; done
+  python - $k <<'PY'
+import glob, json, sys
+k = int(sys.argv[1]); tot = 0.0
+for f in sorted(glob.glob(f"gpurun_out/sweep_k{k}_p*.json")):
+    lines = [l for l in open(f) if l.startswith("{")]
+    if lines:
+        d = json.loads(lines[-1]); tot += d.get("sweep", d).get("conditions_per_hour", 0.0)
+print(f"sweep workers on one GPU: k={k} total conditions/h = {tot:.1f}")
+PY
+done
