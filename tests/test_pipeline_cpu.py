@@ -120,3 +120,47 @@ def test_select_device_has_no_cpu_path():
     assert core.select_device(0) == torch.device("cuda:0") and core.select_device(-1) == torch.device("cuda")
     with pytest.raises(RuntimeError, match="no CPU path"):
         core.select_device(2)
+
+
+def test_background_checkpoint_writer(tmp_path, monkeypatch):
+    """HBA_ASYNC_CKPT=1: same files and contents as the synchronous path, snapshots taken at
+    submit time, atomic replace, flush before loads, write errors surface at flush()."""
+    import pytest
+    from hba.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.arange(4.0))
+    opt = FusedAdamW([p], lr=3e-4)
+    gen = torch.Generator().manual_seed(1)
+    sync_dir, async_dir = str(tmp_path / "sync"), str(tmp_path / "async")
+    torch.manual_seed(5)
+    monkeypatch.delenv("HBA_ASYNC_CKPT", raising=False)
+    assert not core.CheckpointWriter.enabled()
+    core.save_random_states(opt, 0, sync_dir, gen)
+    monkeypatch.setenv("HBA_ASYNC_CKPT", "1")
+    core.save_random_states(opt, 0, async_dir, gen)
+    core.CHECKPOINTS.flush()
+    a = torch.load(os.path.join(sync_dir, "epoch1_random_states.pth"), weights_only=False)
+    b = torch.load(os.path.join(async_dir, "epoch1_random_states.pth"), weights_only=False)
+    assert set(a) == set(b) and torch.equal(a["torch_rng_state"], b["torch_rng_state"])
+    assert a["python_rng_state"] == b["python_rng_state"] and a["epoch"] == b["epoch"] == 0
+    assert str(a["optimizer_state_dict"]) == str(b["optimizer_state_dict"])
+    assert [f for f in os.listdir(async_dir) if ".tmp" in f] == []
+    # snapshot semantics: what is written is the state at submit time
+    live = {"w": torch.zeros(3), "n": np.zeros(2), "nested": [torch.ones(2)]}
+    target = os.path.join(async_dir, "snap.pth")
+    core.CHECKPOINTS.submit(live, target)
+    live["w"].add_(7)
+    live["n"] += 7
+    live["nested"][0].mul_(0)
+    core.CHECKPOINTS.flush()
+    got = torch.load(target, weights_only=False)
+    assert torch.equal(got["w"], torch.zeros(3)) and np.array_equal(got["n"], np.zeros(2)) and torch.equal(got["nested"][0], torch.ones(2))
+    # many epochs queued back to back, then a load: load_random_states flushes first
+    for e in range(1, 9):
+        core.save_random_states(opt, e, async_dir, gen)
+    assert core.load_random_states(async_dir, 9, optimizer=opt, dataloader_generator=gen)
+    assert sorted(os.listdir(async_dir)) == sorted([f"epoch{e}_random_states.pth" for e in range(1, 10)] + ["snap.pth"])
+    # a failing write is reported, once, by the next flush
+    core.CHECKPOINTS.submit({"x": 1}, os.path.join(str(tmp_path), "no_such_dir", "x.pth"))
+    with pytest.raises(RuntimeError, match="background checkpoint write failed"):
+        core.CHECKPOINTS.flush()
+    core.CHECKPOINTS.flush()

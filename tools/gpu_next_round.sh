@@ -69,3 +69,11 @@ for f in sorted(glob.glob(f"gpurun_out/sweep_k{k}_p*.json")):
 print(f"sweep workers on one GPU: k={k} total conditions/h = {tot:.1f}")
 PY
 done
+#   5. background checkpoint writer (HBA_ASYNC_CKPT=1, opt-in): the pipeline tests under it, then the sweep epoch time
+#      with and without it.
+HBA_ASYNC_CKPT=1 timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_sweep.py -q -x -p no:cacheprovider \
+    > gpurun_out/t_async_ckpt.log 2>&1; echo "pipeline tests with HBA_ASYNC_CKPT=1 rc=$?"; tail -3 gpurun_out/t_async_ckpt.log
+for v in 0 1; do
+  HBA_ASYNC_CKPT=$v timeout 300 python bench.py --sweep-only > gpurun_out/sweep_async${v}.json 2> gpurun_out/sweep_async${v}.err
+  echo "HBA_ASYNC_CKPT=$v: $(grep -o '"sec_per_epoch_cached": [0-9.]*' gpurun_out/sweep_async${v}.json)"
+done

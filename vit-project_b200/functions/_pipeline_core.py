@@ -259,13 +259,85 @@ def find_dora_paths(model):
 
 
 # ------------------------------------------------------------------------------- checkpoints
+class CheckpointWriter:
+    """Per-epoch checkpoint files (NEW:657-728) written by a background thread: once the sweep
+    epoch takes tens of milliseconds, the two `torch.save` calls per epoch are a measurable part of it.
+
+    `submit(obj, path)` snapshots `obj` to host memory in the caller (device tensors are copied, host tensors
+    cloned: later in-place updates of the live state do not reach the file), then the thread pickles and writes
+    `path` through a temporary file + `os.replace`, so that a reader never sees a partial checkpoint.  Files and
+    formats are exactly those of the synchronous path.  `flush()` waits for everything submitted and re-raises
+    the first write error; it runs at the end of every `train_model`, before any checkpoint is loaded, and at
+    interpreter exit.  Opt-in: `HBA_ASYNC_CKPT=1` (off by default until it has been timed on a GPU)."""
+
+    def __init__(self):
+        self._queue, self._thread, self._error = None, None, None
+
+    @staticmethod
+    def enabled():
+        return os.environ.get("HBA_ASYNC_CKPT", "0") == "1"
+
+    @classmethod
+    def snapshot(cls, obj):
+        if torch.is_tensor(obj):
+            t = obj.detach()
+            return t.cpu() if t.is_cuda else t.clone()
+        if isinstance(obj, dict):
+            return {k: cls.snapshot(v) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(cls.snapshot(v) for v in obj)
+        if isinstance(obj, np.ndarray):
+            return obj.copy()
+        return obj
+
+    def _run(self):
+        while True:
+            item = self._queue.get()
+            try:
+                if item is None:
+                    return
+                obj, path = item
+                tmp = f"{path}.tmp{os.getpid()}"
+                torch.save(obj, tmp)
+                os.replace(tmp, path)
+            except Exception as exc:  # noqa: BLE001  (reported by flush() in the training thread)
+                if self._error is None:
+                    self._error = exc
+            finally:
+                self._queue.task_done()
+
+    def submit(self, obj, path):
+        if not self.enabled():
+            torch.save(obj, path)
+            return
+        import queue
+        import threading
+        if self._thread is None or not self._thread.is_alive():
+            import atexit
+            self._queue = queue.Queue()
+            self._thread = threading.Thread(target=self._run, name="hba-checkpoint-writer", daemon=True)
+            self._thread.start()
+            atexit.register(self.flush)
+        self._queue.put((self.snapshot(obj), path))
+
+    def flush(self):
+        if self._queue is not None:
+            self._queue.join()
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise RuntimeError(f"background checkpoint write failed: {err}") from err
+
+
+CHECKPOINTS = CheckpointWriter()
+
+
 def save_dora_parameters(model, dora_parameters_path, epoch, logger=None):
     """NEW:657-693: one dict {<module path>.{m,delta_D_A,delta_D_B}: cpu tensor} per epoch.  The
     reference hard-codes blocks 22/23/11 of ViT-L/14; the adapters are located here, which yields
     the same keys for that model."""
     os.makedirs(dora_parameters_path, exist_ok=True)
-    torch.save(_dora_state(model, find_dora_paths(model)),
-               os.path.join(dora_parameters_path, f"epoch{epoch + 1}_dora_params.pth"))
+    CHECKPOINTS.submit(_dora_state(model, find_dora_paths(model)),
+                       os.path.join(dora_parameters_path, f"epoch{epoch + 1}_dora_params.pth"))
 
 
 def save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=None):
@@ -279,13 +351,14 @@ def save_random_states(optimizer, epoch, random_state_path, dataloader_generator
         ckpt["cuda_rng_state_all"] = torch.cuda.get_rng_state_all()
     os.makedirs(random_state_path, exist_ok=True)
     path = os.path.join(random_state_path, f"epoch{epoch + 1}_random_states.pth")
-    torch.save(ckpt, path)
+    CHECKPOINTS.submit(ckpt, path)
     _log_fn(logger)(f"Random states saved: {path}")
 
 
 def load_random_states(random_state_path, epoch, optimizer=None, dataloader_generator=None, logger=None):
     """NEW:88-134."""
     log = _log_fn(logger)
+    CHECKPOINTS.flush()
     path = os.path.join(random_state_path, f"epoch{epoch}_random_states.pth")
     if not os.path.exists(path):
         log(f"Warning: Random state checkpoint not found: {path}")

@@ -12,7 +12,7 @@ from functions._pipeline_core import (  # noqa: F401  (re-exported reference sur
     BASE_HEADERS, CLIPHBA, DoRALayer, ThingsDataset, ThingsInferenceDataset, append_csv_row,
     apply_dora_to_ViT, build_model, count_trainable_parameters, describe_run, evaluate_model,
     load_clip_to_cpu, make_optimizer, open_logger, save_random_states, seed_everything, select_device,
-    setup_logger, switch_dora_layers, train_one_epoch, enable_trunk_cache, resident_loaders)
+    setup_logger, switch_dora_layers, train_one_epoch, enable_trunk_cache, resident_loaders, CHECKPOINTS)
 from functions._pipeline_core import behavioral_RSA as _behavioral_RSA
 from functions.spose_dimensions import classnames66  # noqa: F401
 from src.models.clip_hba_utils import save_dora_parameters
@@ -66,6 +66,7 @@ def train_model(model, train_loader, test_loader, inference_loader, device, opti
             log(f"Early stopping triggered at epoch {epoch+1}")
             log("*********************************\n\n")
             break
+    CHECKPOINTS.flush()   # (background checkpoint writer, HBA_ASYNC_CKPT=1: every file is on disk on return)
 
 
 def run_behavioral_training(config):

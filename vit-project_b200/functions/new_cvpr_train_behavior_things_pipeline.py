@@ -18,7 +18,7 @@ from functions._pipeline_core import (  # noqa: F401  (re-exported reference sur
     load_dataset_split_indices, load_random_states, make_optimizer, open_logger,
     replace_with_gaussian_noise, save_dora_parameters, save_random_states, seed_everything,
     select_device, setup_logger, shuffle_targets, switch_dora_layers, train_one_epoch,
-    enable_trunk_cache, resident_loaders)
+    enable_trunk_cache, resident_loaders, CHECKPOINTS)
 from functions.spose_dimensions import classnames66  # noqa: F401
 
 
@@ -113,6 +113,7 @@ def train_model(model, train_loader, test_loader, inference_loader, device, opti
             log(f"Early stopping triggered at epoch {epoch+1}")
             log("*********************************\n\n")
             break
+    CHECKPOINTS.flush()   # (background checkpoint writer, HBA_ASYNC_CKPT=1: every file is on disk on return)
 
 
 def run_behavioral_training(config):
@@ -150,6 +151,7 @@ def run_behavioral_training(config):
     model = build_model(config, device, logger)
     training_run = config['training_run']
     resume_from_epoch = config.get('resume_from_epoch', 0)
+    CHECKPOINTS.flush()   # checkpoints of an earlier condition in this process are complete before any is read
     if resume_from_epoch > 0 and config.get('resume_dora_parameters_path'):
         dora_path = os.path.join(config['resume_dora_parameters_path'],
                                  f"epoch{resume_from_epoch}_dora_params.pth")
