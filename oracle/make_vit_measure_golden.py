@@ -37,6 +37,21 @@ def load_reference_scripts():
     return mods["MEAS"], mods["VIT"]
 
 
+def cli_surface(mod):
+    """{flag: {type, default, required, nargs}} read from the `parser.add_argument(...)` calls of the script's AST."""
+    import ast
+    flags = {}
+    for node in ast.walk(ast.parse(open(mod.__file__).read())):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument" and node.args:
+            name = ast.literal_eval(node.args[0])
+            kw = {k.arg: k.value for k in node.keywords}
+            flags[name] = {"type": getattr(kw.get("type"), "id", None),
+                           "default": ast.literal_eval(kw["default"]) if "default" in kw else None,
+                           "required": bool(ast.literal_eval(kw["required"])) if "required" in kw else False,
+                           "nargs": ast.literal_eval(kw["nargs"]) if "nargs" in kw else None}
+    return flags
+
+
 class _Labelled(torch.utils.data.Dataset):
     def __init__(self, labels):
         self.labels = labels
@@ -107,6 +122,8 @@ def main():
     out["default_perturb_epochs"] = json.loads(re.search(r"'--perturb_epochs'.*?default=(\[[^\]]*\])", src, re.S).group(1))
     out["default_perturbation_types"] = json.loads(
         re.search(r"'--perturbation_types'.*?default=(\[[^\]]*\])", src, re.S).group(1).replace("'", '"'))
+    # ---- the two scripts' command lines: every flag with its type, default and required-ness (VIT:247-257, MEAS:562-599)
+    out["cli"] = {"VIT": cli_surface(VIT), "MEAS": cli_surface(MEAS)}
     path = os.path.join(ROOT, "tests", "golden", "vit_measure.json")
     with open(path, "w") as f:
         json.dump(out, f)

@@ -607,3 +607,58 @@ def test_measurement_streams_an_imagefolder_tree(tmp_path, monkeypatch):
     with pytest.raises(ValueError):
         vt.measure_perturbation_effect(1, "label_shuffle", ckdir, csv, None, None, vt.ResidentImageSet(things), rdm,
                                        evaluator=_ScipyEvaluator(rdm), log=None)
+
+
+# ------------------------------------------------------------------------------- command lines of the drop-in scripts
+def _script(rel):
+    import importlib.util
+    path = os.path.join(ROOT, "vit-project_b200", "vit_training", rel)
+    spec = importlib.util.spec_from_file_location("_cli_" + os.path.basename(rel)[:-3], path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("which,rel", [("VIT", "baseline/train_vit_sgd.py"),
+                                       ("MEAS", "single_epoch/measure_single_epoch_perturbation_effect.py")])
+def test_script_command_lines_keep_the_reference_flags(which, rel):
+    """Every flag of the reference script (read from its AST by the golden generator: VIT:247-257, MEAS:562-599)
+    exists here with the same type, default and nargs; flags the reference requires stay required, except the two
+    THINGS paths that `--things_csv synthetic` makes unnecessary.  Extra flags here are optional."""
+    mod = _script(rel)
+    actions = {a.option_strings[0]: a for a in mod.build_parser()._actions if a.option_strings and a.option_strings[0] != "-h"}
+    relaxed = {"--things_img_dir", "--things_rdm_path"}
+    for flag, want in GOLD["cli"][which].items():
+        assert flag in actions, flag
+        a = actions[flag]
+        assert (a.type.__name__ if a.type else None) == want["type"], flag
+        assert a.nargs == want["nargs"], flag
+        if want["default"] is not None:
+            assert a.default == want["default"], flag
+        if flag in relaxed:
+            assert want["required"] and not a.required
+        else:
+            assert a.required == want["required"], flag
+    for flag, a in actions.items():
+        if flag not in GOLD["cli"][which]:
+            assert not a.required, flag
+    # the reference's function names are importable from the scripts
+    names = {"VIT": ("setup_distributed", "get_dataloaders", "save_checkpoint", "train_one_epoch", "validate",
+                     "CosineAnnealingLRWithWarmup", "main"),
+             "MEAS": ("setup_distributed", "get_dataloaders", "GaussianNoiseTransform", "UniformGrayTransform", "ShuffledLabelsDataset", "TargetNoiseDataset",
+                      "THINGSInferenceDataset", "train_one_epoch", "validate", "compute_rsa_score",
+                      "CosineAnnealingLRWithWarmup", "measure_perturbation_effect", "main")}[which]
+    for n in names:
+        assert hasattr(mod, n), n
+
+
+def test_measure_script_get_dataloaders_on_cpu_tensors():
+    mod = _script("single_epoch/measure_single_epoch_perturbation_effect.py")
+    tl, vl, sampler = mod.get_dataloaders("synthetic:10:6:7", 4, 0, 2, 1, perturbation_type="target_noise",
+                                          device=torch.device("cpu"))
+    sampler.set_epoch(2)
+    batches = list(tl)
+    assert [x.shape[0] for x, _ in batches] == [4, 1] and len(vl) == 1 and tl.sampler is sampler
+    want = torch.from_numpy(_vt().random_targets(10, 7, 42))
+    order = torch.tensor(list(sampler))
+    assert torch.equal(torch.cat([y for _, y in batches]), want[order])

@@ -49,6 +49,27 @@ class THINGSInferenceDataset(torch.utils.data.Dataset):
         return name, image
 
 
+def setup_distributed():
+    return vt.setup_distributed()
+
+
+def get_dataloaders(data_path, batch_size, num_workers, world_size, rank, perturbation_type=None, epsilon=0.1,
+                    shuffle_seed=42, device=None):
+    """MEAS:139-227 -> (train_loader, val_loader, train_sampler), the training data perturbed as requested."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    syn = vt.parse_synthetic(data_path)
+    if syn is None:
+        return vt.imagenet_loaders(data_path, batch_size, num_workers, world_size, rank, device,
+                                   perturbation_type=perturbation_type, epsilon=epsilon, shuffle_seed=shuffle_seed)
+    n_train, n_val, classes = syn
+    train = vt.synthetic_imagenet(n_train, classes, seed=0, device=device)
+    val = vt.synthetic_imagenet(n_val, classes, seed=1, device=device)
+    train_loader = vt.ShardedLoader(train, batch_size, world_size, rank, shuffle=True, perturbation_type=perturbation_type,
+                                    epsilon=epsilon, shuffle_seed=shuffle_seed, num_classes=classes)
+    val_loader = vt.ShardedLoader(val, batch_size, world_size, rank, shuffle=False, num_classes=classes)
+    return train_loader, val_loader, train_loader.sampler
+
+
 def load_things(things_csv, things_img_dir, things_rdm_path, device):
     """-> (ResidentImageSet of the RSA images, reference RDM)."""
     if str(things_csv).startswith("synthetic"):
