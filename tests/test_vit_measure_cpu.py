@@ -662,3 +662,44 @@ def test_measure_script_get_dataloaders_on_cpu_tensors():
     want = torch.from_numpy(_vt().random_targets(10, 7, 42))
     order = torch.tensor(list(sampler))
     assert torch.equal(torch.cat([y for _, y in batches]), want[order])
+
+
+# ------------------------------------------------------------------------------- against the reference, executed
+def _exec_arm(arm):
+    import subprocess
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "vit_measure_exec.py"), "--arm", arm],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert p.returncode == 0, p.stderr[-3000:]
+    return json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_host_orchestration_equals_the_reference_executed():
+    """The strongest pin of SURVEY 8a row V / 8f N3: the reference's OWN `get_dataloaders`, `train_one_epoch`,
+    `validate`, `save_checkpoint` (VIT) and `measure_perturbation_effect` (MEAS) are executed on the CPU
+    (oracle/vit_measure_exec.py: only `timm.create_model`, `.cuda()`, `torch.load(map_location)` and the process
+    group are stubbed) on a tiny JPEG tree; the product's host side with a CPU stand-in trainer, on the same files
+    and RNG streams, must reproduce two baseline epochs, the metrics CSV text, and the result rows of all four
+    perturbation types - bit for bit against a live reference run where /root/reference is mounted, and within
+    1e-5 of the committed output of the reference arm (tests/golden/vit_measure_exec.json) anywhere."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vit_measure_exec.json")))
+    assert gold["arm"] == "reference" and sorted(gold["measure"]) == sorted(_vt().PERTURBATION_TYPES)
+    got = _exec_arm("product")
+    assert got["missing_epoch"] is None and gold["missing_epoch"] is None            # MEAS:427-430
+
+    def close(a, b, tol):
+        if isinstance(a, (int, str)) or a is None:
+            return a == b
+        return abs(a - b) <= tol * max(1.0, abs(b))
+
+    for (a, b) in zip(got["baseline"], gold["baseline"]):
+        assert all(close(x, y, 1e-5) for x, y in zip(a, b)), (a, b)
+    for kind, want in gold["measure"].items():
+        assert list(got["measure"][kind]) == list(want) == list(_vt().RESULT_COLUMNS)
+        for k in want:
+            assert close(got["measure"][kind][k], want[k], 1e-5), (kind, k, got["measure"][kind][k], want[k])
+    if os.path.isdir("/root/reference/Training/vit_training"):
+        live = _exec_arm("reference")
+        assert live["baseline"] == got["baseline"]
+        assert live["metrics_csv"] == got["metrics_csv"]
+        assert live["measure"] == got["measure"]                                     # every number identical
