@@ -16,6 +16,11 @@ through one of two arms, and prints the results as one JSON line:
                     by a CPU stand-in of the same interface (torch autograd + torch.optim.SGD) and the libhba RSA
                     tail by NumPy / SciPy.
 
+Each arm also runs the collective tails on a world-size-2 `gloo` group (two spawned ranks; lr 0 so that the
+reference's un-wrapped model copies stay identical without DDP): the reference's `train_one_epoch`, `validate`
+(loss = SUM over ranks of the rank means, VIT:196) and `compute_rsa_score` (rank-strided embeddings concatenated
+rank-major, MEAS:326-334) against `hba.vit_train`'s with `reference_rank_sum=True` / `dataset_order=False`.
+
 Both arms see the same files and the same RNG streams (the model factory re-seeds torch after building the
 model; neither side draws from the global generator between that point and the first DataLoader iterator, so
 the worker seeds - hence the random crops / flips / Gaussian images - coincide), so every number must be
@@ -203,6 +208,69 @@ def run_product(fx):
             "metrics_csv": open(os.path.join(fx["ck"], "training_metrics.csv")).read()}
 
 
+# ------------------------------------------------------------------------------------------------ world size 2
+def _collective_worker(rank, world, port, arm, fx, out_dir):
+    """The collective tails on a world-size-2 `gloo` group: per-epoch training loss
+    (mean over ranks), validation loss (SUM over ranks of the rank means - the reference never divides) and the
+    RSA score of rank-strided, rank-major concatenated embeddings."""
+    import torch.distributed as dist
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(1)
+    sys.stdout = sys.stderr
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = factory()
+    res = {}
+    if arm == "reference":
+        from oracle import make_vit_measure_golden as mk
+        from torch.utils.data import DataLoader, DistributedSampler
+        from torchvision import transforms
+        MEAS, VIT = mk.load_reference_scripts()
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        opt = torch.optim.SGD(model.parameters(), lr=0.0, momentum=0.9, weight_decay=0.0)   # lr 0: ranks stay identical without DDP
+        tl, vl, sampler = VIT.get_dataloaders(fx["data"], BATCH, WORKERS, world, rank)
+        sampler.set_epoch(0)
+        res["train_loss"] = VIT.train_one_epoch(model, tl, opt, VIT.GradScaler(), 0, rank, world)
+        res["val"] = list(VIT.validate(model, vl, rank, world))
+        tf = transforms.Compose([transforms.Resize(256), transforms.CenterCrop(224), transforms.ToTensor(),
+                                 transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        ds = MEAS.THINGSInferenceDataset(fx["things_csv"], fx["things_dir"], fx["rdm"], tf)
+        loader = DataLoader(ds, batch_size=8, sampler=DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=False))
+        res["rsa"] = list(MEAS.compute_rsa_score(model, loader, fx["rdm"], rank, world))      # MEAS:451-464, 298-355
+    else:
+        import importlib.util
+        from hba import vit_train as vt
+        spec = importlib.util.spec_from_file_location("_measure_script", os.path.join(
+            ROOT, "vit-project_b200", "vit_training", "single_epoch", "measure_single_epoch_perturbation_effect.py"))
+        script = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(script)
+        cpu = torch.device("cpu")
+        tr = TorchTrainer(model, lr=0.0, weight_decay=0.0)
+        tl, vl, sampler = vt.imagenet_loaders(fx["data"], BATCH, WORKERS, world, rank, cpu)
+        sampler.set_epoch(0)
+        res["train_loss"] = vt.train_one_epoch(tr, tl, 0, rank, world, log=None)
+        res["val"] = list(vt.validate(tr, vl, rank, world, reference_rank_sum=True))
+        res["val_mean"] = list(vt.validate(tr, vl, rank, world, reference_rank_sum=False))
+        things, rdm = script.load_things(fx["things_csv"], fx["things_dir"], fx["rdm"], cpu)
+        ev = ScipyEvaluator(rdm)
+        loader = vt.ShardedLoader(things, 8, world, rank, with_names=True)
+        res["rsa"] = list(vt.compute_rsa_score(model, loader, rdm, rank, world, dataset_order=False, evaluator=ev))
+        res["rsa_dataset_order"] = list(vt.compute_rsa_score(model, loader, rdm, rank, world, dataset_order=True, evaluator=ev))
+        one = vt.ShardedLoader(things, 8, 1, 0, with_names=True)
+        res["rsa_single_rank"] = list(vt.compute_rsa_score(model, one, rdm, 0, 1, evaluator=ev))
+    with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+        json.dump({k: [plain(x) for x in v] if isinstance(v, list) else plain(v) for k, v in res.items()}, f)
+    dist.destroy_process_group()
+
+
+def run_collectives(arm, fx, root):
+    import torch.multiprocessing as mp
+    out_dir = os.path.join(root, f"coll_{arm}")
+    os.makedirs(out_dir)
+    mp.spawn(_collective_worker, args=(2, 29100 + os.getpid() % 500, arm, fx, out_dir), nprocs=2, join=True)
+    return [json.load(open(os.path.join(out_dir, f"rank{r}.json"))) for r in (0, 1)]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", choices=["reference", "product"], required=True)
@@ -212,6 +280,7 @@ def main():
     torch.set_num_threads(2)
     with tempfile.TemporaryDirectory() as root:
         fx = build_fixture(root)
+        collectives = run_collectives(a.arm, fx, root)   # first: the in-process stubs below must not leak into it
         real_stdout = sys.stdout
         sys.stdout = sys.stderr                     # the reference prints its progress; keep stdout for the JSON line
         try:
@@ -219,6 +288,7 @@ def main():
         finally:
             sys.stdout = real_stdout
     out["arm"] = a.arm
+    out["world2"] = collectives
     print(json.dumps(out))
     if a.write_golden:
         if a.arm != "reference":

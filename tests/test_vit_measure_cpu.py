@@ -698,8 +698,23 @@ def test_host_orchestration_equals_the_reference_executed():
         assert list(got["measure"][kind]) == list(want) == list(_vt().RESULT_COLUMNS)
         for k in want:
             assert close(got["measure"][kind][k], want[k], 1e-5), (kind, k, got["measure"][kind][k], want[k])
+    # world size 2 (`gloo`): the reference's collective tails, quirks included
+    for rank in (0, 1):
+        g, w = got["world2"][rank], gold["world2"][rank]
+        assert close(g["train_loss"], w["train_loss"], 1e-5)
+        assert all(close(x, y, 1e-5) for x, y in zip(g["val"], w["val"]))             # SUM over ranks of the rank means
+        assert close(g["val_mean"][0], w["val"][0] / 2, 1e-5)                          # ... which is twice the mean
+        if rank == 0:
+            assert all(close(x, y, 1e-5) for x, y in zip(g["rsa"], w["rsa"]))         # rank-interleaved rows, as the reference
+            assert g["rsa_dataset_order"] == g["rsa_single_rank"]                     # default here: rows in dataset order
+            assert abs(g["rsa"][0] - g["rsa_single_rank"][0]) > 1e-3                  # the interleave does change rho
+        else:
+            assert g["rsa"] == w["rsa"] == [None, None]                               # MEAS:335-336
     if os.path.isdir("/root/reference/Training/vit_training"):
         live = _exec_arm("reference")
         assert live["baseline"] == got["baseline"]
         assert live["metrics_csv"] == got["metrics_csv"]
         assert live["measure"] == got["measure"]                                     # every number identical
+        for rank in (0, 1):
+            for k in ("train_loss", "val", "rsa"):
+                assert live["world2"][rank][k] == got["world2"][rank][k], (rank, k)
