@@ -665,13 +665,18 @@ def test_measure_script_get_dataloaders_on_cpu_tensors():
 
 
 # ------------------------------------------------------------------------------- against the reference, executed
-def _exec_arm(arm):
+def _start_arm(arm):
     import subprocess
     import sys
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "vit_measure_exec.py"), "--arm", arm],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
-    assert p.returncode == 0, p.stderr[-3000:]
-    return json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    return subprocess.Popen([sys.executable, os.path.join(ROOT, "oracle", "vit_measure_exec.py"), "--arm", arm],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT,
+                            env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+
+
+def _finish_arm(proc):
+    out, err = proc.communicate(timeout=900)
+    assert proc.returncode == 0, err[-3000:]
+    return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
 
 
 def test_host_orchestration_equals_the_reference_executed():
@@ -684,7 +689,9 @@ def test_host_orchestration_equals_the_reference_executed():
     1e-5 of the committed output of the reference arm (tests/golden/vit_measure_exec.json) anywhere."""
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "vit_measure_exec.json")))
     assert gold["arm"] == "reference" and sorted(gold["measure"]) == sorted(_vt().PERTURBATION_TYPES)
-    got = _exec_arm("product")
+    have_reference = os.path.isdir("/root/reference/Training/vit_training")
+    procs = [_start_arm("product")] + ([_start_arm("reference")] if have_reference else [])   # side by side
+    got = _finish_arm(procs[0])
     assert got["missing_epoch"] is None and gold["missing_epoch"] is None            # MEAS:427-430
 
     def close(a, b, tol):
@@ -710,8 +717,8 @@ def test_host_orchestration_equals_the_reference_executed():
             assert abs(g["rsa"][0] - g["rsa_single_rank"][0]) > 1e-3                  # the interleave does change rho
         else:
             assert g["rsa"] == w["rsa"] == [None, None]                               # MEAS:335-336
-    if os.path.isdir("/root/reference/Training/vit_training"):
-        live = _exec_arm("reference")
+    if have_reference:
+        live = _finish_arm(procs[1])
         assert live["baseline"] == got["baseline"]
         assert live["metrics_csv"] == got["metrics_csv"]
         assert live["measure"] == got["measure"]                                     # every number identical
