@@ -270,3 +270,67 @@ def test_chained_length_sweep_on_two_workers(tmp_path):
     assert h["kind"] is None and h["resume_from_epoch"] == 0
     with pytest.raises(ValueError):
         sweep.run_sweep(base, conds, [None], layout="sweep", run_fn=_fake_length_condition, chain=True)
+
+
+# ------------------------------------------------------------------------------- LEN executed
+LEN_PATH = "/root/reference/Training/clip_behavioral_finetuning/length_experiments/clip_train_behavior_lengths.py"
+
+
+def _run_len_main(argv, monkeypatch):
+    """The reference's length-experiment driver, unmodified: `main()` with a command line, its
+    `run_behavioral_training` replaced by a recorder -> the config dict it would train with."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_LEN", LEN_PATH)
+    LEN = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(LEN)          # resolves `functions.cvpr_train_behavior_things_pipeline` to this repo's alias
+    seen = []
+    monkeypatch.setattr(LEN, "run_behavioral_training", lambda cfg: seen.append(dict(cfg)))
+    monkeypatch.setattr(sys, "argv", ["clip_train_behavior_lengths.py"] + argv)
+    LEN.main()
+    return seen[0]
+
+
+@pytest.mark.skipif(not os.path.exists(LEN_PATH), reason="reference not mounted")
+def test_length_resume_decisions_equal_the_reference_driver_executed(tmp_path, monkeypatch):
+    """hba.sweep.condition_config('length') + apply_length_resume against LEN's own `main()` (LEN:85-253) on the
+    same directory states: fresh start, shorter finished neighbour (chain), own CSV present (continue)."""
+    from hba import sweep
+    import functions.cvpr_train_behavior_things_pipeline as alias
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    assert alias.run_behavioral_training is NEW.run_behavioral_training          # LEN:1 resolves here
+    out = str(tmp_path / "out")
+    os.makedirs(out)
+    keys = ("training_run", "perturb_length", "perturb_type", "resume_from_epoch", "output_dir", "checkpoint_path",
+            "training_res_path", "dora_parameters_path", "random_state_path", "previous_training_res_path",
+            "resume_random_state_path", "resume_dora_parameters_path")
+
+    def both(e, length):
+        argv = ["--perturb_epoch", str(e), "--perturb_length", str(length), "--output_dir", f"random_target_e{e}_l{length}",
+                "--baseline_dora_directory", "b/dora", "--baseline_random_state_path", "b/rand",
+                "--baseline_split_indices_path", "b/split.pth", "--output_base_directory", out]
+        ref_cfg = _run_len_main(argv, monkeypatch)
+        cfg = sweep.condition_config({"output_base_directory": out, "perturb_type": "random_target"},
+                                     {"training_run": e, "perturb_length": length}, "length")
+        kind = sweep.apply_length_resume(cfg)
+        return {k: ref_cfg.get(k) for k in keys}, {k: cfg.get(k) for k in keys}, kind
+
+    # (3) nothing on disk: baseline epoch e-1
+    ref_cfg, cfg, kind = both(8, 5)
+    assert kind == "baseline" and cfg == ref_cfg and cfg["resume_from_epoch"] == 7
+    # (2) the window-5 run has finished its window (checkpoint of epoch 7 + 5 present): the window-10 run chains
+    os.makedirs(os.path.join(out, "random_target_e8_l5", "dora_params_8"), exist_ok=True)
+    open(os.path.join(out, "random_target_e8_l5", "dora_params_8", "epoch12_dora_params.pth"), "w").close()
+    os.makedirs(os.path.join(out, "random_target_e80_l2"))                       # e8_ must not match e80_
+    os.makedirs(os.path.join(out, "label_shuffle_e8_l7"))                        # other perturbation type
+    ref_cfg, cfg, kind = both(8, 10)
+    assert kind == "chain" and cfg == ref_cfg and cfg["resume_from_epoch"] == 12
+    # (1) the run's own CSV exists: continue after its last completed epoch
+    with open(os.path.join(out, "random_target_e8_l10", "training_res.csv"), "w") as f:
+        f.write("epoch,train_loss\n13,1.0\n14,0.9\n")
+    ref_cfg, cfg, kind = both(8, 10)
+    assert kind == "existing" and cfg == ref_cfg and cfg["resume_from_epoch"] == 14
+    # deliberate difference: a shorter neighbour WITHOUT its checkpoint (failed / still running) - the reference
+    # chains to it regardless (and would then train from un-restored state); here it is stepped over
+    os.makedirs(os.path.join(out, "random_target_e30_l2"))
+    ref_cfg, cfg, kind = both(30, 5)
+    assert ref_cfg["resume_from_epoch"] == 31 and kind == "baseline" and cfg["resume_from_epoch"] == 29
