@@ -11,7 +11,7 @@ import torch
 from test_gpu_pipeline import _write_things_like_dataset
 from test_gpu_sweep import _gpu_condition
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 def test_chained_length_conditions_equal_independent_ones(tmp_path, monkeypatch):

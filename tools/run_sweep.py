@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--start", type=int, default=1)
     ap.add_argument("--end", type=int, default=98)
     ap.add_argument("--gpus", default="0")
+    ap.add_argument("--workers-per-gpu", type=int, default=1,
+                    help="worker processes per GPU (they time-share it and fill each other's host phases; to be "
+                         "measured with tools/gpu_next_round.sh before changing the default)")
     ap.add_argument("--plan", action="store_true")
     ap.add_argument("--chain", action="store_true",
                     help="grid only: LEN's shorter -> longer resume chain, one start epoch per worker at a time")
@@ -41,7 +44,7 @@ def main():
     a = ap.parse_args()
     from hba import sweep
     conds = sweep.single_epoch_conditions(a.start, a.end) if a.kind == "single" else sweep.length_grid_conditions()
-    devices = [int(x) for x in a.gpus.split(",")]
+    devices = [int(x) for x in a.gpus.split(",") for _ in range(max(1, a.workers_per_gpu))]
     if a.plan and a.chain:
         groups = sweep.chain_groups(conds)
         plan, loads = sweep.lpt_assign(groups, len(devices), cost=sweep.chain_cost)
