@@ -730,3 +730,18 @@ def test_host_orchestration_equals_the_reference_executed():
         for rank in (0, 1):
             for k in ("train_loss", "val", "rsa"):
                 assert live["world2"][rank][k] == got["world2"][rank][k], (rank, k)
+
+
+@pytest.mark.parametrize("n,world", [(48, 2), (48, 8), (12, 5), (7, 3), (5, 1)])
+def test_rank_blocks_return_to_dataset_order_for_any_world_size(n, world):
+    """`DistributedSampler(shuffle=False)` shares (padded by wrapping when W does not divide n) -> dataset order."""
+    from torch.utils.data import DistributedSampler
+    vt = _vt()
+    emb = torch.arange(n, dtype=torch.float32).reshape(n, 1) * torch.ones(1, 3)
+    blocks = [emb[list(DistributedSampler(range(n), num_replicas=world, rank=r, shuffle=False))] for r in range(world)]
+    assert len({b.shape for b in blocks}) == 1
+    assert torch.equal(vt.arrange_rank_blocks(blocks, True, n), emb)
+    ref_order = vt.arrange_rank_blocks(blocks, False, n)                      # MEAS:333-334
+    assert torch.equal(ref_order, torch.cat(blocks)[:n])
+    if world > 1 and n > world:
+        assert not torch.equal(ref_order, emb)

@@ -254,8 +254,16 @@ def gather_embeddings(local, world_size, dataset_order=True, n_total=None):
         d.all_gather(blocks, local.contiguous())
     else:
         blocks = [local]
+    return arrange_rank_blocks(blocks, dataset_order, n_total)
+
+
+def arrange_rank_blocks(blocks, dataset_order=True, n_total=None):
+    """Per-rank blocks [n_local, D] of a `DistributedSampler(shuffle=False)` pass -> one matrix.  Rank r's row j is
+    sample j*W + r of the padded index list (samples wrapped from the start fill the last positions), so
+    interleaving the blocks and keeping the first `n_total` rows restores dataset order exactly, also when W does
+    not divide the number of samples; `dataset_order=False` is the reference's rank-major `torch.cat`."""
     if dataset_order:
-        out = torch.stack(blocks, dim=1).reshape(-1, local.shape[1])     # row j*W + r = blocks[r][j]
+        out = torch.stack(blocks, dim=1).reshape(-1, blocks[0].shape[1])     # row j*W + r = blocks[r][j]
     else:
         out = torch.cat(blocks, dim=0)
     return out if n_total is None else out[:n_total]
