@@ -334,3 +334,42 @@ def test_length_resume_decisions_equal_the_reference_driver_executed(tmp_path, m
     os.makedirs(os.path.join(out, "random_target_e30_l2"))
     ref_cfg, cfg, kind = both(30, 5)
     assert ref_cfg["resume_from_epoch"] == 31 and kind == "baseline" and cfg["resume_from_epoch"] == 29
+
+
+@pytest.mark.skipif(not os.path.exists(LEN_PATH), reason="reference not mounted")
+def test_length_resume_decisions_on_random_directory_states(tmp_path, monkeypatch):
+    """Seeded random trees of finished runs (every run holds all its checkpoints, so the one deliberate
+    difference - stepping over a neighbour without its checkpoint - cannot trigger): the config built here equals
+    the one LEN's own `main()` builds, for every query."""
+    import random as pyrandom
+    from hba import sweep
+    rng = pyrandom.Random(7)
+    keys = ("training_run", "perturb_length", "resume_from_epoch", "training_res_path", "dora_parameters_path",
+            "random_state_path", "previous_training_res_path", "resume_random_state_path", "resume_dora_parameters_path")
+    kinds = []
+    for trial in range(4):
+        out = str(tmp_path / f"tree{trial}")
+        os.makedirs(out)
+        for _ in range(rng.randint(3, 9)):
+            t, e, l = rng.choice(["random_target", "label_shuffle"]), rng.choice([1, 2, 10, 11, 12, 21]), rng.choice([2, 5, 10, 20])
+            d = os.path.join(out, f"{t}_e{e}_l{l}", f"dora_params_{e}")
+            os.makedirs(d, exist_ok=True)
+            for ep in range(max(0, e - 1) + 1, max(0, e - 1) + l + 3):
+                open(os.path.join(d, f"epoch{ep}_dora_params.pth"), "w").close()
+            if rng.random() < 0.3:      # some runs are also resumable in place
+                with open(os.path.join(out, f"{t}_e{e}_l{l}", "training_res.csv"), "w") as f:
+                    f.write("epoch,train_loss\n" + "".join(f"{ep},1.0\n" for ep in range(1, max(0, e - 1) + rng.randint(1, l) + 1)))
+        for _ in range(6):
+            t, e, l = rng.choice(["random_target", "label_shuffle"]), rng.choice([1, 2, 10, 11, 12, 21]), rng.choice([2, 5, 10, 20, 50])
+            argv = ["--perturb_type", t, "--perturb_epoch", str(e), "--perturb_length", str(l), "--output_dir", f"{t}_e{e}_l{l}",
+                    "--baseline_dora_directory", "b/dora", "--baseline_random_state_path", "b/rand",
+                    "--baseline_split_indices_path", "b/split.pth", "--output_base_directory", out]
+            existed = os.path.isdir(os.path.join(out, f"{t}_e{e}_l{l}"))
+            ref_cfg = _run_len_main(argv, monkeypatch)
+            cfg = sweep.condition_config({"output_base_directory": out, "perturb_type": t},
+                                         {"training_run": e, "perturb_length": l}, "length")
+            kinds.append(sweep.apply_length_resume(cfg))
+            assert {k: cfg.get(k) for k in keys} == {k: ref_cfg.get(k) for k in keys}, (trial, t, e, l)
+            if not existed:      # both sides create the queried run's directory: keep the tree to finished runs only
+                __import__("shutil").rmtree(os.path.join(out, f"{t}_e{e}_l{l}"))
+    assert {"baseline", "chain", "existing"} <= set(kinds), kinds      # the random states reached every branch
