@@ -226,3 +226,45 @@ def test_fig2_tables_from_the_reference_tree_directly(tmp_path):
     assert len(pd.read_csv(out)) == 28
     shipped = open(os.path.join(data, "vit_results", "perturbation_summary_table.csv")).read()
     assert analysis.vit_perturbation_summary(os.path.join(data, "vit_results", "perturbation_effects.csv")).to_csv(index=False) == shipped
+
+
+# ------------------------------------------------------------------------------- the notebooks, executed
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Figures"), reason="reference not mounted")
+def test_analysis_layer_equals_the_notebooks_executed():
+    """The reference's figure notebooks (fig2 / fig3 / fig4) are executed cell by cell on the reference's own Data/
+    tree (oracle/run_notebook.py: plotting libraries mocked, nothing else touched); the tables they compute are
+    compared with the analysis layer's directory-level entry points: all 136 length-grid runs, all 98
+    single-epoch runs, 4 x 7 perturbation-type deltas."""
+    from oracle import run_notebook as rn
+    data = "/root/reference/Data/clip_results"
+    base_csv = os.path.join(data, "baseline_clip_results_seed1.csv")
+    # fig2 (cells 3-7)
+    ns = rn.run_cells("fig2", stop_after=7)
+    t = analysis.perturbation_type_summary(base_csv, data)
+    for name, loss_var, ba_var in (("image_noise", "in_dev", "in_ba"), ("blank_image", "bi_dev", "bi_ba"),
+                                   ("label_shuffle", "ls_dev", "ls_ba"), ("target_noise", "tn_dev", "tn_ba")):
+        sub = t[t["perturbation"] == name]
+        assert list(sub["epoch"]) == list(ns["target_epochs"])
+        assert np.array_equal(sub["delta_test_loss"].to_numpy(), np.array(ns[loss_var], dtype=np.float64), equal_nan=True)
+        assert np.array_equal(sub["delta_behavioral_rsa_rho"].to_numpy(), np.array(ns[ba_var], dtype=np.float64), equal_nan=True)
+    # fig3 (cells 4-10)
+    ns = rn.run_cells("fig3", stop_after=10)
+    s = analysis.single_sweep_summary(base_csv, os.path.join(data, "single_sweep_experiments"))
+    want_loss = dict(zip(ns["run_numbers_deviation"], ns["perturbation_deviations"]))
+    want_ba = dict(zip(ns["run_numbers_deviation_ba"], ns["perturbation_deviations_ba"]))
+    assert len(want_loss) == 98 and sorted(want_loss) == list(s["run"])
+    assert [want_loss[r] for r in s["run"]] == list(s["delta_test_loss"])
+    assert [want_ba[r] for r in s["run"]] == list(s["delta_behavioral_rsa_rho"])
+    # fig4 (cells 4-12)
+    ns = rn.run_cells("fig4", stop_after=12)
+    g = analysis.length_grid_summary(base_csv, os.path.join(data, "perturb_length_experiments_baselineseed1_perturbseed0"))
+    want = {r["run_name"]: r for r in ns["recovery_data"]}
+    assert len(want) == 136 and sorted(want) == sorted(g["run_name"])
+    for row in g.to_dict("records"):
+        w = want[row["run_name"]]
+        assert (row["start_epoch"], row["length"], row["perturbation_end"]) == (w["start_epoch"], w["length"], w["perturbation_end"])
+        assert bool(row["recovered"]) == bool(w["recovered"])
+        if w["recovered"]:
+            assert int(row["recovery_epoch"]) == w["recovery_epoch"] and int(row["epochs_to_recovery"]) == w["epochs_to_recovery"]
+        else:
+            assert pd.isna(row["recovery_epoch"]) and pd.isna(row["epochs_to_recovery"])
