@@ -373,3 +373,45 @@ def test_length_resume_decisions_on_random_directory_states(tmp_path, monkeypatc
             if not existed:      # both sides create the queried run's directory: keep the tree to finished runs only
                 __import__("shutil").rmtree(os.path.join(out, f"{t}_e{e}_l{l}"))
     assert {"baseline", "chain", "existing"} <= set(kinds), kinds      # the random states reached every branch
+
+
+# ------------------------------------------------------------------------------- SWEEP executed
+SWEEP_PATH = "/root/reference/Training/clip_behavioral_finetuning/uniform_sweep/clip_train_behavior_sweep.py"
+
+
+@pytest.mark.skipif(not os.path.exists(SWEEP_PATH), reason="reference not mounted")
+def test_single_epoch_layout_equals_the_reference_sweep_driver_executed(monkeypatch):
+    """SWEEP's own `main()` (SWEEP:111-237) with a recording `run_behavioral_training`: per-condition paths, resume
+    epoch and loop behaviour (a failing run is counted and the loop goes on) against `condition_config('sweep')` /
+    `run_sweep`.  The driver hard-codes an output tree under /home: directory creation and its log file are
+    intercepted, nothing is written outside the test."""
+    import importlib.util
+    import logging
+    from hba import sweep
+    spec = importlib.util.spec_from_file_location("_ref_SWEEP", SWEEP_PATH)
+    SWEEP = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(SWEEP)
+    seen, made = [], []
+
+    def record(cfg):
+        seen.append(dict(cfg))
+        if cfg["training_run"] == 25:
+            raise RuntimeError("run 25 fails")                    # SWEEP:215-223: logged, counted, loop continues
+
+    monkeypatch.setattr(SWEEP, "run_behavioral_training", record)
+    monkeypatch.setattr(os, "makedirs", lambda p, *a, **k: made.append(p))
+    monkeypatch.setattr(logging, "FileHandler", lambda *a, **k: logging.NullHandler())
+    SWEEP.main()
+    assert [c["training_run"] for c in seen] == [15, 25, 35, 70]   # the shipped training_order; all four attempted
+    keys = ("training_run", "resume_from_epoch", "checkpoint_path", "training_res_path", "dora_parameters_path",
+            "random_state_path", "perturb_length", "perturb_type", "perturb_seed", "output_base_directory")
+    base = {k: v for k, v in seen[0].items() if k not in ("training_run", "resume_from_epoch", "checkpoint_path",
+                                                           "training_res_path", "dora_parameters_path", "random_state_path")}
+    for ref_cfg in seen:
+        cfg = sweep.condition_config(base, {"training_run": ref_cfg["training_run"], "perturb_length": 1}, "sweep")
+        assert {k: cfg[k] for k in keys} == {k: ref_cfg[k] for k in keys}
+        assert os.path.join(base["output_base_directory"], f"training_run{ref_cfg['training_run']}") in made
+    assert all(p.startswith(base["output_base_directory"]) for p in made)
+    # the midpoint order helper the driver ships covers every epoch once (SWEEP:8-60); run_sweep orders by cost instead
+    order = SWEEP.generate_midpoint_order(1, 98)
+    assert sorted(order) == list(range(1, 99)) == [c["training_run"] for c in sweep.single_epoch_conditions(1, 98)]
