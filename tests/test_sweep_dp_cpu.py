@@ -415,3 +415,67 @@ def test_single_epoch_layout_equals_the_reference_sweep_driver_executed(monkeypa
     # the midpoint order helper the driver ships covers every epoch once (SWEEP:8-60); run_sweep orders by cost instead
     order = SWEEP.generate_midpoint_order(1, 98)
     assert sorted(order) == list(range(1, 99)) == [c["training_run"] for c in sweep.single_epoch_conditions(1, 98)]
+
+
+# ------------------------------------------------------------------------------- config contract of the drivers
+BDRV_PATH = "/root/reference/Training/clip_behavioral_finetuning/baseline/clip_train_behavior_baseline.py"
+
+
+def _required_config_keys(*modules):
+    """Keys read as `config['k']` (no default) anywhere in the given modules' source."""
+    import ast
+    import inspect
+    keys, guarded = set(), set()
+    for mod in modules:
+        for node in ast.walk(ast.parse(inspect.getsource(mod))):
+            if (isinstance(node, ast.Subscript) and isinstance(node.value, ast.Name) and node.value.id in ("config", "cfg")
+                    and isinstance(node.slice, ast.Constant) and isinstance(node.slice.value, str)
+                    and isinstance(node.ctx, ast.Load)):
+                keys.add(node.slice.value)
+            if (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "get"
+                    and isinstance(node.func.value, ast.Name) and node.func.value.id in ("config", "cfg")
+                    and node.args and isinstance(node.args[0], ast.Constant)):
+                guarded.add(node.args[0].value)      # `if config.get('k'): ... config['k']` is an optional key
+    return keys - guarded
+
+
+@pytest.mark.skipif(not os.path.exists(BDRV_PATH), reason="reference not mounted")
+def test_pipelines_require_only_keys_the_reference_drivers_provide(tmp_path, monkeypatch):
+    """Drop-in contract of the config dict (SURVEY 5 'Config / flags'): every key the drop-in pipelines read
+    without a default is in the dict the reference's own drivers build (BDRV / SWEEP / LEN `main()` executed with a
+    recording `run_behavioral_training`); keys this repo adds (`hba_*`) are optional."""
+    import importlib.util
+    import logging
+    import functions._pipeline_core as core
+    import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+
+    def driver_config(path, argv=None):
+        spec = importlib.util.spec_from_file_location("_ref_driver", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        seen = []
+        monkeypatch.setattr(mod, "run_behavioral_training", lambda cfg: seen.append(dict(cfg)))
+        monkeypatch.setattr(sys, "argv", [os.path.basename(path)] + (argv or []))
+        mod.main()
+        return seen[0]
+
+    bdrv = driver_config(BDRV_PATH)
+    len_cfg = driver_config(LEN_PATH, ["--perturb_epoch", "3", "--perturb_length", "2", "--output_dir", "random_target_e3_l2",
+                                       "--baseline_dora_directory", "b", "--baseline_random_state_path", "r",
+                                       "--baseline_split_indices_path", "s", "--output_base_directory", str(tmp_path)])
+    with monkeypatch.context() as m:
+        m.setattr(os, "makedirs", lambda p, *a, **k: None)
+        m.setattr(logging, "FileHandler", lambda *a, **k: logging.NullHandler())
+        sweep_cfg = driver_config(SWEEP_PATH)
+    base_needs = _required_config_keys(BASE)
+    new_needs = _required_config_keys(NEW)
+    shared_needs = _required_config_keys(core)
+    assert base_needs and new_needs
+    # (shared helpers also serve the perturbation pipeline: keys only its drivers provide are not needed by BDRV runs)
+    base_missing = (base_needs | shared_needs) - set(bdrv)
+    assert base_missing <= {k for k in shared_needs if k in sweep_cfg}, sorted(base_missing)
+    for name, cfg in (("SWEEP", sweep_cfg), ("LEN", len_cfg)):
+        missing = (new_needs | shared_needs) - set(cfg)
+        assert not missing, (name, sorted(missing))
+    assert not any(k.startswith("hba_") for k in base_needs | new_needs | shared_needs)      # our additions are .get() only
