@@ -1,0 +1,68 @@
+"""CPU tests of the HBM-resident input store (hba.data) - device-agnostic host logic: the resident
+loader visits the items exactly like the reference's `DataLoader(dataset, batch_size, shuffle, generator=...)`
+(NEW:1119-1126) and consumes the shuffle generator identically, so that the generator state saved / restored per
+epoch (NEW:129-131, 709-727) stays interchangeable."""
+import pytest
+import torch
+from torch.utils.data import DataLoader, Dataset, Subset
+
+
+class _Things(Dataset):
+    """(name, image, target) items like ThingsDataset (NEW:196-204)."""
+
+    def __init__(self, n):
+        g = torch.Generator().manual_seed(n)
+        self.images = torch.randn(n, 3, 4, 4, generator=g)
+        self.targets = torch.randn(n, 66, generator=g)
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        return f"img_{i:03d}.jpg", self.images[i], self.targets[i]
+
+
+@pytest.mark.parametrize("shuffle", [True, False])
+def test_resident_loader_equals_dataloader_order_and_generator_consumption(shuffle):
+    from hba import data
+    ds = _Things(23)
+    store = data.ResidentStore(ds, "cpu")
+    assert len(store) == 23 and store.images.dtype == torch.float32 and store.names[5] == "img_005.jpg"
+    g_ref, g_mine = torch.Generator().manual_seed(11), torch.Generator().manual_seed(11)
+    ref = DataLoader(ds, batch_size=4, shuffle=shuffle, generator=g_ref)
+    mine = data.ResidentLoader(store, 4, shuffle=shuffle, generator=g_mine)
+    assert len(mine) == len(ref) == 6
+    for epoch in range(3):
+        got, want = list(mine), list(ref)
+        assert len(got) == len(want)
+        for (gn, gi, gt), (wn, wi, wt) in zip(got, want):
+            assert list(gn) == list(wn) and torch.equal(gi, wi) and torch.equal(gt, wt)
+        assert torch.equal(g_mine.get_state(), g_ref.get_state())          # same consumption, epoch after epoch
+        if epoch == 0:       # restoring a saved generator state (NEW:129-131) replays the same epoch on both sides
+            saved = g_ref.get_state().clone()
+    g_ref.set_state(saved)
+    g_mine.set_state(saved)
+    assert [list(b[0]) for b in mine] == [list(b[0]) for b in ref]
+
+
+def test_resident_loader_subset_ids_and_inference_items():
+    from hba import data
+    ds = _Things(12)
+    store = data.ResidentStore(ds, "cpu")
+    subset = [7, 2, 9, 4, 0]
+    g_ref, g_mine = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+    ref = DataLoader(Subset(ds, subset), batch_size=2, shuffle=True, generator=g_ref)   # SubsetWithIndices, NEW:164-177
+    mine = data.ResidentLoader(store, 2, shuffle=True, generator=g_mine, index_map=subset)
+    it = iter(mine)
+    for wn, wi, wt in ref:
+        gn, gi, gt = next(it)
+        assert list(gn) == list(wn) and torch.equal(gi, wi) and torch.equal(gt, wt)
+        assert mine.last_ids == [data.image_id(n) for n in gn] == mine.last_ids_dev.tolist()
+    assert list(it) == [] and mine.last_ids is None
+    assert data.image_id("img_007.jpg") == data.image_id("img_007.jpg") != data.image_id("img_008.jpg")
+    # (name, image) items - ThingsInferenceDataset, NEW:206-224 - give two-element batches
+    pairs = [(f"v{i}.jpg", torch.full((3, 2, 2), float(i))) for i in range(5)]
+    inf = data.ResidentLoader(data.ResidentStore(pairs, "cpu"), 4)
+    batches = list(inf)
+    assert [len(b) for b in batches] == [2, 2] and list(batches[1][0]) == ["v4.jpg"] and batches[0][1].shape == (4, 3, 2, 2)
+    assert list(data.ResidentLoader(data.ResidentStore(ds, "cpu"), 4, index_map=[])) == []
