@@ -1,4 +1,5 @@
-"""CPU tests of the HBM-resident input store (hba.data) - device-agnostic host logic: the resident
+"""CPU tests of host-side pieces without a device dependency: the Spearman p-value (hba.rsa), and the HBM-resident
+input store (hba.data) - device-agnostic host logic: the resident
 loader visits the items exactly like the reference's `DataLoader(dataset, batch_size, shuffle, generator=...)`
 (NEW:1119-1126) and consumes the shuffle generator identically, so that the generator state saved / restored per
 epoch (NEW:129-131, 709-727) stays interchangeable."""
@@ -66,3 +67,25 @@ def test_resident_loader_subset_ids_and_inference_items():
     batches = list(inf)
     assert [len(b) for b in batches] == [2, 2] and list(batches[1][0]) == ["v4.jpg"] and batches[0][1].shape == (4, 3, 2, 2)
     assert list(data.ResidentLoader(data.ResidentStore(ds, "cpu"), 4, index_map=[])) == []
+
+
+@pytest.mark.parametrize("n", [3, 10, 66, 1128, 1_717_731])
+def test_spearman_pvalue_equals_scipy(n):
+    """hba.rsa.spearman_pvalue (the one scalar of the RSA tail evaluated on the host, NEW:652 / MEAS:351) against the
+    p-value `scipy.stats.spearmanr` attaches to the same rho, incl. rho = +-1 and tiny samples."""
+    import numpy as np
+    from scipy import stats
+    from hba.rsa import spearman_pvalue
+    rng = np.random.default_rng(n)
+    m = min(n, 5000)                                    # scipy on a sample of the same size class; rho is what matters
+    for _ in range(5):
+        a = rng.standard_normal(m)
+        b = a * rng.uniform(-1, 1) + rng.standard_normal(m) * rng.uniform(0.01, 2)
+        rho, p = stats.spearmanr(a, b)
+        assert spearman_pvalue(float(rho), m) == pytest.approx(float(p), rel=1e-10, abs=1e-300)
+    assert spearman_pvalue(1.0, n) == 0.0 and spearman_pvalue(-1.0, n) == 0.0      # t = +-inf
+    rho1, p1 = stats.spearmanr(np.arange(m), np.arange(m))          # scipy's rho of identical rankings: 1 - 1 ulp
+    if m > 3:
+        assert spearman_pvalue(float(rho1), m) == pytest.approx(float(p1), rel=1e-6, abs=1e-300)
+    assert spearman_pvalue(0.0, n) == pytest.approx(1.0)
+    assert np.isnan(spearman_pvalue(0.5, 2))            # dof = 0: scipy returns nan as well
