@@ -89,3 +89,38 @@ def test_spearman_pvalue_equals_scipy(n):
         assert spearman_pvalue(float(rho1), m) == pytest.approx(float(p1), rel=1e-6, abs=1e-300)
     assert spearman_pvalue(0.0, n) == pytest.approx(1.0)
     assert np.isnan(spearman_pvalue(0.5, 2))            # dof = 0: scipy returns nan as well
+
+
+@pytest.mark.parametrize("shape,r", [((96, 80), 16), ((64, 64), 8), ((128, 256), 32)])
+def test_product_dora_layer_construction_equals_oracle_and_reference(shape, r):
+    """hba.DoRALayer.__init__ runs on the host (the merge is the device part): decomposition S = ||W0^T||_col,
+    D = W0^T / S, Kaiming-uniform A then B on the global RNG, frozen bias, attribute names and state_dict keys
+    (NEW:407-445) - bit for bit against the oracle restatement and, where mounted, the reference's own class."""
+    import hba
+    from oracle import dora_ref, ref_loader
+    in_f, out_f = shape
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(in_f, out_f)
+    torch.manual_seed(4)
+    mine = hba.DoRALayer(lin, r=r)
+    rng_after = torch.get_rng_state()
+    torch.manual_seed(4)
+    want = dora_ref.DoRALayerRef(lin, r=r)
+    assert torch.equal(torch.get_rng_state(), rng_after)                      # same consumption of the global RNG
+    for n in ("m", "D", "delta_D_A", "delta_D_B", "bias"):
+        assert torch.equal(getattr(mine, n), getattr(want, n)), n
+    assert mine.scaling == want.scaling and mine.original_layer is lin
+    assert sorted(k for k in mine.state_dict() if not k.startswith("original_layer")) == \
+        sorted(k for k in want.state_dict() if not k.startswith("original_layer"))
+    assert [n for n, p in mine.named_parameters() if p.requires_grad and not n.startswith("original_layer")] == \
+        [n for n, p in want.named_parameters() if p.requires_grad and not n.startswith("original_layer")]
+    assert (mine.in_features, mine.out_features) == (in_f, out_f) if hasattr(mine, "in_features") else True
+    if ref_loader.reference_available():
+        NEW, BASE = ref_loader.load_reference()
+        for cls in (NEW.DoRALayer, BASE.DoRALayer):
+            torch.manual_seed(4)
+            ref = cls(lin, r=r)
+            for n in ("m", "D", "delta_D_A", "delta_D_B", "bias"):
+                assert torch.equal(getattr(mine, n), getattr(ref, n)), n
+            assert sorted(mine.state_dict()) == sorted(ref.state_dict())
+            assert {n: p.requires_grad for n, p in mine.named_parameters()} == {n: p.requires_grad for n, p in ref.named_parameters()}
