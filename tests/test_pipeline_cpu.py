@@ -164,3 +164,44 @@ def test_background_checkpoint_writer(tmp_path, monkeypatch):
     with pytest.raises(RuntimeError, match="background checkpoint write failed"):
         core.CHECKPOINTS.flush()
     core.CHECKPOINTS.flush()
+
+
+def test_model_construction_and_dora_surgery_match_reference_golden_on_the_host(tmp_path, monkeypatch):
+    """The host part of SURVEY 8a rows A / D / P (everything before the first forward): `CLIPHBA(...)` over the
+    plug-in clip module, `apply_dora_to_ViT`, `switch_dora_layers`, `count_trainable_parameters`, and the
+    per-epoch DoRA checkpoint keys - against the golden the reference's own code wrote (tests/golden/
+    tiny_clip_forward.pt, tiny_training.pt): trainable count, DoRA initial values bit for bit (same consumption of the
+    global RNG), parameter names and on-disk keys."""
+    from oracle import clip_ref
+    from oracle.synth import PROMPTS
+    from src.models.CLIPs.clip_hba import clip
+    path = tmp_path / "ViT-tiny-14.pt"
+    torch.save(clip_ref.synthetic_state_dict("ViT-tiny/14", seed=1), path)
+    monkeypatch.setattr(clip, "_download", lambda url, root: str(path))
+    g = torch.load(os.path.join(GOLD, "tiny_clip_forward.pt"), weights_only=False)
+    gt = torch.load(os.path.join(GOLD, "tiny_training.pt"), weights_only=False)
+    for mod in (NEW, BASE):
+        model = mod.CLIPHBA(PROMPTS, backbone_name="ViT-tiny/14", pos_embedding=True)
+        assert not any(isinstance(m, NEW.DoRALayer) for m in model.modules())
+        torch.manual_seed(123)
+        mod.apply_dora_to_ViT(model, n_vision_layers=2, n_transformer_layers=1, r=8, dora_dropout=0.1)
+        mod.switch_dora_layers(model, freeze_all=True, dora_state=True)
+        assert NEW.count_trainable_parameters(model) == g["n_trainable"]
+        trainable = {n: p for n, p in model.named_parameters() if p.requires_grad}
+        assert sorted(trainable) == sorted(g["dora_init"])
+        for n, p in trainable.items():
+            assert torch.equal(p.detach(), g["dora_init"][n]), n
+        mod.switch_dora_layers(model, freeze_all=True, dora_state=False)
+        assert NEW.count_trainable_parameters(model) == 0
+        mod.switch_dora_layers(model, freeze_all=True, dora_state=True)
+    core.save_dora_parameters(model, str(tmp_path / "dora"), 2)
+    saved = torch.load(tmp_path / "dora" / "epoch3_dora_params.pth")
+    assert sorted(saved) == sorted(gt["dora_epoch3"]) == sorted(g["dora_init"])          # NEW:657-693 keys
+    assert all(not t.is_cuda and t.shape == gt["dora_epoch3"][k].shape for k, t in saved.items())
+    fresh = NEW.CLIPHBA(PROMPTS, backbone_name="ViT-tiny/14", pos_embedding=True)
+    torch.manual_seed(5)
+    NEW.apply_dora_to_ViT(fresh, n_vision_layers=2, n_transformer_layers=1, r=8, dora_dropout=0.1)
+    missing, unexpected = fresh.load_state_dict(gt["dora_epoch3"], strict=False)      # NEW:1167-1168
+    assert not unexpected
+    for k, t in gt["dora_epoch3"].items():
+        assert torch.equal(dict(fresh.named_parameters())[k].detach(), t)
