@@ -124,3 +124,40 @@ def test_product_dora_layer_construction_equals_oracle_and_reference(shape, r):
                 assert torch.equal(getattr(mine, n), getattr(ref, n)), n
             assert sorted(mine.state_dict()) == sorted(ref.state_dict())
             assert {n: p.requires_grad for n, p in mine.named_parameters()} == {n: p.requires_grad for n, p in ref.named_parameters()}
+
+
+def test_trunk_cache_bookkeeping_on_the_host():
+    """hba.engine.TrunkCache (frozen-trunk activation cache, north star item 2) - the host-side bookkeeping with a
+    stand-in engine: miss -> store -> hit returns the stored rows in request order, partial presence is a miss,
+    a changed weight stamp / precision / device drops every entry, ids outside the capacity are refused."""
+    import types
+    from hba.engine import TrunkCache
+    bufs = {}
+
+    def _buf(name, shape, dtype=torch.float32):
+        return bufs.setdefault((name, tuple(shape)), torch.empty(*shape, dtype=dtype))
+
+    eng = types.SimpleNamespace(vis=types.SimpleNamespace(T=5, d=4), precision="bf16", _stamp=1,
+                                device=torch.device("cpu"), _buf=_buf)
+    cache = TrunkCache(capacity=16)
+    ctx = cache.lookup(eng, [3, 7])
+    assert ctx["hit"] is False and "x" not in ctx and not cache.all_present([3])
+    g = torch.Generator().manual_seed(0)
+    x, a = torch.randn(2 * 5, 4, generator=g), torch.randn(2 * 5, 4, generator=g)
+    cache.store(ctx["ids"], x, a)
+    assert cache.all_present([7, 3]) and not cache.all_present([3, 8])
+    hit = cache.lookup(eng, [7, 3])                                   # request order, not insertion order
+    assert hit["hit"] and torch.equal(hit["x"], torch.cat([x[5:], x[:5]])) and torch.equal(hit["a"], torch.cat([a[5:], a[:5]]))
+    assert hit["x"].shape == (10, 4)
+    dev = cache.lookup_device_ids(eng, torch.tensor([3, 3, 7]))
+    assert dev["hit"] and dev["ids"] is None and torch.equal(dev["x"][:5], x[:5]) and torch.equal(dev["x"][10:], x[5:])
+    assert cache.lookup(eng, [3, 8])["hit"] is False                  # one absent image: the whole batch recomputes
+    with pytest.raises(RuntimeError, match="capacity"):
+        cache.lookup(eng, [16])
+    with pytest.raises(RuntimeError, match="capacity"):
+        cache.lookup(eng, [-1])
+    eng._stamp = 2                                                    # weights restaged (e.g. another checkpoint loaded)
+    assert cache.lookup(eng, [3, 7])["hit"] is False and not cache.all_present([3])
+    cache.store(cache.lookup(eng, [3, 7])["ids"], x, a)
+    eng.precision = "fp32"                                            # precision mode changed
+    assert cache.lookup(eng, [3, 7])["hit"] is False
