@@ -11,6 +11,7 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(900)      # worker pools / spawned ranks / torchrun: a hang must fail, not stall the suite
 
 
 # ------------------------------------------------------------------------------- sweep scheduler

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "vit_measure.json")))
+pytestmark = pytest.mark.timeout(900)      # DataLoader workers / spawned ranks: a hang must fail, not stall the suite
 
 
 def _vt():
