@@ -77,3 +77,13 @@ for v in 0 1; do
   HBA_ASYNC_CKPT=$v timeout 300 python bench.py --sweep-only > gpurun_out/sweep_async${v}.json 2> gpurun_out/sweep_async${v}.err
   echo "HBA_ASYNC_CKPT=$v: $(grep -o '"sec_per_epoch_cached": [0-9.]*' gpurun_out/sweep_async${v}.json)"
 done
+#   6. where the two weakest HBM-roofline fractions come from: launch list of the kernel benchmark (radix passes of the
+#      RSA-at-scale ranking, LayerNorm forward), then one full capture of the single-CTA scan and of LayerNorm.
+CMD="python tools/bench_kernels.py --reps 5"
+timeout 300 $CMD > gpurun_out/kernels_r02.json 2> gpurun_out/kernels_r02.err; echo "bench_kernels rc=$?"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_kernels_r02.csv \
+    $CMD > gpurun_out/ncu_kernels_list.log 2>&1; echo "ncu launch list rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:radix_scan_kernel -c 2 -o gpurun_out/radix_scan_r02 -f \
+    $CMD > gpurun_out/ncu_radix_scan.log 2>&1; echo "ncu radix_scan rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm_fwd_kernel -c 2 -o gpurun_out/layernorm_fwd_r02 -f \
+    $CMD > gpurun_out/ncu_layernorm.log 2>&1; echo "ncu layernorm rc=$?"
