@@ -1,5 +1,6 @@
 # First gpurun call of the next round (nothing below has run on a B200 yet; written after round 1's GPU budget
-# was spent).  Usage:  gpurun --timeout 1500 -- 'bash tools/gpu_next_round.sh'
+# was spent).  Usage:  gpurun --timeout 3600 -- 'bash tools/gpu_next_round.sh'   (typically ~35 min of box time; every
+# step has its own timeout - comment out sections 4-6 for a quick first call)
 #   1. the new GPU tests on their own (ViT measurement path, chained sweep), so that a failure there does not hide
 #      behind the -x of the full suite;
 #   2. compute-sanitizer memcheck + racecheck over the kernel unit tests of the HBM-bound ops (graphs off,
