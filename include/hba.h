@@ -191,6 +191,28 @@ int hba_cos_head_fwd(const float* img, const float* txt, int32_t B, int32_t C, i
 int hba_cos_head_bwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E,
                      const float* logit_scale, const float* d_pred, const float* pred,
                      const float* target, float* d_img, float* d_txt, void* stream);
+/* The same head with nn.MSELoss(reduction='mean') (BDRV:31; applied NEW:994 / NEW:597) and the loop's
+ * per-batch bookkeeping (NEW:989-1004) fused into ONE launch, for `groups` independent problems
+ * (lock-stepped sweep conditions; groups = 1 for a single run).  Group g owns img [B,E], txt [C,E],
+ * pred [B,C] (contiguous per group) and target + g * target_group_stride (stride 0 = shared targets).
+ *   loss[g]       = mean((pred - target)^2)
+ *   bad_step[g]   = loss not finite   (the isnan(pred) / isnan(target) / isnan|isinf(loss) `continue`s
+ *                   of NEW:932-935, 989-998: any of them makes the loss non-finite)        (optional)
+ *   bad_total[g] += bad_step[g]                                                            (optional)
+ *   total[g]     += loss * B, skipped for a bad batch when bad_step is given (NEW:1003-1004; evaluate_model
+ *                   NEW:599-601 passes bad_step = NULL)                                     (optional)
+ * workspace: groups * (B + 1) floats, zero before the first use (the kernel leaves it ready for the next).
+ * target == NULL: plain forward (loss / bad_* / total / workspace must be NULL).
+ * hba_cos_mse_bwd: d_img / d_txt of the fused loss, dL/dpred = 2 (pred - target) / (B C) * d_loss[g]
+ * (d_loss optional device array of `groups` upstream gradients; 1 when NULL). */
+int hba_cos_mse_fwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E, int32_t groups,
+                    const float* logit_scale, float* pred, const float* target,
+                    int64_t target_group_stride, float* loss, int32_t* bad_step, int32_t* bad_total,
+                    double* total, float* workspace, void* stream);
+int hba_cos_mse_bwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E, int32_t groups,
+                    const float* logit_scale, const float* pred, const float* target,
+                    int64_t target_group_stride, const float* d_loss, float* d_img, float* d_txt,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimisers. Multi-tensor, one launch.  AdamW(model.parameters(), lr) of NEW:1181 (betas

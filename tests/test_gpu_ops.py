@@ -331,6 +331,65 @@ def test_cos_head_fwd_bwd():
     assert rel_err(dt, txt.grad) < 2e-4
 
 
+@pytest.mark.parametrize("B,Cc,E,G,shared", [(32, 66, 768, 1, False), (4, 66, 768, 3, False), (32, 66, 768, 4, True),
+                                             (7, 5, 128, 2, False), (20, 9, 1024, 2, False)])
+def test_cos_mse_fused_single_launch(B, Cc, E, G, shared):
+    """hba_cos_mse_fwd / _bwd: logits + nn.MSELoss + non-finite flag + running sums in one launch per direction,
+    for G independent groups (lock-stepped conditions) with per-group or shared targets; upstream d_loss."""
+    hba, ops, ref = _imports()
+    g = torch.Generator().manual_seed(B + Cc + G)
+    img = torch.randn(G, B, E, generator=g, dtype=torch.float64).requires_grad_(True)
+    txt = torch.randn(G, Cc, E, generator=g, dtype=torch.float64).requires_grad_(True)
+    ls = torch.tensor(math.log(100.0), dtype=torch.float64)
+    tgt = torch.randn(1 if shared else G, B, Cc, generator=g, dtype=torch.float64) * 9.5 + 5.75
+    up = torch.rand(G, generator=g, dtype=torch.float64) + 0.5
+    losses = []
+    for k in range(G):
+        pred = ref.cos_logits(img[k], txt[k], ls)
+        losses.append(torch.nn.functional.mse_loss(pred, tgt[0 if shared else k]))
+    (torch.stack(losses) * up).sum().backward()
+    f = lambda t: t.detach().float().to(DEV).contiguous()
+    imgd, txtd, tgtd = f(img).view(G * B, E), f(txt).view(G * Cc, E), f(tgt)
+    lsd = ls.float().reshape(1).to(DEV)
+    p = torch.empty(G * B, Cc, device=DEV)
+    loss = torch.empty(G, device=DEV)
+    bad_step = torch.full((G,), 7, dtype=torch.int32, device=DEV)
+    bad_total = torch.zeros(G, dtype=torch.int32, device=DEV)
+    total = torch.zeros(G, dtype=torch.float64, device=DEV)
+    ws = torch.zeros(G * (B + 1), device=DEV)
+    stride = 0 if shared else B * Cc
+    for rep in range(3):   # the workspace is left ready for the next launch
+        ops.cos_mse_fwd(imgd, txtd, lsd, p, B=B, groups=G, target=tgtd, target_group_stride=stride, loss=loss,
+                        bad_step=bad_step, bad_total=bad_total, total=total, workspace=ws)
+    torch.cuda.synchronize()
+    want = torch.stack(losses).detach()
+    assert rel_err(loss, want) < 1e-5
+    assert bad_step.tolist() == [0] * G and bad_total.tolist() == [0] * G
+    assert rel_err(total, 3 * B * want) < 1e-5
+    first = loss.clone()
+    ops.cos_mse_fwd(imgd, txtd, lsd, p, B=B, groups=G, target=tgtd, target_group_stride=stride, loss=loss,
+                    bad_step=bad_step, bad_total=bad_total, total=total, workspace=ws)
+    assert torch.equal(loss, first)                       # fixed-order reduction: run-to-run identical
+    di, dt = torch.empty(G * B, E, device=DEV), torch.empty(G * Cc, E, device=DEV)
+    ops.cos_mse_bwd(imgd, txtd, lsd, p, tgtd, di, dt, B=B, groups=G, target_group_stride=stride, d_loss=f(up))
+    assert rel_err(di.view(G, B, E), img.grad) < 2e-4
+    assert rel_err(dt.view(G, Cc, E), txt.grad) < 2e-4
+    # a non-finite target in the last group: flagged, counted, not accumulated; the other groups unaffected
+    if not shared:
+        before = total.clone()
+        tgtd[G - 1, 0, 0] = float("nan")
+        ops.cos_mse_fwd(imgd, txtd, lsd, p, B=B, groups=G, target=tgtd, target_group_stride=stride, loss=loss,
+                        bad_step=bad_step, bad_total=bad_total, total=total, workspace=ws)
+        assert bad_step.tolist() == [0] * (G - 1) + [1] and bad_total.tolist() == [0] * (G - 1) + [1]
+        assert float(total[G - 1]) == float(before[G - 1])
+        if G > 1:
+            assert rel_err(total[:G - 1] - before[:G - 1], B * want[:G - 1]) < 1e-5
+        # evaluate_model's form (no flag): accumulated unconditionally
+        ops.cos_mse_fwd(imgd, txtd, lsd, p, B=B, groups=G, target=tgtd, target_group_stride=stride, loss=loss,
+                        total=total, workspace=ws)
+        assert math.isnan(float(total[G - 1]))
+
+
 def test_softmax_ce():
     hba, ops, ref = _imports()
     g = torch.Generator().manual_seed(8)

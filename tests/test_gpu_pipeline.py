@@ -343,3 +343,60 @@ def test_captured_step_graphs_are_bit_identical_to_eager_steps(tiny_checkpoint, 
     steps_g = [float(v["step"]) for v in g[2]["optimizer_state_dict"]["state"].values()]
     steps_e = [float(v["step"]) for v in e[2]["optimizer_state_dict"]["state"].values()]
     assert steps_g == steps_e and steps_g[0] == 7 * 5   # 17 train images / batch 4 -> 5 steps per epoch, 7 epochs
+
+
+def test_fused_mse_step_equals_the_criterion_called_step(tiny_checkpoint, monkeypatch):
+    """nn.MSELoss fused into the head kernel (hba_cos_mse_fwd / _bwd: loss, NaN guard, loss bookkeeping, head
+    backward from (pred, target)) against the same step with the caller's criterion run by torch
+    (HBA_FUSED_MSE=0): losses within 1e-6 relative (different fp32 summation order of the 5 x 3 squared errors),
+    DoRA parameters within 1e-5 after 6 steps; a NaN target batch is skipped and counted in both forms;
+    evaluate_model returns the same mean."""
+    import hba
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    from functions import _pipeline_core as core
+    from oracle.synth import synthetic_problem
+    prob = synthetic_problem()
+    hba.set_precision("fp32")
+    try:
+        x = prob["train_images"][:6].to(DEV)
+        y = prob["train_targets"][:6].to(DEV)
+        ybad = y[:3].clone()
+        ybad[1, 2] = float("nan")
+        crit = torch.nn.MSELoss()
+        results = []
+        for fused in ("1", "0"):
+            monkeypatch.setenv("HBA_FUSED_MSE", fused)
+            monkeypatch.setenv("HBA_STEP_GRAPH", "1")
+            model = build_model(NEW).to(DEV)
+            opt = core.make_optimizer(model, 3e-3)
+            step = core.TrainStep(model, opt, crit, DEV)
+            step.start_epoch()
+            losses = []
+            for i in range(6):          # eager warm-up, capture, replays
+                step(x[3 * (i % 2):3 * (i % 2) + 3], y[3 * (i % 2):3 * (i % 2) + 3])
+                losses.append(float(step.last_loss))
+            before = [p.detach().clone() for p in model.parameters() if p.requires_grad]
+            step(x[:3], ybad)
+            assert int(step.guard.total) == 1
+            for a, b in zip(before, [p for p in model.parameters() if p.requires_grad]):
+                assert torch.equal(a, b.detach())            # the optimiser skipped the bad batch
+            total = float(step.total)
+
+            class _L:   # minimal loader: (names, images, targets) batches
+                dataset = list(range(6))
+
+                def __iter__(self):
+                    return iter([(None, x[:3], y[:3]), (None, x[3:], y[3:])])
+
+                def __len__(self):
+                    return 2
+            ev = core.evaluate_model(model, _L(), DEV, crit)
+            results.append((losses, before, total, ev))
+        (l1, p1, t1, e1), (l0, p0, t0, e0) = results
+        assert l1 == pytest.approx(l0, rel=1e-6)
+        assert t1 == pytest.approx(t0, rel=1e-6) and t1 == pytest.approx(3 * sum(l1), rel=1e-6)
+        assert e1 == pytest.approx(e0, rel=1e-6)
+        for a, b in zip(p1, p0):
+            assert rel_err(a, b) < 1e-5
+    finally:
+        hba.set_precision("bf16")

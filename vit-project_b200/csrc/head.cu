@@ -22,16 +22,33 @@ __device__ __forceinline__ float row_sumsq_warp(const float* __restrict__ row, i
   return warp_sum(s);
 }
 
-// grid = B; pred[b, c] = exp(ls) * <img_b, txt_c> / (|img_b| |txt_c|); one warp per class row
+// grid = (B, G): group g (one lock-stepped sweep condition) owns img [B, E], txt [C, E], pred [B, C].
+// pred[b, c] = exp(ls) * <img_b, txt_c> / (|img_b| |txt_c|); one warp per class row.
+// With `target` the same launch produces nn.MSELoss(reduction='mean') (BDRV:31, applied NEW:994 / NEW:597)
+// and the bookkeeping the reference's loop does on the host around it (NEW:989-1004): every CTA leaves its
+// row's squared error in `ws`, the last CTA to finish sums the B partials in a fixed order (deterministic),
+// and writes loss, the non-finite flag (a NaN / Inf anywhere in pred or target makes the loss non-finite,
+// so the three checks of NEW:932-935, 989-998 collapse into this one), the count of skipped batches and the
+// running sum of loss * batch.
 __global__ void __launch_bounds__(kHeadThreads)
-    cos_head_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, int C, int E,
-                        const float* __restrict__ logit_scale, float* __restrict__ pred) {
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* x = img + (size_t)b * E;
+    cos_mse_fwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, int B, int C, int E,
+                       const float* __restrict__ logit_scale, float* __restrict__ pred,
+                       const float* __restrict__ target, int64_t target_gstride, float* __restrict__ loss,
+                       int* __restrict__ bad_step, int* __restrict__ bad_total, double* __restrict__ total,
+                       float* __restrict__ ws) {
+  __shared__ float sErr[kHeadThreads / 32];
+  __shared__ int sLast;
+  const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* x = img + ((size_t)g * B + b) * E;
+  const float* tg = txt + (size_t)g * C * E;
+  float* prow = pred + ((size_t)g * B + b) * C;
+  const float* trow = target ? target + (size_t)g * target_gstride + (size_t)b * C : nullptr;
   const float nx = sqrtf(row_sumsq_warp(x, E, lane));
   const float s = expf(*logit_scale);
+  float err = 0.f;
   for (int c = warp; c < C; c += kHeadThreads / 32) {
-    const float* y = txt + (size_t)c * E;
+    const float* y = tg + (size_t)c * E;
     float dot = 0.f, sq = 0.f;
     for (int e = lane * 4; e < E; e += 128) {
       const float4 a = *reinterpret_cast<const float4*>(x + e);
@@ -41,11 +58,47 @@ __global__ void __launch_bounds__(kHeadThreads)
     }
     dot = warp_sum(dot);
     sq = warp_sum(sq);
-    if (lane == 0) pred[(size_t)b * C + c] = s * (dot / nx / sqrtf(sq));
+    const float p = s * (dot / nx / sqrtf(sq));
+    if (lane == 0) {
+      prow[c] = p;
+      if (trow) {
+        const float d = p - trow[c];
+        err += d * d;
+      }
+    }
+  }
+  if (!target) return;
+  if (lane == 0) sErr[warp] = err;
+  __syncthreads();
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ws) + g;
+  float* part = ws + G + (size_t)g * B;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kHeadThreads / 32; ++w) t += sErr[w];
+    part[b] = t;
+    __threadfence();
+    sLast = (atomicAdd(counter, 1u) == (unsigned int)(B - 1));
+  }
+  __syncthreads();
+  if (sLast && warp == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = lane; i < B; i += 32) t += *reinterpret_cast<volatile float*>(part + i);
+    t = warp_sum(t);
+    if (lane == 0) {
+      const float l = t / (float)((size_t)B * C);
+      loss[g] = l;
+      const int bad = isfinite(l) ? 0 : 1;
+      if (bad_step) bad_step[g] = bad;
+      if (bad_total) bad_total[g] += bad;
+      if (total && !(bad && bad_step)) total[g] += (double)l * (double)B;
+      *counter = 0u;   // ready for the next launch (stream-ordered reuse of the workspace)
+    }
   }
 }
 
-// single CTA, deterministic: loss = mean((pred - target)^2)
+// single CTA, deterministic: loss = mean((pred - target)^2)  (the two-launch form behind hba_cos_head_fwd)
 __global__ void __launch_bounds__(256)
     mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int n,
                float* __restrict__ loss) {
@@ -62,6 +115,9 @@ __global__ void __launch_bounds__(256)
 // One CTA per row of X (own side).  g_x = (d_u - u <u, d_u>) / |x| with u = x/|x| and
 // d_u = s * sum_o dpred(own, o) * y_o / |y_o|.
 // dpred(own, o) = dp[own * s_own + o * s_oth]  (or the fused MSE gradient when dp == nullptr)
+// PER = ceil(E / kHeadThreads): elements of the row per thread (compile-time: the accumulators stay in
+// registers; the 8-wide generic form spilled)
+template <int PER>
 __device__ __forceinline__ void cos_head_bwd_side(const float* __restrict__ X,
                                                   const float* __restrict__ Y, int n_other, int E,
                                                   float s, const float* __restrict__ dp,
@@ -81,20 +137,21 @@ __device__ __forceinline__ void cos_head_bwd_side(const float* __restrict__ X,
   }
   __syncthreads();
   const float* x = X + (size_t)own * E;
-  float acc[kHeadMaxPer], xv[kHeadMaxPer];
+  float acc[PER], xv[PER];
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < kHeadMaxPer; ++k) {
+  for (int k = 0; k < PER; ++k) {
     const int e = threadIdx.x + kHeadThreads * k;
     acc[k] = 0.f;
     xv[k] = (e < E) ? x[e] : 0.f;
     sq += xv[k] * xv[k];
   }
+#pragma unroll 2
   for (int o = 0; o < n_other; ++o) {
     const float cf = sCoef[o];
     const float* y = Y + (size_t)o * E;
 #pragma unroll
-    for (int k = 0; k < kHeadMaxPer; ++k) {
+    for (int k = 0; k < PER; ++k) {
       const int e = threadIdx.x + kHeadThreads * k;
       if (e < E) acc[k] += cf * y[e];
     }
@@ -102,37 +159,46 @@ __device__ __forceinline__ void cos_head_bwd_side(const float* __restrict__ X,
   const float nx = sqrtf(block_sum(sq, scratch));
   float dot = 0.f;
 #pragma unroll
-  for (int k = 0; k < kHeadMaxPer; ++k) {
+  for (int k = 0; k < PER; ++k) {
     acc[k] *= s;
     xv[k] /= nx;
     dot += xv[k] * acc[k];
   }
   dot = block_sum(dot, scratch);
 #pragma unroll
-  for (int k = 0; k < kHeadMaxPer; ++k) {
+  for (int k = 0; k < PER; ++k) {
     const int e = threadIdx.x + kHeadThreads * k;
     if (e < E) gX[(size_t)own * E + e] = (acc[k] - xv[k] * dot) / nx;
   }
 }
 
+// grid = (B + C, G); group g owns img [B, E], txt [C, E], d_pred / pred [B, C], target (+ g * target_gstride),
+// d_loss[g] (optional upstream gradient of the fused loss; 1 when absent)
+template <int PER>
 __global__ void __launch_bounds__(kHeadThreads)
     cos_head_bwd_kernel(const float* __restrict__ img, const float* __restrict__ txt, int B, int C,
                         int E, const float* __restrict__ logit_scale,
                         const float* __restrict__ d_pred, const float* __restrict__ pred,
-                        const float* __restrict__ target, float* __restrict__ d_img,
+                        const float* __restrict__ target, int64_t target_gstride,
+                        const float* __restrict__ d_loss, float* __restrict__ d_img,
                         float* __restrict__ d_txt) {
   __shared__ float sCoef[kHeadMaxOther];
   __shared__ float scratch[32];
+  const int g = blockIdx.y;
+  img += (size_t)g * B * E, txt += (size_t)g * C * E;
+  if (d_pred) d_pred += (size_t)g * B * C;
+  if (pred) pred += (size_t)g * B * C;
+  if (target) target += (size_t)g * target_gstride;
   const float s = expf(*logit_scale);
-  const float mse_coef = 2.0f / (float)(B * C);
+  const float mse_coef = 2.0f / (float)(B * C) * (d_loss ? d_loss[g] : 1.0f);
   if ((int)blockIdx.x < B) {
     if (d_img)
-      cos_head_bwd_side(img, txt, C, E, s, d_pred, pred, target, mse_coef, blockIdx.x, C, 1, d_img,
-                        sCoef, scratch);
+      cos_head_bwd_side<PER>(img, txt, C, E, s, d_pred, pred, target, mse_coef, blockIdx.x, C, 1,
+                             d_img + (size_t)g * B * E, sCoef, scratch);
   } else {
     if (d_txt)
-      cos_head_bwd_side(txt, img, B, E, s, d_pred, pred, target, mse_coef, blockIdx.x - B, 1, C,
-                        d_txt, sCoef, scratch);
+      cos_head_bwd_side<PER>(txt, img, B, E, s, d_pred, pred, target, mse_coef, blockIdx.x - B, 1, C,
+                             d_txt + (size_t)g * C * E, sCoef, scratch);
   }
 }
 
@@ -193,20 +259,54 @@ __global__ void __launch_bounds__(256)
 
 using namespace hba;
 
+extern "C" int hba_cos_mse_fwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E,
+                               int32_t groups, const float* logit_scale, float* pred, const float* target,
+                               int64_t target_group_stride, float* loss, int32_t* bad_step,
+                               int32_t* bad_total, double* total, float* workspace, void* stream) {
+  HBA_REQUIRE(img && txt && logit_scale && pred && B > 0 && C > 0 && groups > 0, "hba_cos_mse_fwd: bad arguments");
+  HBA_REQUIRE(E > 0 && E % 4 == 0, "hba_cos_mse_fwd: E=%d must be a multiple of 4", E);
+  HBA_REQUIRE(groups <= 65535, "hba_cos_mse_fwd: too many groups");
+  if (target) HBA_REQUIRE(loss && workspace, "hba_cos_mse_fwd: target given without loss / workspace");
+  else HBA_REQUIRE(!loss && !bad_step && !bad_total && !total, "hba_cos_mse_fwd: loss outputs requested without target");
+  cos_mse_fwd_kernel<<<dim3(B, groups), kHeadThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, txt, B, C, E, logit_scale, pred, target, target_group_stride, loss, bad_step, bad_total, total,
+      workspace);
+  return check_launch("cos_mse_fwd_kernel");
+}
+
 extern "C" int hba_cos_head_fwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E,
                                 const float* logit_scale, float* pred, const float* target,
                                 float* loss, void* stream) {
   HBA_REQUIRE(img && txt && logit_scale && pred && B > 0 && C > 0, "hba_cos_head_fwd: bad arguments");
   HBA_REQUIRE(E > 0 && E % 4 == 0, "hba_cos_head_fwd: E=%d must be a multiple of 4", E);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cos_head_fwd_kernel<<<B, kHeadThreads, 0, s>>>(img, txt, C, E, logit_scale, pred);
-  HBA_CHECK(check_launch("cos_head_fwd_kernel"));
+  cos_mse_fwd_kernel<<<dim3(B, 1), kHeadThreads, 0, s>>>(img, txt, B, C, E, logit_scale, pred, nullptr, 0,
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
+  HBA_CHECK(check_launch("cos_mse_fwd_kernel"));
   if (loss) {
     HBA_REQUIRE(target != nullptr, "hba_cos_head_fwd: loss requested without target");
     mse_kernel<<<1, 256, 0, s>>>(pred, target, B * C, loss);
     HBA_CHECK(check_launch("mse_kernel"));
   }
   return HBA_OK;
+}
+
+static int launch_cos_head_bwd(const float* img, const float* txt, int B, int C, int E, int groups,
+                               const float* logit_scale, const float* d_pred, const float* pred,
+                               const float* target, int64_t target_gstride, const float* d_loss,
+                               float* d_img, float* d_txt, cudaStream_t s) {
+  const dim3 grid(B + C, groups);
+  const int per = (E + kHeadThreads - 1) / kHeadThreads;
+#define HBA_HEAD_BWD(P)                                                                                     \
+  cos_head_bwd_kernel<P><<<grid, kHeadThreads, 0, s>>>(img, txt, B, C, E, logit_scale, d_pred, pred, target, \
+                                                       target_gstride, d_loss, d_img, d_txt)
+  if (per <= 1) HBA_HEAD_BWD(1);
+  else if (per <= 2) HBA_HEAD_BWD(2);
+  else if (per <= 3) HBA_HEAD_BWD(3);
+  else if (per <= 4) HBA_HEAD_BWD(4);
+  else HBA_HEAD_BWD(kHeadMaxPer);
+#undef HBA_HEAD_BWD
+  return check_launch("cos_head_bwd_kernel");
 }
 
 extern "C" int hba_cos_head_bwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E,
@@ -216,9 +316,21 @@ extern "C" int hba_cos_head_bwd(const float* img, const float* txt, int32_t B, i
   HBA_REQUIRE(d_pred || (pred && target), "hba_cos_head_bwd: need d_pred or (pred, target)");
   HBA_REQUIRE(E % 4 == 0 && E <= kHeadThreads * kHeadMaxPer, "hba_cos_head_bwd: E=%d unsupported", E);
   HBA_REQUIRE(B <= kHeadMaxOther && C <= kHeadMaxOther, "hba_cos_head_bwd: B, C must be <= %d", kHeadMaxOther);
-  cos_head_bwd_kernel<<<B + C, kHeadThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      img, txt, B, C, E, logit_scale, d_pred, pred, target, d_img, d_txt);
-  return check_launch("cos_head_bwd_kernel");
+  return launch_cos_head_bwd(img, txt, B, C, E, 1, logit_scale, d_pred, pred, target, 0, nullptr, d_img, d_txt,
+                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hba_cos_mse_bwd(const float* img, const float* txt, int32_t B, int32_t C, int32_t E,
+                               int32_t groups, const float* logit_scale, const float* pred,
+                               const float* target, int64_t target_group_stride, const float* d_loss,
+                               float* d_img, float* d_txt, void* stream) {
+  HBA_REQUIRE(img && txt && logit_scale && pred && target && (d_img || d_txt) && B > 0 && C > 0 && groups > 0,
+              "hba_cos_mse_bwd: bad arguments");
+  HBA_REQUIRE(E % 4 == 0 && E <= kHeadThreads * kHeadMaxPer, "hba_cos_mse_bwd: E=%d unsupported", E);
+  HBA_REQUIRE(B <= kHeadMaxOther && C <= kHeadMaxOther && groups <= 65535,
+              "hba_cos_mse_bwd: B, C must be <= %d", kHeadMaxOther);
+  return launch_cos_head_bwd(img, txt, B, C, E, groups, logit_scale, nullptr, pred, target, target_group_stride,
+                             d_loss, d_img, d_txt, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int hba_softmax_ce_fwd_bwd(const float* logits, int64_t ld, const int64_t* labels,

@@ -33,7 +33,7 @@ from tqdm import tqdm
 
 from hba import DoRALayer, ops, rsa
 from hba.data import ResidentLoader, ResidentStore
-from hba.engine import TrunkCache
+from hba.engine import LossRequest, TrunkCache
 from hba.optim import FusedAdamW
 from src.models.CLIPs.clip_hba import clip
 
@@ -427,6 +427,23 @@ def _announce_ids(model, loader, allowed=True):
         eng.batch_ids = getattr(loader, "last_ids", None) if allowed else None
 
 
+def fused_mse_ok(model, criterion, targets):
+    """nn.MSELoss(reduction='mean') on [batch, prompts] fp32 targets (BDRV:31, NEW:994 / NEW:597) is computed
+    by the head kernel itself (hba_cos_mse_fwd / _bwd); any other criterion runs as the caller wrote it."""
+    return (type(criterion) is nn.MSELoss and criterion.reduction == "mean" and _engine_of(model) is not None
+            and os.environ.get("HBA_FUSED_MSE", "1") != "0" and torch.is_tensor(targets) and targets.is_cuda
+            and targets.dtype == torch.float32 and targets.ndim == 2
+            and targets.shape[1] == _n_prompts(model))
+
+
+def _n_prompts(model):
+    m = _unwrap(model)
+    n = getattr(m, "num_clip", None)
+    if n is None and torch.is_tensor(getattr(m, "tokenized_prompts", None)):
+        n = m.tokenized_prompts.shape[0]
+    return -1 if n is None else int(n)
+
+
 class _CachedForwardGraphs:
     """CUDA graphs of the no-grad forward on trunk-cached images (evaluation / RSA batches), one per
     batch size; see TrainStep.  __call__ returns a fresh tensor (a copy of the graph's static
@@ -451,30 +468,45 @@ class _CachedForwardGraphs:
                 and getattr(loader, "last_ids_dev", None) is not None and not torch.is_grad_enabled()
                 and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids))
 
-    def __call__(self, images, ids_dev):
+    def loss_total(self):
+        """float64 device scalar that the fused-MSE evaluation batches accumulate loss * batch into."""
+        t = self.__dict__.get("_loss_total")
+        if t is None or t.device != self.eng.device:
+            t = self.__dict__["_loss_total"] = torch.zeros((), device=self.eng.device, dtype=torch.float64)
+        return t
+
+    def __call__(self, images, ids_dev, targets=None):
+        """targets given: nn.MSELoss is fused into the head kernel and loss * batch is added to loss_total()."""
         eng = self.eng
-        key = (tuple(images.shape), eng._stamp, eng.precision)
+        key = (tuple(images.shape), eng._stamp, eng.precision, targets is not None)
         if key not in self.warm:
             self.warm.add(key)
             eng.batch_ids = ids_dev
+            if targets is not None:
+                eng.loss_request = LossRequest(targets.contiguous(), total=self.loss_total())
             return self.model(images)
         entry = self.entries.get(key)
         if entry is None:
             s_img, s_ids = torch.zeros_like(images), ids_dev.clone()
+            s_tgt = targets.clone().contiguous() if targets is not None else None
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             c0 = ops.COUNTERS["launches"]
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 eng.batch_ids = s_ids
+                if s_tgt is not None:
+                    eng.loss_request = LossRequest(s_tgt, total=self.loss_total())
                 out = self.model(s_img)
-            entry = (graph, s_ids, out, ops.COUNTERS["launches"] - c0)
+            entry = (graph, s_ids, s_tgt, out, ops.COUNTERS["launches"] - c0)
             ops.COUNTERS["launches"] = c0
             self.entries[key] = entry
-        graph, s_ids, out, n_launch = entry
+        graph, s_ids, s_tgt, out, n_launch = entry
         s_ids.copy_(ids_dev, non_blocking=True)
+        if s_tgt is not None:
+            s_tgt.copy_(targets, non_blocking=True)
         graph.replay()
         ops.COUNTERS["launches"] += n_launch
-        return out.clone()
+        return out.clone() if targets is None else out
 
 
 # ------------------------------------------------------------------------------- evaluation
@@ -482,12 +514,25 @@ def evaluate_model(model, data_loader, device, criterion):
     """NEW:584-602: sample-weighted mean loss; accumulated on the device, one read at the end."""
     model.eval()
     total = torch.zeros((), device=device, dtype=torch.float64)
+    fwd = _CachedForwardGraphs.of(model)
+    eng = fwd.eng
     with torch.no_grad():
         for _, images, targets in tqdm(data_loader, total=len(data_loader), desc="Evaluating",
                                        file=sys.stderr):
             images = images.to(device, non_blocking=True)
             targets = targets.to(device, non_blocking=True)
-            fwd = _CachedForwardGraphs.of(model)
+            if fused_mse_ok(model, criterion, targets):
+                # MSE and the loss * batch accumulation run inside the head kernel (one launch)
+                if fwd.loss_total() is not total:
+                    total = fwd.loss_total()
+                    total.zero_()
+                if fwd.usable(data_loader):
+                    fwd(images, data_loader.last_ids_dev, targets)
+                else:
+                    _announce_ids(model, data_loader)
+                    eng.loss_request = LossRequest(targets.contiguous(), total=total)
+                    model(images)
+                continue
             if fwd.usable(data_loader):
                 predictions = fwd(images, data_loader.last_ids_dev)
             else:
@@ -664,6 +709,19 @@ class TrainStep:
         self.opt.zero_grad()
         if self.eng is not None:
             self.eng.batch_ids = ids
+        if self.fused and fused_mse_ok(self.model, self.crit, targets) and targets.shape[0] == images.shape[0]:
+            # nn.MSELoss, the NaN / Inf guard and the loss bookkeeping are part of the head kernel; the head
+            # backward reads (pred, target) directly - no eager loss kernels in the step
+            eng = self.eng
+            eng.loss_request = LossRequest(targets.contiguous(), self.guard.step, self.guard.total, self.total)
+            self.model(images)
+            loss = eng.loss_out
+            if loss is None:
+                raise RuntimeError("libhba: the forward pass did not consume the fused-loss request")
+            loss.backward()
+            self.opt.step(skip_flag=self.guard.step)
+            self.last_loss.copy_(loss.detach())
+            return
         predictions = self.model(images)
         loss = self.crit(predictions, targets)
         bad = self.guard.check(predictions, loss.reshape(1), targets)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "hba_dora_merge_bwd": (i32, [vp, i64, vp, vp, vp, vp, i32, i32, i32, f32, f32, vp, vp, vp, vp, vp]),
     "hba_cos_head_fwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "hba_cos_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "hba_cos_mse_fwd": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]),
+    "hba_cos_mse_bwd": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, vp, vp]),
     "hba_adamw_multi": (i32, [vp, vp, i32, i64, f32, f32, f32, f32, f32, i64, vp, vp, vp]),
     "hba_sgd_multi": (i32, [vp, vp, i32, i64, f32, f32, f32, i32, vp, vp]),
     "hba_sgd_staged": (i32, [vp, vp, i32, i64, f32, f32, f32, i32, vp, vp]),

@@ -58,6 +58,17 @@ class _Tower:
     __slots__ = ("blocks", "d", "heads", "T", "causal")
 
 
+class LossRequest:
+    """Asks the next forward pass to fuse nn.MSELoss(reduction='mean') (BDRV:31, applied NEW:994 / NEW:597) and
+    the loop's per-batch bookkeeping into the head kernel (hba_cos_mse_fwd): `target` [B, S] fp32; optional
+    device scalars `bad_step` (int32, non-finite loss -> the optimiser skips the update, NEW:989-998),
+    `bad_total` (int32 running count) and `total` (float64 running sum of loss * batch, NEW:1003-1004)."""
+    __slots__ = ("target", "bad_step", "bad_total", "total")
+
+    def __init__(self, target, bad_step=None, bad_total=None, total=None):
+        self.target, self.bad_step, self.bad_total, self.total = target, bad_step, bad_total, total
+
+
 class Engine:
     def __init__(self, model):
         self.model = model
@@ -68,6 +79,8 @@ class Engine:
         self.cache_text = True
         self.trunk_cache = None   # TrunkCache: frozen-trunk activations per image id (exact reuse)
         self.batch_ids = None     # image ids of the next forward batch (consumed by run_forward)
+        self.loss_request = None  # LossRequest of the next forward batch (consumed by run_forward)
+        self.loss_out = None      # the fused loss of the last forward that carried a LossRequest
         self._text_cache = None
         self._gen = 0
         self.launches = 0  # kernels launched by the last run_forward / run_backward (our own count)
@@ -482,6 +495,13 @@ class Engine:
         B = images.shape[0]
         L = len(self.vis.blocks)
         ids, self.batch_ids = self.batch_ids, None
+        req, self.loss_request = self.loss_request, None
+        if req is not None:
+            t = req.target
+            if (t.dtype != torch.float32 or not t.is_contiguous() or t.device != images.device
+                    or t.ndim != 2 or t.shape[0] != B or t.shape[1] != tokens.shape[0]):
+                raise RuntimeError("libhba: fused MSE needs contiguous fp32 targets of shape [batch, prompts] "
+                                   "on the model's device")
         cache_ctx = None
         native = images.shape[2] == self.res and images.shape[3] == self.res
         if self.trunk_cache is not None and ids is not None and L >= 2 and native:
@@ -513,10 +533,18 @@ class Engine:
         else:
             main.wait_stream(side)   # join: the cosine head needs both towers
         pred = torch.empty(B, txt_feat.shape[0], device=self.device)
-        ops.cos_head_fwd(img_feat, txt_feat, self.logit_scale, pred)
+        loss = None
+        if req is None:
+            ops.cos_head_fwd(img_feat, txt_feat, self.logit_scale, pred)
+        else:
+            loss = torch.empty((), device=self.device)
+            ops.cos_mse_fwd(img_feat, txt_feat, self.logit_scale, pred, B=B, target=req.target, loss=loss,
+                            bad_step=req.bad_step, bad_total=req.bad_total, total=req.total,
+                            workspace=self._buf("head.ws", (B + 1,), zero=True))
         self.launches += 1
         self._gen += 1
-        return pred, {"v": sv, "t": st, "img_feat": img_feat, "txt_feat": txt_feat, "gen": self._gen}
+        return pred, {"v": sv, "t": st, "img_feat": img_feat, "txt_feat": txt_feat, "gen": self._gen,
+                      "loss": loss, "pred": pred.detach(), "target": req.target if req is not None else None}
 
     # ---------------------------------------------------------------- backward
     def _grad_operand(self, name, g, rows, cols, transpose=False, k_pad=None):
@@ -554,8 +582,10 @@ class Engine:
         self.launches += 2 if s > 1 else 1
         return dW
 
-    def run_backward(self, saved, d_pred):
-        """-> dict {('v', block_index) | ('t', block_index): dL/dW [out, in] fp32}."""
+    def run_backward(self, saved, d_pred, d_loss=None):
+        """-> dict {('v', block_index) | ('t', block_index): dL/dW [out, in] fp32}.
+        d_loss: upstream gradient of the fused loss (LossRequest); with d_pred None the head backward reads
+        (pred, target) directly (hba_cos_mse_bwd) and no dL/dpred tensor is ever formed."""
         if saved["gen"] != self._gen:
             raise RuntimeError("libhba: backward called after a newer forward pass overwrote the "
                                "saved activations (call backward before the next forward)")
@@ -565,8 +595,14 @@ class Engine:
         B, S, E = img_feat.shape[0], txt_feat.shape[0], self.E
         d_img = self._buf("b.dimg", (B, E))
         d_txt = self._buf("b.dtxt", (S, E))
-        ops.cos_head_bwd(img_feat, txt_feat, self.logit_scale, d_img, d_txt,
-                         d_pred=d_pred.contiguous().float())
+        if d_loss is not None and d_pred is None:
+            ops.cos_mse_bwd(img_feat, txt_feat, self.logit_scale, saved["pred"], saved["target"], d_img, d_txt,
+                            B=B, d_loss=d_loss.reshape(1).float())
+        else:
+            if d_loss is not None:   # both outputs were used downstream: fold the loss gradient into dL/dpred
+                d_pred = d_pred + (2.0 / saved["pred"].numel()) * d_loss * (saved["pred"] - saved["target"])
+            ops.cos_head_bwd(img_feat, txt_feat, self.logit_scale, d_img, d_txt,
+                             d_pred=d_pred.contiguous().float())
         self.launches += 1
         # ------------------------------------------------ text: last block, EOT rows
         st = saved["t"]
@@ -706,11 +742,16 @@ class _ClipForward(torch.autograd.Function):
             raise RuntimeError("libhba: gradients w.r.t. the input images are not supported")
         pred, saved = engine.run_forward(images, tokens, pos_embedding, v_ad, t_ad, need_grad)
         ctx.engine, ctx.saved, ctx.keys = engine, saved, keys
-        return pred
+        ctx.set_materialize_grads(False)
+        if saved["loss"] is None:
+            return pred
+        return pred, saved["loss"]
 
     @staticmethod
-    def backward(ctx, d_pred):
-        grads = ctx.engine.run_backward(ctx.saved, d_pred)
+    def backward(ctx, d_pred, d_loss=None):
+        if d_pred is None and d_loss is None:
+            return (None,) * (5 + 2 * len(ctx.keys))
+        grads = ctx.engine.run_backward(ctx.saved, d_pred, d_loss)
         out = []
         for i, k in enumerate(ctx.keys):
             g = grads.get(k)
@@ -734,10 +775,15 @@ def clip_forward(model, image, text, pos_embedding=False):
                 keys.append((side, i))
                 weights.append(op.weight)   # DoRALayer.weight property: merged W [out, in]
                 biases.append(op.bias)
+    eng.loss_out = None
     if torch.is_grad_enabled() and any(w.requires_grad for w in weights):
-        return _ClipForward.apply(eng, image, text, pos_embedding, tuple(keys), *weights, *biases)
+        out = _ClipForward.apply(eng, image, text, pos_embedding, tuple(keys), *weights, *biases)
+        if isinstance(out, tuple):
+            out, eng.loss_out = out
+        return out
     with torch.no_grad():
         v_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "v"}
         t_ad = {k[1]: (w, b) for k, w, b in zip(keys, weights, biases) if k[0] == "t"}
-        pred, _ = eng.run_forward(image, text, pos_embedding, v_ad, t_ad, False)
+        pred, saved = eng.run_forward(image, text, pos_embedding, v_ad, t_ad, False)
+        eng.loss_out = saved["loss"]
     return pred

@@ -80,7 +80,7 @@ def check(rc, what, kernels=None):
 
 __all__ = ["gemm", "split_bf16", "layernorm_fwd", "layernorm_bwd", "im2col_patches",
            "assemble_tokens_ln", "embed_tokens", "gather_rows", "attention_fwd",
-           "attention_bwd_row0", "dora_merge_fwd", "dora_merge_bwd", "cos_head_fwd", "cos_head_bwd",
+           "attention_bwd_row0", "dora_merge_fwd", "dora_merge_bwd", "cos_head_fwd", "cos_head_bwd", "cos_mse_fwd", "cos_mse_bwd",
            "adamw_multi", "sgd_multi", "rdm_f64", "rank_avg_f64", "pearson_f64", "softmax_ce",
            "add_rows", "nonfinite_flag", "Operand"]
 
@@ -295,6 +295,30 @@ def cos_head_bwd(img, txt, logit_scale, d_img, d_txt, *, d_pred=None, pred=None,
     check(_lib.load().hba_cos_head_bwd(_p(img), _p(txt), B, txt.shape[0], E, _p(logit_scale),
                                        _p(d_pred), _p(pred), _p(target), _p(d_img), _p(d_txt),
                                        _stream()), "hba_cos_head_bwd")
+
+
+def cos_mse_fwd(img, txt, logit_scale, pred, *, B, groups=1, target=None, target_group_stride=0, loss=None,
+                bad_step=None, bad_total=None, total=None, workspace=None):
+    """Cosine logits (+ fused nn.MSELoss, non-finite flag and running loss sum) in one launch; `groups`
+    independent problems laid out contiguously: img [groups*B, E], txt [groups*C, E], pred [groups*B, C]."""
+    E = img.shape[-1]
+    C_ = txt.shape[0] // groups
+    assert img.shape[0] == groups * B and txt.shape[0] == groups * C_ and pred.numel() == groups * B * C_
+    if target is not None:
+        assert target.dtype == torch.float32 and target.is_contiguous()
+        assert workspace is not None and workspace.numel() >= groups * (B + 1)
+    check(_lib.load().hba_cos_mse_fwd(_p(img), _p(txt), B, C_, E, groups, _p(logit_scale), _p(pred), _p(target),
+                                      target_group_stride, _p(loss), _p(bad_step), _p(bad_total), _p(total),
+                                      _p(workspace), _stream()), "hba_cos_mse_fwd")
+
+
+def cos_mse_bwd(img, txt, logit_scale, pred, target, d_img, d_txt, *, B, groups=1, target_group_stride=0,
+                d_loss=None):
+    E = img.shape[-1]
+    C_ = txt.shape[0] // groups
+    check(_lib.load().hba_cos_mse_bwd(_p(img), _p(txt), B, C_, E, groups, _p(logit_scale), _p(pred), _p(target),
+                                      target_group_stride, _p(d_loss), _p(d_img), _p(d_txt), _stream()),
+          "hba_cos_mse_bwd")
 
 
 def adamw_multi(ptr_table, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step, skip_flag=None,
