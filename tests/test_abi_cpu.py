@@ -96,3 +96,67 @@ def test_plugin_module_surface():
     assert blk.attn.out_proj.weight.shape == (256, 256)
     assert model.transformer.resblocks[-1].attn.out_proj.in_features == 128
     assert not model.training
+
+
+def _write_vocab(path, merges):
+    import gzip
+    with gzip.open(path, "wt", encoding="utf-8") as f:
+        f.write("#version: test\n" + "\n".join(merges) + "\n")
+
+
+def test_bpe_tokenizer_merges_in_rank_order(tmp_path, monkeypatch):
+    """simple_tokenizer.py on a hand-made merge table: ids = 512 + merge index for merged symbols, byte symbols
+    in the published order ('!' = 0 ... , the same with </w> from 256), SOT / EOT last."""
+    from src.models.CLIPs.clip_hba import simple_tokenizer as st
+    vocab = tmp_path / "bpe_simple_vocab_16e6.txt.gz"
+    _write_vocab(vocab, ["h e", "he l", "l o</w>", "w o", "r l", "rl d</w>"])
+    monkeypatch.setenv("HBA_BPE_VOCAB", str(vocab))
+    st.load.cache_clear()
+    tok = st.load()
+    try:
+        sym = lambda ch: ord(ch) - ord("!")
+        # hello -> h e l l o</w> -> he l l o</w> -> hel l o</w> -> hel lo</w>
+        assert tok.encode("hello") == [512 + 1, 512 + 2]
+        # "World!" is lower-cased; wo | rl d</w> -> wo rld</w>;  "!" is its own token with </w>
+        assert tok.encode("  World! ") == [512 + 3, 512 + 5, 256 + sym("!")]
+        assert tok.encode("a&amp;b") == [256 + sym("a"), 256 + sym("&"), 256 + sym("b")]   # html unescape
+        assert tok.sot == tok.eot - 1 == len(tok.encoder) - 2
+    finally:
+        st.load.cache_clear()
+
+
+def test_tokenize_refuses_made_up_ids_for_a_real_checkpoint(tmp_path, monkeypatch):
+    """the word-hash pseudo ids are for synthetic (random-init) checkpoints only."""
+    from src.models.CLIPs.clip_hba import clip, simple_tokenizer as st
+    monkeypatch.delenv("HBA_TOKENIZER", raising=False)
+    monkeypatch.setenv("HBA_BPE_VOCAB", str(tmp_path / "missing.gz"))
+    monkeypatch.setattr(st, "vocab_candidates", lambda: [str(tmp_path / "missing.gz")])
+    st.load.cache_clear()
+    real = tmp_path / "ViT-L-14.pt"
+    real.write_bytes(b"x")                              # a cached "published" checkpoint
+    saved = dict(clip._CHECKPOINT)
+    try:
+        assert clip._download(clip._MODELS["ViT-L/14"], str(tmp_path)) == str(real)
+        assert clip._CHECKPOINT["synthetic"] is False
+        with pytest.raises(RuntimeError, match="BPE merge table"):
+            clip.tokenize("metallic; artificial")
+        monkeypatch.setenv("HBA_TOKENIZER", "pseudo")
+        with pytest.warns(RuntimeWarning, match="pseudo ids"):
+            t = clip.tokenize("metallic; artificial")
+        assert t.shape == (1, 77)
+        monkeypatch.delenv("HBA_TOKENIZER")
+        # with a merge table the published encoding is used
+        vocab = tmp_path / "bpe_simple_vocab_16e6.txt.gz"
+        _write_vocab(vocab, ["h e", "he l", "l o</w>"])
+        monkeypatch.setattr(st, "vocab_candidates", lambda: [str(vocab)])
+        st.load.cache_clear()
+        t = clip.tokenize("hello")
+        tok = st.load()
+        assert t[0, :4].tolist() == [tok.sot, 513, 514, tok.eot] and int(t[0].argmax()) == 3
+        # a synthetic checkpoint goes back to the word-hash ids (what the oracle / goldens use)
+        clip._download("synthetic://ViT-tiny-14.pt", str(tmp_path))
+        assert clip._CHECKPOINT["synthetic"] is True
+        assert clip.tokenize("hello")[0, 0] == clip.SOT_TOKEN and int(clip.tokenize("hello")[0, 2]) == clip.EOT_TOKEN
+    finally:
+        clip._CHECKPOINT.update(saved)
+        st.load.cache_clear()

@@ -58,9 +58,13 @@ def test_resident_loader_subset_ids_and_inference_items():
     for wn, wi, wt in ref:
         gn, gi, gt = next(it)
         assert list(gn) == list(wn) and torch.equal(gi, wi) and torch.equal(gt, wt)
-        assert mine.last_ids == [data.image_id(n) for n in gn] == mine.last_ids_dev.tolist()
+        assert mine.last_ids == [data.image_id(n, store.namespace) for n in gn] == mine.last_ids_dev.tolist()
     assert list(it) == [] and mine.last_ids is None
     assert data.image_id("img_007.jpg") == data.image_id("img_007.jpg") != data.image_id("img_008.jpg")
+    # the same file name under another image directory is another image (another cache entry)
+    assert data.image_id("img_007.jpg", "/data/a") != data.image_id("img_007.jpg", "/data/b")
+    other = data.ResidentStore(_Things(12), "cpu")
+    assert other.namespace != store.namespace and not set(other.ids) & set(store.ids)
     # (name, image) items - ThingsInferenceDataset, NEW:206-224 - give two-element batches
     pairs = [(f"v{i}.jpg", torch.full((3, 2, 2), float(i))) for i in range(5)]
     inf = data.ResidentLoader(data.ResidentStore(pairs, "cpu"), 4)

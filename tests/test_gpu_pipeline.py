@@ -400,3 +400,47 @@ def test_fused_mse_step_equals_the_criterion_called_step(tiny_checkpoint, monkey
             assert rel_err(a, b) < 1e-5
     finally:
         hba.set_precision("bf16")
+
+
+def test_trunk_cache_is_never_served_after_the_engine_was_restaged(tiny_checkpoint):
+    """a cache filled under one staging (precision mode) must not answer a hit after the engine was
+    restaged - TrainStep decides `cached` before the forward pass, so the check has to compare the stamps, and a
+    device-id lookup on a freshly reallocated cache must raise instead of returning uninitialised memory."""
+    import hba
+    import functions.new_cvpr_train_behavior_things_pipeline as NEW
+    from functions import _pipeline_core as core
+    from hba.engine import TrunkCache
+    from oracle.synth import synthetic_problem
+    prob = synthetic_problem()
+    x = prob["train_images"][:4].to(DEV)
+    y = torch.randn(4, 6, generator=torch.Generator().manual_seed(3)).to(DEV)
+    ids, ids_dev = [3, 7, 1, 9], torch.tensor([3, 7, 1, 9], device=DEV)
+    crit = torch.nn.MSELoss()
+    hba.set_precision("bf16")
+    try:
+        model = build_model(NEW).to(DEV)
+        eng = model.clip_model.hba_engine()
+        eng.trunk_cache = TrunkCache(16)
+        step = core.TrainStep(model, core.make_optimizer(model, 3e-4), crit, DEV)
+        step(x, y, ids, ids_dev)                                  # fills the cache (bf16 staging)
+        assert eng.trunk_cache.all_present(ids, eng)
+        hba.set_precision("fp32")                                 # the next forward restages the engine
+        assert not eng.trunk_cache.all_present(ids, eng)          # stale: not a hit
+        eng.ensure(eng.device)
+        assert not eng.trunk_cache.all_present(ids, eng)
+        with pytest.raises(RuntimeError, match="restaged"):
+            eng.trunk_cache.lookup_device_ids(eng, ids_dev)
+        assert eng.trunk_cache.present == set()
+        # the forward recomputes (and refills) instead of reading the old buffers
+        with torch.no_grad():
+            eng.batch_ids = None
+            base = model(x)
+            eng.batch_ids = ids
+            fill = model(x)
+            assert torch.equal(base, fill)
+            assert eng.trunk_cache.all_present(ids, eng)
+            eng.batch_ids = ids_dev
+            assert torch.equal(base, model(x))
+        assert eng.trunk_cache.all_present(ids, eng)
+    finally:
+        hba.set_precision("bf16")

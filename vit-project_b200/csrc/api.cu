@@ -26,17 +26,26 @@ int check_launch(const char* what) {
   return HBA_OK;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
       return kNumSMs;
   }
-  return cached;
+  return cached[dev];
 }
 
 // cuTensorMapEncodeTiled is resolved through the runtime so that the library has no link-time

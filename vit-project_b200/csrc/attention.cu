@@ -401,18 +401,8 @@ static int attention_fwd_dispatch(const T* qkv, int64_t ld_qkv, int B, int Tn, i
   const size_t smem = sizeof(float) * ((((size_t)Tn * kKStride + 3) & ~(size_t)3) + (size_t)Tn * kHd +
                                        kAttnWarps * kQPerWarp * kHd +
                                        (size_t)kAttnWarps * kQPerWarp * Tp);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<T>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("attention_fwd_kernel: cannot reserve %zu bytes of shared memory: %s", smem,
-                cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    configured = smem;
-  }
+  static SmemAttr attr;
+  HBA_CHECK(ensure_dyn_smem(attention_fwd_kernel<T>, smem, attr, "attention_fwd_kernel"));
   attention_fwd_kernel<T><<<B * H, kAttnWarps * 32, smem, s>>>(qkv, ld_qkv, Tn, H, causal, out,
                                                               ld_out, lo_off, out_f32, ld_of);
   return check_launch("attention_fwd_kernel");

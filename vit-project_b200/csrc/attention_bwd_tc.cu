@@ -416,17 +416,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 int attention_bwd_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
                             const __nv_bfloat16* o, int64_t ld_o, const __nv_bfloat16* d_out, int64_t ld_do,
                             const float* lse, __nv_bfloat16* d_qkv, int64_t ld_dqkv, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("cudaFuncSetAttribute(attention_bwd_tc_kernel): %s", cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static SmemAttr attr;
+  HBA_CHECK(ensure_dyn_smem(attention_bwd_tc_kernel, kSmemBytes, attr, "attention_bwd_tc_kernel"));
   if (T > kMaxRows) {
     set_error("attention_bwd_tc: T=%d exceeds %d", T, kMaxRows);
     return HBA_ERR_ARG;

@@ -539,17 +539,8 @@ static long long* g_attn_trace = nullptr;
 int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, int H, int causal,
                         __nv_bfloat16* out, int64_t ld_out, float* out_f32, int64_t ld_of, float* lse,
                         cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("cudaFuncSetAttribute(attention_tc_kernel): %s", cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static SmemAttr attr;
+  HBA_CHECK(ensure_dyn_smem(attention_tc_kernel, kTcSmemBytes, attr, "attention_tc_kernel"));
   AttnTcArgs g;
   g.T = T, g.H = H, g.causal = causal;
   g.n_units = B * H;

@@ -23,7 +23,27 @@ int check_launch(const char* what);  // 0 or HBA_ERR_CUDA with message
   } while (0)
 
 constexpr int kNumSMs = 148;
-int num_sms();  // SM count of the current device (148 on B200)
+constexpr int kMaxDevices = 64;
+int current_device();  // ordinal of the calling thread's current CUDA device (0 when unknown)
+int num_sms();         // SM count of the current device (148 on B200)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: each launcher keeps one
+// SmemAttr (function-local static) and raises the limit on the device it is about to launch on
+struct SmemAttr {
+  size_t configured[kMaxDevices] = {};
+};
+template <typename Kernel>
+int ensure_dyn_smem(Kernel kernel, size_t bytes, SmemAttr& st, const char* name) {
+  const int dev = current_device();
+  if (bytes <= st.configured[dev]) return HBA_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot reserve %zu bytes of dynamic shared memory: %s", name, bytes, cudaGetErrorString(e));
+    return HBA_ERR_CUDA;
+  }
+  st.configured[dev] = bytes;
+  return HBA_OK;
+}
 // 2-D bf16 row-major tensor map, box = [box_rows, box_cols]; 64-column boxes use SWIZZLE_128B
 int make_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols);

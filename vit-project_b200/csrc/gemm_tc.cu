@@ -671,18 +671,8 @@ static int gemm_cta_group() {
 template <int BN, int CG, int ACT>
 static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, CG, ACT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("cudaFuncSetAttribute(gemm_tc_kernel<%d,%d>): %s", BN, CG, cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    attr_set = true;
-  }
+  static SmemAttr smem_attr;
+  HBA_CHECK(ensure_dyn_smem(gemm_tc_kernel<BN, CG, ACT>, Cfg::kSmemBytes, smem_attr, "gemm_tc_kernel"));
   constexpr int BNC = BN / CG;
   const uint64_t a_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->a_lo_off : 0);
   const uint64_t b_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);

@@ -401,18 +401,8 @@ static int launch_attention_bwd(const void* qkv, int64_t ld_qkv, int B, int T, i
                                 cudaStream_t s) {
   const size_t smem = sizeof(uint32_t) * 4 * (size_t)T * AbSt<sizeof(TI) == 4>::pitch + sizeof(float) * 3 * (size_t)T +
                       sizeof(float) * kAbWarps * 2 * kAbMaxT;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<TI, TG, TO>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("attention_bwd_kernel: cannot reserve %zu bytes of shared memory: %s", smem,
-                cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    configured = smem;
-  }
+  static SmemAttr attr;
+  HBA_CHECK(ensure_dyn_smem(attention_bwd_kernel<TI, TG, TO>, smem, attr, "attention_bwd_kernel"));
   attention_bwd_kernel<TI, TG, TO><<<B * H, kAbWarps * 32, smem, s>>>(
       static_cast<const TI*>(qkv), ld_qkv, T, H, causal, static_cast<const TG*>(d_out), ld_do,
       static_cast<TO*>(d_qkv), ld_dqkv);

@@ -466,7 +466,7 @@ class _CachedForwardGraphs:
         eng = self.eng
         return (os.environ.get("HBA_STEP_GRAPH", "1") != "0" and eng is not None and eng.trunk_cache is not None
                 and getattr(loader, "last_ids_dev", None) is not None and not torch.is_grad_enabled()
-                and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids))
+                and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids, eng))
 
     def loss_total(self):
         """float64 device scalar that the fused-MSE evaluation batches accumulate loss * batch into."""
@@ -477,6 +477,12 @@ class _CachedForwardGraphs:
 
     def __call__(self, images, ids_dev, targets=None):
         """targets given: nn.MSELoss is fused into the head kernel and loss * batch is added to loss_total()."""
+        if images.is_cuda and images.device.index != torch.cuda.current_device():
+            with torch.cuda.device(images.device):
+                return self._run(images, ids_dev, targets)
+        return self._run(images, ids_dev, targets)
+
+    def _run(self, images, ids_dev, targets):
         eng = self.eng
         key = (tuple(images.shape), eng._stamp, eng.precision, targets is not None)
         if key not in self.warm:
@@ -735,10 +741,16 @@ class TrainStep:
 
     def __call__(self, images, targets, ids_host=None, ids_dev=None):
         """ids_host / ids_dev: trunk-cache ids of the batch (None for perturbed images / no cache)."""
+        if images.is_cuda and images.device.index != torch.cuda.current_device():
+            with torch.cuda.device(images.device):   # graph capture / replay happen on the current device
+                return self._run(images, targets, ids_host, ids_dev)
+        return self._run(images, targets, ids_host, ids_dev)
+
+    def _run(self, images, targets, ids_host, ids_dev):
         eng = self.eng
         cache = eng.trunk_cache if eng is not None else None
         have_ids = cache is not None and ids_host is not None
-        cached = have_ids and ids_dev is not None and cache.x is not None and cache.all_present(ids_host)
+        cached = have_ids and ids_dev is not None and cache.x is not None and cache.all_present(ids_host, eng)
         if not self._graphs_on() or (have_ids and not cached):
             return self._body(images, ids_host if have_ids else None, targets)
         mode = "cached" if cached else "full"
@@ -800,8 +812,16 @@ def select_device(cuda_flag):
     """config['cuda'] (NEW:1137-1144): -1 / 0 / 1 -> CUDA device; anything else asked for the CPU in
     the reference, which this build does not have."""
     if cuda_flag == -1:
-        return torch.device("cuda")
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
     if cuda_flag in (0, 1):
+        if torch.cuda.is_available():
+            # CUDA-graph capture, side streams and the C-ABI launches all work on the CURRENT device: make the
+            # selected GPU current for the whole run (a sweep worker pins its GPU through CUDA_VISIBLE_DEVICES
+            # and maps every request onto the one device it sees)
+            if cuda_flag >= torch.cuda.device_count():
+                raise RuntimeError(f"config['cuda'] = {cuda_flag} but only {torch.cuda.device_count()} CUDA "
+                                   "device(s) are visible")
+            torch.cuda.set_device(cuda_flag)
         return torch.device(f"cuda:{cuda_flag}")
     raise RuntimeError("config['cuda'] selects the CPU, but the libhba pipeline has no CPU path; "
                        "use 0, 1 or -1")

@@ -11,15 +11,19 @@ on the device.  ``last_ids`` carries stable per-image integer ids for the frozen
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.utils.data import DataLoader, Dataset
 
 _NAME_IDS = {}
 
 
-def image_id(name: str) -> int:
-    """Process-wide stable integer id of an image name (key of the frozen-trunk cache)."""
-    return _NAME_IDS.setdefault(name, len(_NAME_IDS))
+def image_id(name: str, namespace: str = "") -> int:
+    """Process-wide stable integer id of an image (key of the frozen-trunk cache).  `namespace` is the image
+    directory (or a per-store token for synthetic stores): two runs in one worker whose img_dir differs but
+    whose file names collide must not share cache entries."""
+    return _NAME_IDS.setdefault((namespace, name), len(_NAME_IDS))
 
 
 class _Indices(Dataset):
@@ -36,8 +40,12 @@ class _Indices(Dataset):
 class ResidentStore:
     """All items of `dataset` decoded once and stacked on `device`."""
 
-    def __init__(self, dataset, device, names=None, images=None, targets=None):
+    def __init__(self, dataset, device, names=None, images=None, targets=None, namespace=None):
         self.device = torch.device(device)
+        if namespace is None:
+            img_dir = getattr(dataset, "img_dir", None)
+            namespace = os.path.abspath(img_dir) if isinstance(img_dir, str) else f"store@{id(self):x}"
+        self.namespace = namespace
         if images is None:
             names, imgs, tgts = [], [], []
             for i in range(len(dataset)):
@@ -51,7 +59,7 @@ class ResidentStore:
         self.names = list(names)
         self.images = images.to(self.device, torch.float32).contiguous()
         self.targets = None if targets is None else targets.to(self.device, torch.float32).contiguous()
-        self.ids = [image_id(n) for n in self.names]
+        self.ids = [image_id(n, namespace) for n in self.names]
         self.ids_dev = torch.tensor(self.ids, dtype=torch.int64, device=self.device)
 
     def __len__(self):

@@ -674,22 +674,40 @@ class TrunkCache:
         self.present = set()
         self.stamp = None
 
+    @staticmethod
+    def _stamp_of(eng):
+        return (eng.precision, eng._stamp, eng.vis.T * eng.vis.d, str(eng.device))
+
     def _ensure(self, eng):
-        width = eng.vis.T * eng.vis.d
-        stamp = (eng.precision, eng._stamp, width, str(eng.device))
+        """(Re)allocates the buffers when the engine's staging changed (precision switch, frozen weights
+        edited or reloaded, device move): everything cached before is invalid.  Returns True when the cache
+        was (re)initialised, i.e. holds nothing."""
+        stamp = self._stamp_of(eng)
         if self.x is None or self.stamp != stamp:
+            width = stamp[2]
             self.x = torch.empty(self.capacity, width, device=eng.device)
             self.a = torch.empty(self.capacity, width, device=eng.device)
             self.present = set()
             self.stamp = stamp
+            return True
+        return False
 
-    def all_present(self, ids):
+    def all_present(self, ids, eng=None):
+        """With `eng`: also validates that the entries were produced by the engine's CURRENT staging (and that
+        the engine itself is staged for the current precision mode) - a stale cache answers False, never a hit."""
+        if eng is not None:
+            if (eng.device is None or eng.precision != _PRECISION or self.x is None
+                    or self.stamp != self._stamp_of(eng)):
+                return False
         return all(int(i) in self.present for i in ids)
 
     def lookup_device_ids(self, eng, ids_dev):
-        """Hit path with the ids already on the device (the caller has checked `all_present`): no host
+        """Hit path with the ids already on the device (the caller has checked `all_present(ids, eng)`): no host
         work, no host->device copy - what a captured CUDA graph of the cached step replays."""
-        self._ensure(eng)
+        if self._ensure(eng):
+            raise RuntimeError("TrunkCache: the engine was restaged after the cache was filled (precision switch, "
+                               "frozen weight change or device move); the cached activations are invalid - "
+                               "check all_present(ids, eng) before a device-id lookup")
         B, d = ids_dev.numel(), eng.vis.d
         x = torch.index_select(self.x, 0, ids_dev, out=eng._buf("v.x", (B, self.x.shape[1])))
         a = torch.index_select(self.a, 0, ids_dev, out=eng._buf("v.acache", (B, self.x.shape[1])))

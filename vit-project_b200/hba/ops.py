@@ -6,6 +6,8 @@ the C-ABI and raises ``RuntimeError`` on failure.  Nothing here computes on the 
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import itertools
 
 import torch
 
@@ -426,3 +428,37 @@ def add_rows(dst, src, rows, cols, dst_row_step=1):
 
 def nonfinite_flag(x, flag):
     check(_lib.load().hba_nonfinite_flag(_p(x), x.numel(), _p(flag), _stream()), "hba_nonfinite_flag")
+
+
+# ------------------------------------------------------------------------------------------------------
+# Device guard.  The C-ABI launches on the calling thread's CURRENT device / the stream passed in, and
+# `_stream()` is the current stream of the current device: a call whose tensors live on another GPU
+# (config['cuda'] = 1 of the reference, NEW:1137-1144, while the process' current device is still 0) would
+# launch in the wrong context.  Every front end therefore runs under `torch.cuda.device(<its tensors' device>)`
+# and refuses operands that are spread over several devices.
+def _device_guarded(fn):
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in itertools.chain(args, kwargs.values()):
+            t = a.buf if isinstance(a, Operand) else a
+            if torch.is_tensor(t) and t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise RuntimeError(f"libhba {fn.__name__}: operands on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name in ("gemm", "split_bf16", "layernorm_fwd", "layernorm_bwd", "im2col_patches", "assemble_tokens_ln",
+              "embed_tokens", "gather_rows", "attention_fwd", "attention_bwd_row0", "dora_merge_fwd", "dora_merge_bwd",
+              "cos_head_fwd", "cos_head_bwd", "cos_mse_fwd", "cos_mse_bwd", "adamw_multi", "sgd_multi", "sgd_staged",
+              "rdm_f64", "rank_avg_f64", "pearson_f64", "softmax_ce", "colsum", "layernorm_param_grad",
+              "attention_bwd", "layernorm_bwd_fused", "attention_fwd_lse", "attention_bwd_lse", "add_rows",
+              "nonfinite_flag"):
+    globals()[_name] = _device_guarded(globals()[_name])
+del _name

@@ -192,6 +192,9 @@ def synthetic_state_dict(fname, seed=1):
         torch.set_rng_state(state)
 
 
+_CHECKPOINT = {"synthetic": True, "path": None}   # what the last _download() call handed out
+
+
 def _download(url, root):
     """Returns the local checkpoint path.  A cached file wins; real URLs are fetched only when
     HBA_ALLOW_DOWNLOAD=1; otherwise (offline) a seeded synthetic checkpoint of the same
@@ -199,34 +202,66 @@ def _download(url, root):
     os.makedirs(root, exist_ok=True)
     fname = os.path.basename(url)
     target = os.path.join(root, fname)
-    if os.path.exists(target):
-        return target
-    if not url.startswith("synthetic://") and os.environ.get("HBA_ALLOW_DOWNLOAD") == "1":
-        import urllib.request
-        urllib.request.urlretrieve(url, target)
-        return target
-    if not url.startswith("synthetic://"):
-        warnings.warn(f"{fname}: no cached checkpoint under {root} and downloads are disabled; "
-                      "using seeded random-init weights of the same architecture", RuntimeWarning)
-        target = os.path.join(root, "synthetic-" + fname)
-        if os.path.exists(target):
-            return target
-    torch.save(synthetic_state_dict(fname), target)
+    synthetic = url.startswith("synthetic://")
+    if not os.path.exists(target):
+        if not synthetic and os.environ.get("HBA_ALLOW_DOWNLOAD") == "1":
+            import urllib.request
+            urllib.request.urlretrieve(url, target)
+        else:
+            if not synthetic:
+                warnings.warn(f"{fname}: no cached checkpoint under {root} and downloads are disabled; "
+                              "using seeded random-init weights of the same architecture", RuntimeWarning)
+                target, synthetic = os.path.join(root, "synthetic-" + fname), True
+            if not os.path.exists(target):
+                torch.save(synthetic_state_dict(fname), target)
+    _CHECKPOINT.update(synthetic=synthetic, path=target)
     return target
 
 
-def tokenize(texts, context_length=CONTEXT_LENGTH):
-    """str | list[str] -> int64 [n, context_length]: [SOT, word ids ..., EOT, 0-pad].
-    With the BPE vocabulary unavailable offline, each lower-cased whitespace-separated word maps to
-    a stable pseudo-id (sha256); EOT stays the row maximum, which is all the model relies on
-    (``text.argmax(-1)``).  A str yields [1,77] like the published tokenizer, so the reference's
-    ``torch.stack([clip.tokenize(c) ...])`` (NEW:282) gives [66,1,77]."""
+def _pseudo_ids(text, context_length):
+    ids = [SOT_TOKEN]
+    for w in text.lower().replace(",", " , ").split()[: context_length - 2]:
+        h = int.from_bytes(hashlib.sha256(w.encode()).digest()[:4], "little")
+        ids.append(1 + h % (SOT_TOKEN - 1))
+    return ids + [EOT_TOKEN]
+
+
+def tokenize(texts, context_length=CONTEXT_LENGTH, truncate=False):
+    """str | list[str] -> int64 [n, context_length]: [SOT, token ids ..., EOT, 0-pad]; a str yields [1,77] like
+    the published tokenizer, so the reference's ``torch.stack([clip.tokenize(c) ...])`` (NEW:282) gives [66,1,77].
+
+    Real checkpoint (the last ``_download`` returned a published ViT-*.pt): the published byte-pair encoding
+    (simple_tokenizer.py; needs the merge table ``bpe_simple_vocab_16e6.txt.gz`` next to this module, under
+    ~/.cache/clip, or at $HBA_BPE_VOCAB).  Without the table this raises: feeding made-up ids to a pretrained
+    token_embedding would change every prediction silently.
+    Synthetic checkpoint (``synthetic://`` / ``synthetic-*``, the offline stand-in): the embedding table is
+    random, so any injective word -> id map is as good as the real one; each lower-cased whitespace-separated
+    word maps to a stable pseudo-id (sha256) - what the oracle and the golden fixtures use.  EOT stays the row
+    maximum, which is all the model relies on (``text.argmax(-1)``).  HBA_TOKENIZER=bpe|pseudo overrides."""
+    from . import simple_tokenizer
+    mode = os.environ.get("HBA_TOKENIZER", "")
+    if mode not in ("", "bpe", "pseudo"):
+        raise ValueError("HBA_TOKENIZER must be 'bpe' or 'pseudo'")
+    use_bpe = mode == "bpe" or (mode == "" and not _CHECKPOINT["synthetic"])
+    tok = simple_tokenizer.load() if use_bpe else None
+    if use_bpe and tok is None:
+        raise RuntimeError(
+            f"clip.tokenize: the checkpoint {_CHECKPOINT['path']} is a published CLIP model but the BPE merge "
+            f"table {simple_tokenizer.VOCAB_FILE} was not found (looked in {simple_tokenizer.vocab_candidates()}). "
+            "Copy it next to clip.py, or set HBA_BPE_VOCAB. (HBA_TOKENIZER=pseudo forces the word-hash ids, "
+            "which are only meaningful for random-init weights.)")
+    if mode == "pseudo" and not _CHECKPOINT["synthetic"]:
+        warnings.warn("clip.tokenize: word-hash pseudo ids with a pretrained checkpoint - the text features do "
+                      "not correspond to the prompts", RuntimeWarning)
     rows = []
     for t in ([texts] if isinstance(texts, str) else list(texts)):
-        ids = [SOT_TOKEN]
-        for w in t.lower().replace(",", " , ").split()[: context_length - 2]:
-            h = int.from_bytes(hashlib.sha256(w.encode()).digest()[:4], "little")
-            ids.append(1 + h % (SOT_TOKEN - 1))
-        ids.append(EOT_TOKEN)
+        if tok is not None:
+            ids = [tok.sot] + tok.encode(t) + [tok.eot]
+            if len(ids) > context_length:
+                if not truncate:
+                    raise RuntimeError(f"Input {t} is too long for context length {context_length}")
+                ids = ids[:context_length - 1] + [tok.eot]
+        else:
+            ids = _pseudo_ids(t, context_length)
         rows.append(ids + [0] * (context_length - len(ids)))
     return torch.tensor(rows, dtype=torch.long)
