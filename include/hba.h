@@ -254,6 +254,15 @@ int hba_rank_avg_f64(const double* x, int64_t n, double* ranks, void* workspace,
                      int64_t workspace_bytes, void* stream);
 int hba_pearson_f64(const double* a, const double* b, int64_t n, double* rho_out,
                     double* workspace /* >= 5*1024 doubles */, void* stream);
+/* RSA at scale (BASELINE config 5: 1,854 x 66 embeddings per checkpoint -> P = 1,717,731 pairs), the whole
+ * chain of NEW:625-652 for one checkpoint in 11 stream-ordered launches: E [N, Dm] fp32 -> RDM entries written
+ * directly as sortable 64-bit keys -> all eight digit histograms in one pass -> one radix kernel per non-constant
+ * digit (decoupled look-back) -> tie-averaged ranks consumed in sorted order by the Pearson sums against
+ * ref_ranks [P] (the average ranks of the reference RDM's upper triangle) -> rho_out (device double).
+ * rdm [N,N] f64 and ranks [P] f64 are optional outputs.  NaN semantics are numpy's / scipy's: a NaN or constant
+ * embedding row gives rho = NaN.  Needs N(N-1)/2 > 2048; workspace: hba_rank_workspace_bytes(N(N-1)/2). */
+int hba_rdm_spearman(const float* E, int32_t N, int32_t Dm, const double* ref_ranks, double* rdm,
+                     double* ranks, double* rho_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Softmax cross-entropy (nn.CrossEntropyLoss at VIT:291, applied VIT:139) forward + backward:

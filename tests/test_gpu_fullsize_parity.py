@@ -98,7 +98,11 @@ def _build(sd, tokens, which):
     torch.manual_seed(123)
     dora_ref.apply_dora_ref(model, 2, 1, r=32, layer_cls=layer)
     dora_ref.switch_dora_ref(model, layer_cls=layer)
-    return model.to(DEV)
+    model = model.to(DEV)
+    # the prompts are a plain attribute (NEW:282): keep them on the device so that the per-call `.to(device)` of
+    # the wrapper is a no-op - a host->device copy is not allowed inside a captured step
+    model.tokenized_prompts = model.tokenized_prompts.to(DEV)
+    return model
 
 
 def _trainable(model):

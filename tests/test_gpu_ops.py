@@ -163,6 +163,37 @@ def test_layernorm_fwd_bwd(cols, split):
     assert rel_err(ysel, y.detach()[::5][: rows // 5]) < 1e-5
 
 
+@pytest.mark.parametrize("rows,cols", [(8224, 1024), (5082, 768), (1024, 128), (1031, 256), (3000, 1024)])
+@pytest.mark.parametrize("split", [False, True])
+def test_layernorm_fwd_streaming_form(rows, cols, split):
+    """>= 1024 rows take the persistent bulk-copy-staged kernel (layernorm_fwd_stream_kernel): same arithmetic as
+    the warp-per-row kernel, checked against torch and - bit for bit - against the warp-per-row kernel run on the
+    same rows in two halves of < 1024 rows... (which the launcher routes to the per-row kernel)."""
+    hba, ops, ref = _imports()
+    g = torch.Generator().manual_seed(rows + cols)
+    x = (torch.randn(rows, cols, generator=g) * 3 - 0.7)
+    x[5, 7] = 250.0                                   # an outlier feature, as the CLIP residual stream has
+    w, b = torch.randn(cols, generator=g), torch.randn(cols, generator=g)
+    want = torch.nn.functional.layer_norm(x, (cols,), w, b, 1e-5)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    yf = torch.full((rows, cols), float("nan"), device=DEV)
+    yo = ops.Operand.empty(rows, cols, split, DEV)
+    ops.layernorm_fwd(xd, rows, cols, wd, bd, 1e-5, y_f32=yf, y=yo)
+    assert rel_err(yf, want) < 1e-5
+    assert rel_err(operand_value(yo), want) < (2e-5 if split else 5e-3)
+    # the per-row kernel on chunks of 1000 rows: identical bits
+    yc = torch.empty(rows, cols, device=DEV)
+    for r0 in range(0, rows, 1000):
+        n = min(1000, rows - r0)
+        ops.layernorm_fwd(xd[r0:], n, cols, wd, bd, 1e-5, y_f32=yc[r0:])
+    assert torch.equal(yc, yf)
+    # bf16-only output with a strided source (every 2nd row), as the engine never uses but the ABI allows
+    if rows >= 2048:
+        ys = torch.empty(rows // 2, cols, device=DEV)
+        ops.layernorm_fwd(xd, rows // 2, cols, wd, bd, 1e-5, row_step=2, y_f32=ys)
+        assert torch.equal(ys, yf[::2][: rows // 2])
+
+
 @pytest.mark.parametrize("split", [False, True])
 def test_patch_embed_front_end(split):
     hba, ops, ref = _imports()
@@ -512,3 +543,29 @@ def test_spearman_pipeline(N):
     assert abs(rho - rho_w) < 1e-10       # north star: within 1e-4
     assert abs(p - p_w) <= 1e-9 * max(p_w, 1e-300) + 1e-300
     assert np.abs(rdm - rdm_w).max() < 1e-12
+
+
+@pytest.mark.parametrize("N", [48, 300])
+@pytest.mark.parametrize("bad", ["nan_row", "constant_row"])
+def test_rsa_nan_semantics(N, bad):
+    """A diverged model (NaN or constant embedding row) must log nan, as numpy.corrcoef / scipy.stats.spearmanr do
+    (NEW:625-652) - never rho = -1 (CUDA fmin/fmax drop NaN).  N=48 takes the three-kernel path, N=300 the fused
+    RSA-at-scale chain."""
+    from scipy.stats import spearmanr
+    from hba import rsa
+    rng = np.random.default_rng(N)
+    E = rng.standard_normal((N, 66)).astype(np.float32)
+    if bad == "nan_row":
+        E[3, 5] = np.nan
+    else:
+        E[7] = 0.25
+    ref_rdm = 1 - np.corrcoef(rng.standard_normal((N, 66)))
+    np.fill_diagonal(ref_rdm, 0)
+    with np.errstate(all="ignore"):
+        want_rdm = 1 - np.corrcoef(E)
+        np.fill_diagonal(want_rdm, 0)
+        want_rho = spearmanr(ref_rdm[np.triu_indices(N, 1)], want_rdm[np.triu_indices(N, 1)])[0]
+    assert math.isnan(want_rho)
+    rho, p, rdm = rsa.rsa_from_embeddings(torch.from_numpy(E).to(DEV), ref_rdm)
+    assert math.isnan(rho) and math.isnan(p)
+    assert np.array_equal(np.isnan(rdm), np.isnan(want_rdm))

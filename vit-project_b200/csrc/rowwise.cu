@@ -1,6 +1,8 @@
 // Bandwidth-bound row-wise kernels of the CLIP-HBA towers: operand staging (fp32 -> bf16 hi/lo),
 // LayerNorm forward/backward, patch im2col, token assembly + ln_pre, text embedding, row gathers.
 // All are one-warp-per-row or grid-stride kernels with 128-bit accesses; bound: HBM.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hba {
@@ -116,6 +118,113 @@ __global__ void __launch_bounds__(256)
       ln_store(y, c, y_f32 ? y_f32 + row * ld_yf : nullptr, y_bf16 ? y_bf16 + row * ld_yb : nullptr,
                lo_off);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward, streaming form for the big activations (>= 1024 rows; the 74 launches of a CLIP-HBA step
+// are 8224 x 1024 / 5082 x 768): one persistent CTA per SM owns a contiguous range of rows and pulls them
+// through a ring of shared-memory stages with bulk asynchronous copies (cp.async.bulk, one per row, completion
+// on an mbarrier), so that ~190 KB of loads are in flight per SM independently of register pressure and the
+// grid has no second wave.  Warp w of the 8 consumer warps normalises row w of a stage out of shared memory;
+// the arithmetic (per-lane partial sums in the same order, xor-shuffle reductions, two-pass variance) is the
+// one of layernorm_fwd_kernel, so both kernels produce identical bits.
+constexpr int kLnsRows = 8;         // rows per stage = consumer warps
+constexpr int kLnsThreads = 32 * (kLnsRows + 1);
+constexpr int kLnsMaxStages = 8;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kLnsThreads, 1)
+    layernorm_fwd_stream_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                int64_t row_step, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, float* __restrict__ y_f32,
+                                int64_t ld_yf, __nv_bfloat16* __restrict__ y_bf16, int64_t ld_yb,
+                                int64_t lo_off, int stages) {
+  extern __shared__ __align__(128) uint8_t lns_smem[];
+  float* s_gamma = reinterpret_cast<float*>(lns_smem);
+  float* s_beta = s_gamma + cols;
+  float* s_rows = s_beta + cols;                                    // [stages][kLnsRows][cols]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_rows + (size_t)stages * kLnsRows * cols);
+  uint64_t* empty_bar = full_bar + kLnsMaxStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_begin = rows * blockIdx.x / gridDim.x, row_end = rows * (blockIdx.x + 1) / gridDim.x;
+  const int n_iters = (int)((row_end - row_begin + kLnsRows - 1) / kLnsRows);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kLnsRows);
+    }
+    mbar_fence_init();
+  }
+  for (int c = threadIdx.x * 4; c < cols; c += kLnsThreads * 4) {
+    *reinterpret_cast<float4*>(s_gamma + c) = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    *reinterpret_cast<float4*>(s_beta + c) = __ldg(reinterpret_cast<const float4*>(beta + c));
+  }
+  __syncthreads();
+  const uint32_t row_bytes = (uint32_t)cols * 4u;
+  if (warp == kLnsRows) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int st = it % stages;
+        if (it >= stages) mbar_wait(&empty_bar[st], ((it / stages) - 1) & 1);
+        const int64_t r0 = row_begin + (int64_t)it * kLnsRows;
+        const int n = (int)min((int64_t)kLnsRows, row_end - r0);
+        mbar_arrive_expect_tx(&full_bar[st], n * row_bytes);
+        for (int r = 0; r < n; ++r)
+          bulk_load_1d(s_rows + ((size_t)st * kLnsRows + r) * cols, x + (r0 + r) * row_step * ldx, row_bytes,
+                       &full_bar[st]);
+      }
+    }
+    return;
+  }
+  const int nvec = cols / 128;  // float4 per lane
+  for (int it = 0; it < n_iters; ++it) {
+    const int st = it % stages;
+    mbar_wait(&full_bar[st], (it / stages) & 1);
+    const int64_t row = row_begin + (int64_t)it * kLnsRows + warp;
+    if (row < row_end) {
+      const float* xr = s_rows + ((size_t)st * kLnsRows + warp) * cols;
+      float4 v[kLnMaxVec];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLnMaxVec; ++i)
+        if (i < nvec) {
+          v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+          sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+      const float mean = warp_sum(sum) / cols;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLnMaxVec; ++i)
+        if (i < nvec) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          sq += (a * a + b * b) + (c * c + d * d);
+        }
+      const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+#pragma unroll
+      for (int i = 0; i < kLnMaxVec; ++i)
+        if (i < nvec) {
+          const int c = (i * 32 + lane) * 4;
+          const float4 gm = *reinterpret_cast<const float4*>(s_gamma + c);
+          const float4 bt = *reinterpret_cast<const float4*>(s_beta + c);
+          float4 y;
+          y.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+          y.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+          y.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+          y.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+          ln_store(y, c, y_f32 ? y_f32 + row * ld_yf : nullptr, y_bf16 ? y_bf16 + row * ld_yb : nullptr,
+                   lo_off);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp's row of the stage has been read
+  }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
@@ -344,8 +453,29 @@ extern "C" int hba_layernorm_fwd(const float* x, int64_t rows, int32_t cols, int
   HBA_REQUIRE(x && gamma && beta && (y_f32 || y_bf16) && rows > 0, "hba_layernorm_fwd: bad arguments");
   HBA_REQUIRE(cols % 128 == 0 && cols <= 128 * kLnMaxVec, "hba_layernorm_fwd: cols=%d must be a multiple of 128 and <= %d", cols, 128 * kLnMaxVec);
   HBA_REQUIRE(ldx % 4 == 0 && ld_yf % 4 == 0 && ld_yb % 4 == 0 && lo_off % 4 == 0 && ((uintptr_t)y_bf16 & 7) == 0, "hba_layernorm_fwd: leading dimensions must keep 16-byte (fp32) / 8-byte (bf16) alignment");
-  layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols, ldx, row_step < 1 ? 1 : row_step, gamma, beta, eps, y_f32, ld_yf,
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (row_step < 1) row_step = 1;
+  static int use_stream = -1;
+  if (use_stream < 0) {
+    const char* e = getenv("HBA_LN_STREAM");
+    use_stream = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_stream && rows >= 1024 && ((uintptr_t)x & 15) == 0) {
+    // streaming form: persistent CTAs, rows staged through shared memory by bulk asynchronous copies
+    int stages = (int)((220 * 1024 - 2 * cols * 4 - 256) / ((size_t)kLnsRows * cols * 4));
+    if (stages > kLnsMaxStages) stages = kLnsMaxStages;
+    const size_t smem = (size_t)2 * cols * 4 + (size_t)stages * kLnsRows * cols * 4 + 2 * kLnsMaxStages * 8;
+    static SmemAttr attr;
+    HBA_CHECK(ensure_dyn_smem(layernorm_fwd_stream_kernel, smem, attr, "layernorm_fwd_stream_kernel"));
+    int grid = num_sms();
+    if ((int64_t)grid * kLnsRows > rows) grid = (int)((rows + kLnsRows - 1) / kLnsRows);
+    layernorm_fwd_stream_kernel<<<grid, kLnsThreads, smem, s>>>(x, rows, cols, ldx, row_step, gamma, beta, eps,
+                                                                y_f32, ld_yf, static_cast<__nv_bfloat16*>(y_bf16),
+                                                                ld_yb, lo_off, stages);
+    return check_launch("hba_layernorm_fwd (stream)");
+  }
+  layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+      x, rows, cols, ldx, row_step, gamma, beta, eps, y_f32, ld_yf,
       static_cast<__nv_bfloat16*>(y_bf16), ld_yb, lo_off);
   return check_launch("hba_layernorm_fwd");
 }

@@ -16,6 +16,7 @@ optimiser skip the update, which is what the reference's ``continue`` achieves.
 from __future__ import annotations
 
 import csv
+import gc
 import logging
 import os
 import random
@@ -721,7 +722,9 @@ class TrainStep:
             eng = self.eng
             eng.loss_request = LossRequest(targets.contiguous(), self.guard.step, self.guard.total, self.total)
             self.model(images)
-            loss = eng.loss_out
+            # (take the loss off the engine: a tensor that outlives the step keeps its autograd graph - and the
+            # AccumulateGrad nodes bound to this step's stream - alive into the next graph capture)
+            loss, eng.loss_out = eng.loss_out, None
             if loss is None:
                 raise RuntimeError("libhba: the forward pass did not consume the fused-loss request")
             loss.backward()
@@ -765,6 +768,7 @@ class TrainStep:
             s_ids = ids_dev.clone() if cached else None
             s_tgt = targets.clone()
             graph = torch.cuda.CUDAGraph()
+            gc.collect()   # no autograd graph of an earlier (eager, default-stream) step may survive into the capture
             torch.cuda.synchronize()
             c0 = ops.COUNTERS["launches"]
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):

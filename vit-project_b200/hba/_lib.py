@@ -67,6 +67,7 @@ SIGNATURES = {
     "hba_rank_workspace_bytes": (i64, [i64]),
     "hba_rank_avg_f64": (i32, [vp, i64, vp, vp, i64, vp]),
     "hba_pearson_f64": (i32, [vp, vp, i64, vp, vp, vp]),
+    "hba_rdm_spearman": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "hba_softmax_ce_fwd_bwd": (i32, [vp, i64, vp, i32, i32, vp, vp, i64, vp, vp, vp]),
     "hba_colsum": (i32, [vp, i32, i64, i32, i64, vp, i32, vp, vp]),
     "hba_layernorm_param_grad": (i32, [vp, i64, vp, i64, i32, i64, i64, f32, vp, i32, vp, vp]),

@@ -759,11 +759,16 @@ class _ClipForward(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             raise RuntimeError("libhba: gradients w.r.t. the input images are not supported")
         pred, saved = engine.run_forward(images, tokens, pos_embedding, v_ad, t_ad, need_grad)
+        # the loss becomes an OUTPUT of this node: keeping it in ctx.saved as well would close a reference cycle
+        # (node -> saved -> tensor -> grad_fn = node) that only the garbage collector breaks, and the step's
+        # autograd graph (with AccumulateGrad nodes bound to this step's stream) would survive into the next
+        # CUDA-graph capture
+        loss = saved.pop("loss")
         ctx.engine, ctx.saved, ctx.keys = engine, saved, keys
         ctx.set_materialize_grads(False)
-        if saved["loss"] is None:
+        if loss is None:
             return pred
-        return pred, saved["loss"]
+        return pred, loss
 
     @staticmethod
     def backward(ctx, d_pred, d_loss=None):

@@ -358,12 +358,21 @@ def rank_avg_f64(x, ranks, workspace=None):
     if workspace is None:
         workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
     check(_lib.load().hba_rank_avg_f64(_p(x), n, _p(ranks), _p(workspace), workspace.numel(), _stream()),
-          "hba_rank_avg_f64", 1 if n <= 2048 else 26)
+          "hba_rank_avg_f64", 1 if n <= 2048 else 10)
 
 
 def pearson_f64(a, b, rho_out, workspace):
     check(_lib.load().hba_pearson_f64(_p(a), _p(b), a.numel(), _p(rho_out), _p(workspace), _stream()),
           "hba_pearson_f64")
+
+
+def rdm_spearman(E, ref_ranks, rho_out, workspace, rdm=None, ranks=None):
+    """RSA at scale, one checkpoint: E [N, Dm] fp32 -> rho (device double) against ref_ranks [N(N-1)/2] f64."""
+    N, Dm = E.shape
+    assert E.dtype == torch.float32 and E.is_contiguous() and ref_ranks.dtype == torch.float64
+    assert ref_ranks.numel() == N * (N - 1) // 2
+    check(_lib.load().hba_rdm_spearman(_p(E), N, Dm, _p(ref_ranks), _p(rdm), _p(ranks), _p(rho_out), _p(workspace),
+                                       workspace.numel(), _stream()), "hba_rdm_spearman", 11)
 
 
 def softmax_ce(logits, labels, loss, d_logits, correct, workspace):
@@ -457,7 +466,7 @@ def _device_guarded(fn):
 for _name in ("gemm", "split_bf16", "layernorm_fwd", "layernorm_bwd", "im2col_patches", "assemble_tokens_ln",
               "embed_tokens", "gather_rows", "attention_fwd", "attention_bwd_row0", "dora_merge_fwd", "dora_merge_bwd",
               "cos_head_fwd", "cos_head_bwd", "cos_mse_fwd", "cos_mse_bwd", "adamw_multi", "sgd_multi", "sgd_staged",
-              "rdm_f64", "rank_avg_f64", "pearson_f64", "softmax_ce", "colsum", "layernorm_param_grad",
+              "rdm_f64", "rank_avg_f64", "pearson_f64", "rdm_spearman", "softmax_ce", "colsum", "layernorm_param_grad",
               "attention_bwd", "layernorm_bwd_fused", "attention_fwd_lse", "attention_bwd_lse", "add_rows",
               "nonfinite_flag"):
     globals()[_name] = _device_guarded(globals()[_name])

@@ -42,6 +42,10 @@ class RSAEvaluator:
         if emb.shape[0] != self.N:
             raise ValueError(f"expected {self.N} embeddings, got {emb.shape[0]}")
         emb = emb.detach().to(self.device, torch.float32).contiguous()
+        if self.P > 2048:
+            # RSA at scale: one fused chain (keys straight from the RDM kernel, ranks consumed in sorted order)
+            ops.rdm_spearman(emb, self.ref_ranks, self.rho, self.rank_ws, rdm=self.rdm if want_rdm else None)
+            return self.rho
         ops.rdm_f64(emb, self.rdm if want_rdm else None, self.tri)
         ops.rank_avg_f64(self.tri, self.ranks, self.rank_ws)
         ops.pearson_f64(self.ref_ranks, self.ranks, self.rho, self.pearson_ws)
@@ -49,7 +53,8 @@ class RSAEvaluator:
 
     def __call__(self, emb, want_rdm=True):
         """-> (rho, p_value, model_rdm ndarray | None), like behavioral_RSA's return (NEW:654)."""
-        rho = float(self.rho_device(emb, want_rdm).cpu())
+        with torch.cuda.device(self.device):
+            rho = float(self.rho_device(emb, want_rdm).cpu())
         rdm = self.rdm.cpu().numpy() if want_rdm else None
         return rho, spearman_pvalue(rho, self.P), rdm
 
@@ -58,7 +63,7 @@ def spearman_pvalue(rho, n):
     """Two-sided p-value of scipy.stats.spearmanr: t = r sqrt(dof / ((r+1)(1-r))), dof = n-2."""
     from scipy import special
     dof = n - 2
-    if dof <= 0:
+    if dof <= 0 or rho != rho:   # scipy returns (nan, nan) for constant / NaN input
         return float("nan")
     denom = (rho + 1.0) * (1.0 - rho)
     with np.errstate(divide="ignore", invalid="ignore"):
