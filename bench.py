@@ -47,7 +47,13 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--backbone", default="ViT-L/14")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample-images", type=int, default=8)
+    ap.add_argument("--cpu-sample-images", type=int, default=0,
+                    help="images per CPU-arm step (0 = the stated batch: same config as the GPU arm)")
+    ap.add_argument("--sweep-per-gpu", type=int, default=4, help="grid conditions per GPU in the scheduler-run slice")
+    ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-hbm-kernels", action="store_true")
+    ap.add_argument("--roofline-seconds", type=float, default=2.6,
+                    help="minimum duration of the event-bracketed GEMM roofline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-vit", action="store_true")
@@ -144,23 +150,25 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(build_cpu_reference(args.backbone), args.cpu_sample_images)
+    n_img = args.cpu_sample_images or args.batch
+    step = cpu_step_fn(build_cpu_reference(args.backbone), n_img)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = args.cpu_sample_images * args.steps / dt
-    sample = (f"{args.cpu_sample_images} images per step (fwd + bwd + AdamW, text tower recomputed each "
-              f"step), {args.steps} steps, PyTorch fp32, {torch.get_num_threads()} threads")
+    value = n_img * args.steps / dt
+    sample = (f"{n_img} images per step = the stated batch (fwd + bwd + AdamW, text tower recomputed each "
+              f"step), {args.steps} steps, PyTorch fp32, {torch.get_num_threads()} threads; oracle port "
+              "(the reference is pure Python on an un-vendored CLIP: there is no reference binary to build)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": sample},
+                         "sample": sample, "sample_batch": n_img},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -323,6 +331,51 @@ def measure_sweep(args, device, world):
             "reference_baseline": "1.52 conditions/h, 43.5 s/epoch on one unnamed GPU (BASELINE.md, derived)"}
 
 
+def measure_sweep_scheduler(args, world, rank, dist):
+    """BASELINE.json configs[3] (the variable-length perturbation grid) through the scheduler: rank 0 runs
+    tools/grid_sweep_bench.py (hba.sweep.run_sweep over GPUs 0..world-1, `--sweep-per-gpu` grid conditions per GPU
+    taken longest-first from the conditions that start at epoch <= 10: weak scaling) while the other ranks
+    wait on the rendezvous store, their GPUs idle.  conditions/hour = conditions / wall clock from the first
+    worker spawn to the last result (worker start-up, cache fill, graph capture and every file included)."""
+    import tempfile
+    from datetime import timedelta
+    key = "hba_sweep_slice_done"
+    store = None
+    if dist is not None:
+        from torch.distributed import distributed_c10d
+        store = distributed_c10d._get_default_store()
+        dist.barrier()
+    if rank != 0:
+        store.wait([key], timedelta(seconds=1800))   # CPU-side wait: no NCCL kernel spins on this GPU meanwhile
+        return None
+    res = {}
+    try:
+        out_path = os.path.join(tempfile.mkdtemp(prefix="hba_sched_"), "slice.json")
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK",
+                            "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE", "TORCHELASTIC_RUN_ID",
+                            "HBA_STEP_GRAPH", "HBA_TEXT_STREAM")}
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "grid_sweep_bench.py"), "--kind", "grid",
+               "--gpus", ",".join(str(i) for i in range(world)), "--per-gpu", str(args.sweep_per_gpu),
+               "--max-start", "10", "--batch-size", str(args.batch), "--backbone", args.backbone,
+               "--root", tempfile.mkdtemp(prefix="hba_grid_"), "--out", out_path]
+        t0 = time.perf_counter()
+        proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+        if os.path.exists(out_path):
+            full = json.load(open(out_path))
+            res = {k: v for k, v in full.items() if k != "per_condition"}
+            res["unit"] = "conditions/h"
+            res["epochs_per_condition"] = [c["epochs_trained"] for c in full["per_condition"]]
+            res["tool_wall_s"] = time.perf_counter() - t0
+        if proc.returncode != 0:
+            res["error"] = (proc.stderr or proc.stdout)[-400:]
+    except Exception as exc:
+        res["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    if store is not None:
+        store.set(key, "1")
+    return res
+
+
 def measure_vit(args, device, world, dist):
     """BASELINE.json configs[2]: ViT-B/16 classification training, data parallel (VIT = Training/
     vit_training/baseline/train_vit_sgd.py): batch 256 per GPU, synthetic 224^2 images / 1000 classes,
@@ -363,10 +416,13 @@ def measure_vit(args, device, world, dist):
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["bf16_tflops_sustained"] if os.path.exists(peaks_path) else 1400.0
     tflops = value / world * 105.3e9 / 1e12   # 3 x 35.1 GFLOP per image
+    loss_val, n_launch = float(loss), ops.COUNTERS["launches"] - c0
+    tr.close()
+    del tr, model
     return {"metric": "ViT-B/16 train imgs/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "ms_per_step": ms / steps, "scaling": "weak", "dtype": "bf16", "global_batch": batch * world,
             "parallelism": f"dp{world}: batch {batch}/GPU, NCCL gradient all-reduce per block bucket, CUDA-graph step",
-            "loss": float(loss), "gpu_launches": ops.COUNTERS["launches"] - c0,
+            "loss": loss_val, "gpu_launches": n_launch,
             "algorithmic_tflops_per_gpu": tflops, "frac_of_sustained_bf16_peak": tflops / peak}
 
 
@@ -485,7 +541,14 @@ def main():
     # (and with the text tower on the main stream: overlapped kernels would stretch each other's events)
     os.environ["HBA_STEP_GRAPH"] = "0"
     os.environ["HBA_TEXT_STREAM"] = "0"
-    ms_eager, _, prof = timed(step_resident, args.steps, profile_gemm=True)
+    ms_probe, _, _ = timed(step_resident, 3)
+    # long enough (>= --roofline-seconds) for the clocks to settle where a training run keeps them: the
+    # denominator is then MEASURED_PEAKS' sustained figure; the burst fraction is reported beside it
+    roof_steps = max(args.steps, int(args.roofline_seconds * 1e3 / (ms_probe / 3)) + 1)
+    roof_sampler = ClockSampler(local)
+    roof_sampler.start()
+    ms_eager, _, prof = timed(step_resident, roof_steps, profile_gemm=True)
+    roof_clocks = roof_sampler.stop()
     os.environ.pop("HBA_STEP_GRAPH")
     # the kernel's SHARE of the step: every libhba launch of a few host-launched steps bracketed by events the
     # same way (numerator and denominator then carry the same launch-latency bias)
@@ -512,16 +575,20 @@ def main():
     gemm_ms = sum(a.elapsed_time(b) for (M, N, K, ns, a, b) in prof)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        pk = json.load(open(peaks_path))
+        peak, peak_burst = pk["bf16_tflops_sustained"], pk["bf16_tflops"]
+        peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: the roofline pass runs "
+                    f"{ms_eager / 1e3:.1f} s back to back)")
     else:
-        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+        peak, peak_burst = 1400.0, 1650.0
+        peak_src = "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     shapes = {}
     for (M, N, K, ns, a, b) in prof:
         e = shapes.setdefault((M, N, K), [0, 0.0])
         e[0] += 1
         e[1] += a.elapsed_time(b)
-    by_shape = [{"M": M, "N": N, "K": K, "launches_per_step": n / args.steps, "us_per_launch": 1e3 * t / n,
+    by_shape = [{"M": M, "N": N, "K": K, "launches_per_step": n / roof_steps, "us_per_launch": 1e3 * t / n,
                  "tflops": 2.0 * M * N * K * n / (t / 1e3) / 1e12}
                 for (M, N, K), (n, t) in sorted(shapes.items(), key=lambda kv: -kv[1][1])][:12]
     traffic = None
@@ -543,19 +610,54 @@ def main():
         "gpu_launches": launches, "loss": loss_val, "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "gemm_launches_per_step": len(prof) / args.steps,
-                     "gemm_flops_per_step": flops / args.steps,
-                     "gemm_ms_per_step": gemm_ms / args.steps,
+                     "peak_source": peak_src, "peak_burst": peak_burst, "frac_of_burst_peak": achieved / peak_burst,
+                     "pass_seconds": ms_eager / 1e3, "pass_steps": roof_steps, "pass_clocks": roof_clocks,
+                     "gemm_launches_per_step": len(prof) / roof_steps,
+                     "gemm_flops_per_step": flops / roof_steps,
+                     "gemm_ms_per_step": gemm_ms / roof_steps,
                      "gemm_share_of_step": per_entry.get("hba_gemm_bf16", 0.0) / all_ms,
-                     "kernel_time_shares": shares, "eager_ms_per_step": ms_eager / args.steps,
-                     "how": "CUDA events around every gemm_tc_kernel launch over K host-launched, single-stream steps "
-                            "of the same workload, run right after the timed region (which replays the step as a "
+                     "kernel_time_shares": shares, "eager_ms_per_step": ms_eager / roof_steps,
+                     "how": "CUDA events around every gemm_tc_kernel launch over pass_steps host-launched, single-stream "
+                            "steps of the same workload, run right after the timed region (which replays the step as a "
                             "CUDA graph with the text tower on a parallel branch); shares = event time per C-ABI entry "
                             "point / event time of all libhba launches of 3 further host-launched steps",
                      "by_shape": by_shape},
     }
     out["host_cpus"] = os.cpu_count()
     # The secondary sections must never cost the headline line: a failure is recorded and reported.
+    if not args.no_fp32 and args.precision == "bf16":
+        # the parity mode (three bf16 passes per GEMM, fp32 attention: 1e-3 of the fp32 reference) on the same
+        # workload, through the same TrainStep - reported beside the bf16 headline
+        try:
+            hba.set_precision("fp32")
+            train_step.start_epoch()      # restages the frozen weights as hi/lo operands (as every epoch start does)
+            for _ in range(3):
+                step_resident()
+            n32 = max(3, min(args.steps, 10))
+            ms32, _, _ = timed(step_resident, n32)
+            out["fp32_mode"] = {"value": world * B * n32 / (ms32 / 1e3), "unit": UNIT, "ms_per_step": ms32 / n32,
+                                "steps": n32, "loss": float(train_step.last_loss),
+                                "what": "hba.set_precision('fp32'): 3 bf16 passes per GEMM over hi/lo split operands, "
+                                        "exact fp32 attention / LayerNorm / residual"}
+        except Exception as exc:
+            out["fp32_mode"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        finally:
+            hba.set_precision(args.precision)
+            train_step.start_epoch()
+    if not args.no_hbm_kernels and rank == 0:
+        # north star item 3: the bandwidth-bound kernels against the measured HBM peak (CUDA events, L2 flushed)
+        try:
+            from tools import bench_kernels
+            hk = bench_kernels.measure(device, reps=7, with_cpu=False)
+            out["roofline_hbm"] = {"peak": hk["peak_hbm_gbs"], "unit": "GB/s", "timing": hk["timing"],
+                                   "empty_launch_us": hk.get("empty_launch_us"),
+                                   "kernels": [{"kernel": k, "us": 1e3 * v["ms"], "bytes": v["algorithmic_bytes"],
+                                                "achieved": v["achieved_gbs"], "frac": v["frac_of_measured_peak"],
+                                                "us_in_stream": 1e3 * v["ms_in_stream"] if "ms_in_stream" in v else None,
+                                                "frac_in_stream": v.get("frac_of_measured_peak_in_stream")}
+                                               for k, v in hk["kernels"].items()]}
+        except Exception as exc:
+            out["roofline_hbm"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if not args.no_sweep:
         del model, opt, train_step
         torch.cuda.empty_cache()
@@ -572,6 +674,16 @@ def main():
                                            + (EPOCHS_PER_CONDITION - 2) * float(t))
                 sw["conditions_per_hour"] = world * 3600.0 / sw["sec_per_condition"]
                 sw["blended_images_per_s"] = world * sw["images_per_epoch"] / float(t)
+        # The number that counts: a slice of the 136-condition grid run FOR REAL through the scheduler
+        # (hba.sweep.run_sweep: one pinned worker process per GPU, LPT queue, every condition trained until
+        # the reference's early stopping ends it, all files written).  `steady_state_replica` keeps the
+        # in-process epoch timing above as the explanation of where the time goes.
+        torch.cuda.empty_cache()
+        sched = measure_sweep_scheduler(args, world, rank, dist)
+        if rank == 0:
+            steady = sw
+            sw = dict(sched)
+            sw["steady_state_replica"] = steady
         out["sweep"] = sw
     if not args.no_vit:
         import gc
@@ -584,7 +696,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        n = args.cpu_sample_images
+        n = args.cpu_sample_images or args.batch
         step = cpu_step_fn(build_cpu_reference(args.backbone), n)
         step()  # warm-up (allocations, thread pool)
         t0 = time.perf_counter()
@@ -593,9 +705,9 @@ def main():
             step()
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(),
-                               "kind": "port",
-                               "sample": f"{reps} training steps of {n} images (same model, fwd+bwd+AdamW, "
-                                         "text tower recomputed), oracle port in PyTorch fp32"}
+                               "kind": "port", "sample_batch": n,
+                               "sample": f"{reps} training steps of {n} images = the stated batch (same model, "
+                                         "fwd+bwd+AdamW, text tower recomputed), oracle port in PyTorch fp32"}
         # BASELINE.md 3 "also report": the same oracle port run by PyTorch eager ON THIS B200 (library
         # kernels: cuBLAS / SDPA), fp32 and bf16 autocast, full batch - the bar a user of the reference
         # would get from `model.to('cuda')` alone.  A reported baseline, never part of the product path.
@@ -607,11 +719,20 @@ def main():
         print(json.dumps(out))
     sys.stdout.flush()
     if dist is not None:
-        if not args.no_vit:
-            # captured graphs hold NCCL kernels of the communicator; tearing the group down with live
-            # graphs hung the ranks at exit (observed at N=2): leave without the teardown
-            os._exit(0)
+        # (measure_vit closed its trainer: the captured graphs that held NCCL kernels of the communicator are
+        # gone before the group is torn down.  The watchdog only guards the driver's run against a teardown hang.)
+        done = threading.Event()
+
+        def _watchdog():
+            if not done.wait(60):
+                sys.stderr.write("bench.py: destroy_process_group did not return within 60 s; leaving\n")
+                sys.stderr.flush()
+                os._exit(0)
+        threading.Thread(target=_watchdog, daemon=True).start()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        done.set()
 
 
 if __name__ == "__main__":

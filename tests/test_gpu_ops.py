@@ -121,6 +121,48 @@ def test_gemm_epilogues(split):
     assert float(outT[:, M:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,N,K,slices", [(32, 1024, 4096, 8), (66, 768, 3072, 6), (66, 3072, 768, 3), (32, 768, 1024, 4)])
+@pytest.mark.parametrize("split", [False, True])
+def test_gemm_skinny_split_k_with_fused_epilogue(M, N, K, slices, split):
+    """Row GEMMs (CLS / EOT rows) split along K: the slices write fp32 partial sums and the slice reduction runs the
+    GEMM's own epilogue (bias, pre-activation output, QuickGELU / its gradient, residual, fp32 + bf16 hi/lo outputs).
+    Same results as the unsplit kernel up to fp32 re-association, identical from run to run."""
+    hba, ops, ref = _imports()
+    from hba._lib import HBA_ACT_QUICKGELU, HBA_ACT_QUICKGELU_GRAD
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    bias, res = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    aux = torch.randn(M, N, generator=g).to(DEV).to(torch.bfloat16)
+    A, B = make_operand(ops, a, split), make_operand(ops, b, split)
+    base = (operand_value(A) @ operand_value(B).t()) if not split else a.double() @ b.double().t()
+    tol = 3e-5
+    ws = torch.empty(slices * M * N, device=DEV)
+    z = base + bias.double()
+    # bias + QuickGELU + residual -> fp32 and bf16 outputs, pre-activation saved (bf16)
+    out, out1 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    outb = ops.Operand.empty(max(M, 128), N, split, DEV)
+    ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=out, out=outb, pre_out=pre,
+             k_slices=slices, k_workspace=ws)
+    want = z * torch.sigmoid(1.702 * z) + res.double()
+    assert rel_err(out, want) < tol
+    assert rel_err(pre.float(), z) < 5e-3
+    assert rel_err(operand_value(outb)[:M], want) < (2e-5 if split else 5e-3)
+    ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=out1)      # unsplit kernel
+    assert rel_err(out, out1) < 1e-5
+    out2 = torch.empty(M, N, device=DEV)
+    ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=out2, k_slices=slices, k_workspace=ws)
+    assert torch.equal(out, out2)                                                         # fixed-order reduction
+    # activation gradient with a bf16 pre-activation, bf16-only output
+    gh = ops.Operand.empty(max(M, 128), N, split, DEV)
+    ops.gemm(A, B, M, act=HBA_ACT_QUICKGELU_GRAD, aux=aux, out=gh, k_slices=slices, k_workspace=ws)
+    s_ = torch.sigmoid(1.702 * aux.double())
+    assert rel_err(operand_value(gh)[:M], base * (s_ * (1 + 1.702 * aux.double() * (1 - s_)))) < (2e-5 if split else 5e-3)
+    # "auto" picks a split for these shapes
+    assert ops.auto_k_slices(M, N, K, min_kblocks=4) > 1
+
+
 def test_gemm_errors():
     hba, ops, ref = _imports()
     a = ops.Operand.empty(64, 96, False, DEV)

@@ -460,6 +460,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (HBA_PDL): everything above - barrier init, TMEM allocation, descriptor
+  // prefetch, the cluster rendezvous - touches no global memory and may run while the PRECEDING kernel of the
+  // stream is still draining its last tiles; the wait returns once that kernel has completed and flushed.
+  // launch_dependents lets the NEXT kernel's CTAs do the same on SMs as this grid's CTAs retire.  Both are
+  // no-ops when the kernel was launched without the programmatic attribute.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_m_tiles = (g.M + TM - 1) / TM;
   const int num_n_tiles = (g.N + BN - 1) / BN;
@@ -642,20 +649,79 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-// out[r, c] = sum_s part[s][r, c]  (split-K reduction, fixed order: deterministic)
-__global__ void __launch_bounds__(256)
-    splitk_reduce_kernel(const float* __restrict__ part, size_t slice_stride, int slices, int rows, int cols,
-                         int ld, float* __restrict__ out, int ld_out) {
-  const int c4 = cols >> 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows * c4;
+// out[r, c] = epilogue(sum_s part[s][r, c])  (split-K reduction, fixed order: deterministic).  The epilogue is
+// the GEMM's own (bias -> pre-activation output -> activation / activation gradient -> residual -> fp32 / bf16
+// hi[/lo] outputs): skinny problems (the CLS / EOT row GEMMs, M = 32 / 66: 3..16 output tiles for 74 CTA pairs,
+// each streaming the whole K extent of its weight columns through ONE SM pair) are split along K so that the weight
+// matrix is pulled by many SMs at once, and finished here.
+struct ReduceArgs {
+  const float* part;
+  size_t slice_stride;
+  int slices, rows, cols, ld;
+  const float* bias;
+  const float* residual;
+  int ldr;
+  int act;
+  const void* aux;
+  int ld_aux, aux_dtype;
+  void* pre_out;
+  int ld_pre, pre_dtype;
+  float* out_f32;
+  int ld_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_bf16, out_lo_off;
+};
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) {
+  const int c4 = a.cols >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)a.rows * c4;
        i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / c4), c = (int)(i % c4) * 4;
-    float4 acc = *reinterpret_cast<const float4*>(part + (size_t)r * ld + c);
-    for (int s = 1; s < slices; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(part + s * slice_stride + (size_t)r * ld + c);
+    float4 acc = *reinterpret_cast<const float4*>(a.part + (size_t)r * a.ld + c);
+    for (int s = 1; s < a.slices; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(a.part + s * a.slice_stride + (size_t)r * a.ld + c);
       acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
-    *reinterpret_cast<float4*>(out + (size_t)r * ld_out + c) = acc;
+    Vec4 v = {{acc.x, acc.y, acc.z, acc.w}};
+    if (a.bias) {
+      const Vec4 b = ld4_f32(a.bias + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.x[e] += b.x[e];
+    }
+    if (a.pre_out) {
+      if (a.pre_dtype == HBA_DT_F32) st4_f32(static_cast<float*>(a.pre_out) + (size_t)r * a.ld_pre + c, v);
+      else st4_bf16(static_cast<__nv_bfloat16*>(a.pre_out) + (size_t)r * a.ld_pre + c, v);
+    }
+    if (a.act != HBA_ACT_NONE) {
+      Vec4 x = {{0.f, 0.f, 0.f, 0.f}};
+      if (a.aux) {
+        if (a.aux_dtype == HBA_DT_F32) {
+          const float* p = static_cast<const float*>(a.aux) + (size_t)r * a.ld_aux + c;
+          x = Vec4{{__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)}};
+        } else {
+          const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(a.aux) + (size_t)r * a.ld_aux + c;
+          x = Vec4{{__bfloat162float(p[0]), __bfloat162float(p[1]), __bfloat162float(p[2]), __bfloat162float(p[3])}};
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.x[e] = act_runtime(a.act, v.x[e], x.x[e]);
+    }
+    if (a.residual) {
+      const Vec4 q = ld4_f32(a.residual + (size_t)r * a.ldr + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.x[e] += q.x[e];
+    }
+    if (a.out_f32) st4_f32(a.out_f32 + (size_t)r * a.ld_f32 + c, v);
+    if (a.out_bf16) {
+      __nv_bfloat16* p = a.out_bf16 + (size_t)r * a.ld_bf16 + c;
+      st4_bf16(p, v);
+      if (a.out_lo_off > 0) {
+        Vec4 l;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l.x[e] = v.x[e] - __bfloat162float(__float2bfloat16_rn(v.x[e]));
+        st4_bf16(p + a.out_lo_off, l);
+      }
+    }
   }
 }
 
@@ -668,6 +734,51 @@ static int gemm_cta_group() {
   return cg;
 }
 
+// Encoding a CUtensorMap costs ~1 us of host time (cuTensorMapEncodeTiled) and every GEMM launch needs two; the
+// operands of a training step are the same few hundred (pointer, shape, stride, box) tuples step after step, so
+// the encoded descriptors are kept in a small direct-mapped, per-thread cache.  A descriptor depends on nothing but
+// those six numbers (no device or context state), so a stale entry is impossible: equal key = equal descriptor.
+struct TmaKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmaKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols;
+  }
+};
+static int cached_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                              uint32_t box_rows, uint32_t box_cols) {
+  constexpr int kSlots = 1024;
+  struct Slot {
+    TmaKey key;
+    CUtensorMap map;
+    bool valid;
+  };
+  static thread_local Slot* slots = nullptr;
+  if (!slots) slots = new Slot[kSlots]();
+  const TmaKey key{ptr, rows, cols, ld, box_rows, box_cols};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols << 21) ^ (ld << 7) ^ ((uint64_t)box_rows << 40) ^ box_cols;
+  Slot& sl = slots[(h >> 32) % kSlots];
+  if (sl.valid && sl.key == key) {
+    *map = sl.map;
+    return HBA_OK;
+  }
+  HBA_CHECK(make_tma_2d_bf16(map, ptr, rows, cols, ld, box_rows, box_cols));
+  sl.key = key, sl.map = *map, sl.valid = true;
+  return HBA_OK;
+}
+
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HBA_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 template <int BN, int CG, int ACT>
 static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
@@ -678,16 +789,16 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   const uint64_t b_cols = (uint64_t)p->K + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
   CUtensorMap ta, tb;
   if (!p->a_mn_major) {
-    HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->M, a_cols, p->lda, BM, BK));
+    HBA_CHECK(cached_tma_2d_bf16(&ta, p->A, p->M, a_cols, p->lda, BM, BK));
   } else {
     const uint64_t cols = (uint64_t)p->M + (p->nsplit == 3 ? (uint64_t)p->a_lo_off : 0);
-    HBA_CHECK(make_tma_2d_bf16(&ta, p->A, p->K, cols, p->lda, 64, 64));
+    HBA_CHECK(cached_tma_2d_bf16(&ta, p->A, p->K, cols, p->lda, 64, 64));
   }
   if (!p->b_mn_major) {
-    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BNC, BK));
+    HBA_CHECK(cached_tma_2d_bf16(&tb, p->B, p->N, b_cols, p->ldb, BNC, BK));
   } else {
     const uint64_t cols = (uint64_t)p->N + (p->nsplit == 3 ? (uint64_t)p->b_lo_off : 0);
-    HBA_CHECK(make_tma_2d_bf16(&tb, p->B, p->K, cols, p->ldb, 64, 64));
+    HBA_CHECK(cached_tma_2d_bf16(&tb, p->B, p->K, cols, p->ldb, 64, 64));
   }
   const int tiles = ((p->M + BM * CG - 1) / (BM * CG)) * ((p->N + BN - 1) / BN);
   int workers = num_sms() / CG;
@@ -698,13 +809,18 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, ACT>, ta, tb, g);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -770,17 +886,27 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
   const int kblocks_total = (p->K + BK - 1) / BK;
   int slices = p->k_slices > 1 ? p->k_slices : 1;
   if (slices > kblocks_total) slices = kblocks_total;
+  ReduceArgs red = {};
   if (slices > 1) {
-    HBA_REQUIRE(p->k_workspace && p->out_f32 && !p->out_bf16 && !p->pre_out && !p->bias && !p->residual &&
-                    p->act == HBA_ACT_NONE && !p->transpose_out && p->N % 4 == 0,
-                "hba_gemm_bf16: split-K (k_slices=%d) needs k_workspace, N %% 4 == 0 and a plain out_f32 epilogue",
-                p->k_slices);
+    HBA_REQUIRE(p->k_workspace && !p->transpose_out && !p->colsum_partial && p->N % 4 == 0,
+                "hba_gemm_bf16: split-K (k_slices=%d) needs k_workspace, N %% 4 == 0 and no transposed / column-sum "
+                "output", p->k_slices);
     HBA_REQUIRE(((uintptr_t)p->k_workspace & 15) == 0, "hba_gemm_bf16: k_workspace must be 16-byte aligned");
     // every slice must own at least one k-block
     const int kb_per = (kblocks_total + slices - 1) / slices;
     slices = (kblocks_total + kb_per - 1) / kb_per;
     g.k_slices = slices;
     g.slice_stride = (size_t)p->M * p->N;
+    // the slices write plain fp32 partial sums (alpha applied); the epilogue proper runs in the reduction
+    red.part = p->k_workspace, red.slice_stride = g.slice_stride, red.slices = slices;
+    red.rows = p->M, red.cols = p->N, red.ld = p->N;
+    red.bias = g.bias, red.residual = g.residual, red.ldr = g.ldr;
+    red.act = g.act, red.aux = g.aux, red.ld_aux = g.ld_aux, red.aux_dtype = g.aux_dtype;
+    red.pre_out = g.pre_out, red.ld_pre = g.ld_pre, red.pre_dtype = g.pre_dtype;
+    red.out_f32 = g.out_f32, red.ld_f32 = g.ld_f32;
+    red.out_bf16 = g.out_bf16, red.ld_bf16 = g.ld_bf16, red.out_lo_off = g.out_lo_off;
+    g.bias = nullptr, g.residual = nullptr, g.act = HBA_ACT_NONE, g.aux = nullptr, g.pre_out = nullptr;
+    g.out_bf16 = nullptr, g.out_lo_off = 0;
     g.out_f32 = p->k_workspace;
     g.ld_f32 = p->N;
   }
@@ -800,8 +926,7 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
     const size_t n4 = (size_t)p->M * (p->N / 4);
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p->k_workspace, g.slice_stride, g.k_slices, p->M, p->N, p->N,
-                                                p->out_f32, p->ld_f32);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(red);
     return check_launch("splitk_reduce_kernel");
   }
   if (gemm_cta_group() == 2) {

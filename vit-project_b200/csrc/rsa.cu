@@ -21,10 +21,14 @@ namespace hba {
 // ------------------------------------------------------------------------------------------
 // double -> uint64 whose unsigned order equals the numeric order (-0.0 canonicalised to +0.0);
 // every NaN sorts above +inf
+// (integer arithmetic on the two 32-bit halves: nvcc turns `bits | sign` on a reinterpreted double into the
+// floating-point negation DADD -|x|, which returns the canonical NaN without the flipped sign bit)
 __device__ __forceinline__ unsigned long long f64_to_key(double x) {
   x = x + 0.0;
-  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int neg = hi >> 31;   // all ones for a negative value
+  const unsigned int khi = (unsigned int)(hi ^ (neg | (int)0x80000000)), klo = (unsigned int)(lo ^ neg);
+  return ((unsigned long long)khi << 32) | klo;
 }
 constexpr unsigned long long kKeyPosInf = 0xFFF0000000000000ull;  // f64_to_key(+inf); NaN keys are larger
 // (a negative-signed NaN maps below -inf: keys < f64_to_key(-inf) = 0x000FFFFFFFFFFFFF)

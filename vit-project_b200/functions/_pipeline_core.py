@@ -469,11 +469,17 @@ class _CachedForwardGraphs:
                 and getattr(loader, "last_ids_dev", None) is not None and not torch.is_grad_enabled()
                 and eng.trunk_cache.x is not None and eng.trunk_cache.all_present(loader.last_ids, eng))
 
-    def loss_total(self):
-        """float64 device scalar that the fused-MSE evaluation batches accumulate loss * batch into."""
+    def loss_total(self, device=None):
+        """float64 device scalar that the fused-MSE evaluation batches accumulate loss * batch into.
+        (`device`: where the batches live - the engine has no device before its first forward pass.)"""
+        dev = torch.device(device) if device is not None else self.eng.device
+        if dev is None:
+            raise RuntimeError("loss_total: no device yet (pass the device of the evaluation batches)")
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         t = self.__dict__.get("_loss_total")
-        if t is None or t.device != self.eng.device:
-            t = self.__dict__["_loss_total"] = torch.zeros((), device=self.eng.device, dtype=torch.float64)
+        if t is None or t.device != dev:
+            t = self.__dict__["_loss_total"] = torch.zeros((), device=dev, dtype=torch.float64)
         return t
 
     def __call__(self, images, ids_dev, targets=None):
@@ -490,7 +496,7 @@ class _CachedForwardGraphs:
             self.warm.add(key)
             eng.batch_ids = ids_dev
             if targets is not None:
-                eng.loss_request = LossRequest(targets.contiguous(), total=self.loss_total())
+                eng.loss_request = LossRequest(targets.contiguous(), total=self.loss_total(images.device))
             return self.model(images)
         entry = self.entries.get(key)
         if entry is None:
@@ -502,7 +508,7 @@ class _CachedForwardGraphs:
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 eng.batch_ids = s_ids
                 if s_tgt is not None:
-                    eng.loss_request = LossRequest(s_tgt, total=self.loss_total())
+                    eng.loss_request = LossRequest(s_tgt, total=self.loss_total(images.device))
                 out = self.model(s_img)
             entry = (graph, s_ids, s_tgt, out, ops.COUNTERS["launches"] - c0)
             ops.COUNTERS["launches"] = c0
@@ -530,8 +536,8 @@ def evaluate_model(model, data_loader, device, criterion):
             targets = targets.to(device, non_blocking=True)
             if fused_mse_ok(model, criterion, targets):
                 # MSE and the loss * batch accumulation run inside the head kernel (one launch)
-                if fwd.loss_total() is not total:
-                    total = fwd.loss_total()
+                if fwd.loss_total(images.device) is not total:
+                    total = fwd.loss_total(images.device)
                     total.zero_()
                 if fwd.usable(data_loader):
                     fwd(images, data_loader.last_ids_dev, targets)

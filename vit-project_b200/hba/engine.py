@@ -252,6 +252,18 @@ class Engine:
         self.launches += 2
         return w, wt
 
+    def _skinny(self, tag, R, N, K):
+        """Split-K arguments of a row GEMM (R = the CLS / EOT rows, one row tile): its N / 256 output tiles would
+        leave most of the 74 CTA pairs idle while a few SMs stream the whole weight matrix; split along K the
+        matrix is pulled by ~74 pairs at once and the epilogue runs in the slice reduction (same fused epilogue).
+        The workspace is per tag: the two towers run on different streams."""
+        if R > 256 or os.environ.get("HBA_SKINNY_SPLITK", "1") == "0":
+            return {}
+        s = ops.auto_k_slices(R, N, K, min_kblocks=4)
+        if s <= 1:
+            return {}
+        return {"k_slices": s, "k_workspace": self._buf(tag + ".kws", (s * R * N,))}
+
     def _block_full(self, tw, blk, tag, x_in, x_mid, x_out, B, w_out, b_out, keep=None):
         """One full residual attention block on all M = B*T rows (x_* are fp32 [M, d])."""
         a = self._attn_part(tw, blk, tag, x_in, B, keep.get("a_f32") if keep else None)
@@ -290,14 +302,15 @@ class Engine:
         rows (row stride arbitrary).  Returns x_out [R, d] fp32."""
         d = tw.d
         x_mid = keep["x_mid"] if keep else self._buf(tag + ".xmid", (R, d))
-        ops.gemm(a_rows, w_out, R, bias=b_out, residual=x_res, out_f32=x_mid)
+        ops.gemm(a_rows, w_out, R, bias=b_out, residual=x_res, out_f32=x_mid, **self._skinny(tag, R, d, d))
         h = self._opbuf(tag + ".h2", max(R, 128), d)
         ops.layernorm_fwd(x_mid, R, d, blk.ln2_w, blk.ln2_b, LN_EPS, y=h)
         hid = self._opbuf(tag + ".hid2", max(R, 128), 4 * d)
         ops.gemm(h, blk.w_fc, R, bias=blk.b_fc, act=HBA_ACT_QUICKGELU, out=hid,
-                 pre_out=keep["h_pre"] if keep else None)
+                 pre_out=keep["h_pre"] if keep else None, **self._skinny(tag, R, 4 * d, d))
         x_out = keep["x_out"] if keep else self._buf(tag + ".xout", (R, d))
-        ops.gemm(hid, blk.w_proj, R, bias=blk.b_proj, residual=x_mid, out_f32=x_out)
+        ops.gemm(hid, blk.w_proj, R, bias=blk.b_proj, residual=x_mid, out_f32=x_out,
+                 **self._skinny(tag, R, d, 4 * d))
         self.launches += 4
         return x_out
 
@@ -411,7 +424,7 @@ class Engine:
         hp = self._opbuf("v.lnpost", max(B, 128), d)
         ops.layernorm_fwd(x_out, B, d, self.ln_post[0], self.ln_post[1], LN_EPS, y=hp)
         feat = self._keep("imgfeat", (B, self.E))
-        ops.gemm(hp, self.proj_t, B, out_f32=feat)
+        ops.gemm(hp, self.proj_t, B, out_f32=feat, **self._skinny("v", B, self.E, d))
         self.launches += 4
         saved.update(trainZ=trainZ, keepZ=keepZ, qkvZ=qkv)
         return feat, saved
@@ -473,7 +486,7 @@ class Engine:
         hp = self._opbuf("t.lnfinal", max(S, 128), d)
         ops.layernorm_fwd(x_out, S, d, self.ln_final[0], self.ln_final[1], LN_EPS, y=hp)
         feat = self._keep("txtfeat", (S, self.E))
-        ops.gemm(hp, self.tproj_t, S, out_f32=feat)
+        ops.gemm(hp, self.tproj_t, S, out_f32=feat, **self._skinny("t", S, self.E, d))
         self.launches += 2
         return feat, {"S": S, "trainZ": trainZ, "keepZ": keepZ}
 
@@ -562,9 +575,9 @@ class Engine:
         """dxo [R, d] holds dL/dx_out; on return it holds dL/dx_mid (MLP + LN2 + residual)."""
         g1 = self._grad_operand(tag + ".g1", dxo, R, d)
         gh = self._opbuf(tag + ".gh", max(R, 128), 4 * d)
-        ops.gemm(g1, blk.w_proj_t, R, act=HBA_ACT_QUICKGELU_GRAD, aux=h_pre, out=gh)
+        ops.gemm(g1, blk.w_proj_t, R, act=HBA_ACT_QUICKGELU_GRAD, aux=h_pre, out=gh, **self._skinny(tag, R, 4 * d, d))
         d_ln2 = self._buf(tag + ".dln2", (R, d))
-        ops.gemm(gh, blk.w_fc_t, R, out_f32=d_ln2)
+        ops.gemm(gh, blk.w_fc_t, R, out_f32=d_ln2, **self._skinny(tag, R, d, 4 * d))
         ops.layernorm_bwd(d_ln2, x_mid, R, d, blk.ln2_w, LN_EPS, dxo, accumulate=True)
         self.launches += 3
 
@@ -612,7 +625,7 @@ class Engine:
             blk, kz = tw.blocks[L - 1], st["keepZ"]
             g = self._grad_operand("tb.g0", d_txt, S, E)
             d_lnf = self._buf("tb.dlnf", (S, d))
-            ops.gemm(g, self.tproj_n, S, out_f32=d_lnf)
+            ops.gemm(g, self.tproj_n, S, out_f32=d_lnf, **self._skinny("tb", S, d, E))
             dxo = self._buf("tb.dxo", (S, d))
             ops.layernorm_bwd(d_lnf, kz["x_out"], S, d, self.ln_final[0], LN_EPS, dxo)
             self.launches += 2
@@ -627,7 +640,7 @@ class Engine:
             blkZ, kz = tw.blocks[L - 1], sv["keepZ"]
             g = self._grad_operand("vb.g0", d_img, B, E)
             d_lnp = self._buf("vb.dlnp", (B, d))
-            ops.gemm(g, self.proj_n, B, out_f32=d_lnp)
+            ops.gemm(g, self.proj_n, B, out_f32=d_lnp, **self._skinny("vb", B, d, E))
             dxo = self._buf("vb.dxo", (B, d))
             ops.layernorm_bwd(d_lnp, kz["x_out"], B, d, self.ln_post[0], LN_EPS, dxo)
             self.launches += 2
@@ -639,7 +652,7 @@ class Engine:
                 wtZ = kz["wtZ"] if kz["wtZ"] is not None else self._frozen_wt(blkZ)
                 g2 = self._grad_operand("vb.g2", dxo, B, d)
                 d_a = self._buf("vb.da", (B, d))
-                ops.gemm(g2, wtZ, B, out_f32=d_a)
+                ops.gemm(g2, wtZ, B, out_f32=d_a, **self._skinny("vb", B, d, d))
                 d_qkv = self._buf("vb.dqkv", (M, 3 * d))
                 ops.attention_bwd_row0(sv["qkvZ"], B, T, H, d_a, d_qkv)
                 gq = self._grad_operand("vb.gq", d_qkv, M, 3 * d)

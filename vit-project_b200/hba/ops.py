@@ -128,14 +128,15 @@ class Operand:
         return Operand(self.buf.narrow(0, start, n), n, self.K, self.lo_off)
 
 
-def auto_k_slices(M, N, K, workers=74, max_slices=16):
-    """Split-K factor for a weight-gradient GEMM: minimises rounds-of-work-items / slices (the time of
-    the persistent kernel in units of one full-K tile) plus a small per-slice epilogue / reduction cost."""
+def auto_k_slices(M, N, K, workers=74, max_slices=16, min_kblocks=8):
+    """Split-K factor for a weight-gradient GEMM (or, with min_kblocks=4, a skinny row GEMM): minimises
+    rounds-of-work-items / slices (the time of the persistent kernel in units of one full-K tile) plus a small
+    per-slice epilogue / reduction cost."""
     tiles = -(-M // 256) * -(-N // (256 if N >= 256 else 128))
     kblocks = -(-K // 64)
     best, best_cost = 1, None
     for s in range(1, max_slices + 1):
-        if s > 1 and (kblocks // s < 8 or N % 4):
+        if s > 1 and (kblocks // s < min_kblocks or N % 4):
             break
         cost = -(-tiles * s // workers) / s + 0.02 * (s - 1)
         if best_cost is None or cost < best_cost - 1e-9:

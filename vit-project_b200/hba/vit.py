@@ -513,6 +513,20 @@ class DataParallelTrainer:
     def broadcast_parameters(self):
         self.reducer.broadcast_parameters(self.model.parameters())
 
+    def close(self):
+        """Releases the captured step graphs.  With world size > 1 they hold NCCL kernels of the process group's
+        communicator: `dist.destroy_process_group()` must not find them alive (it waited forever at N = 2), so
+        call this - on every rank - before tearing the group down.  The trainer stays usable (it recaptures)."""
+        import gc
+        self.reducer.wait()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self._graphs.clear()
+        self._static = None
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def step(self, images, labels):
         """One training step; returns (loss, top-1 hits) as device tensors.  With use_graph the step's
         ~400 launches (and the bucketed all-reduces) are captured once per (batch size, lr) into a CUDA
