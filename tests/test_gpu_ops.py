@@ -150,7 +150,7 @@ def test_gemm_skinny_split_k_with_fused_epilogue(M, N, K, slices, split):
     assert rel_err(pre.float(), z) < 5e-3
     assert rel_err(operand_value(outb)[:M], want) < (2e-5 if split else 5e-3)
     ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=out1)      # unsplit kernel
-    assert rel_err(out, out1) < 1e-5
+    assert rel_err(out, out1) < (4e-5 if split else 1e-5)   # fp32 mode: two bf16x3 evaluations, 2e-5 each
     out2 = torch.empty(M, N, device=DEV)
     ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=out2, k_slices=slices, k_workspace=ws)
     assert torch.equal(out, out2)                                                         # fixed-order reduction

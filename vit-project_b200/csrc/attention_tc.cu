@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the out_proj GEMM that follows may set itself up on SMs as this grid's CTAs retire
 
   // units of this CTA: u = blockIdx.x + n * gridDim.x, n = 0 .. my_units-1
   const int my_units = (g.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;

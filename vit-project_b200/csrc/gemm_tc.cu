@@ -774,7 +774,7 @@ static bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("HBA_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = (e && e[0] == '0') ? 0 : 1;
   }
   return on == 1;
 }

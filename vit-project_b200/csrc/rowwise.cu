@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(kLnsThreads, 1)
     *reinterpret_cast<float4*>(s_beta + c) = __ldg(reinterpret_cast<const float4*>(beta + c));
   }
   __syncthreads();
+  pdl_launch_dependents();   // the GEMM that consumes y may run its prologue while the last rows are normalised
   const uint32_t row_bytes = (uint32_t)cols * 4u;
   if (warp == kLnsRows) {
     if (lane == 0) {
