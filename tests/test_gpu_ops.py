@@ -163,6 +163,34 @@ def test_gemm_skinny_split_k_with_fused_epilogue(M, N, K, slices, split):
     assert ops.auto_k_slices(M, N, K, min_kblocks=4) > 1
 
 
+@pytest.mark.parametrize("M,N,K,even_ctas", [(8224, 3072, 1024, 132), (8224, 4096, 1024, 132), (5082, 3072, 768, 120),
+                                             (5082, 2304, 768, 120), (8224, 2000, 256, 88), (8224, 2904, 512, 132)])
+def test_gemm_tail_split_is_bit_identical(M, N, K, even_ctas):
+    """The partial last round of the persistent schedule is cut into 2 or 4 column slabs per tile (narrower UMMAs on
+    the same accumulator columns).  Every element still sums its K products in the same order, so the result equals -
+    bit for bit - a launch whose worker count divides the tile count (no partial round, nothing split), and the
+    fused epilogue (bias + QuickGELU + residual, fp32 + bf16 outputs) sees the same values."""
+    hba, ops, ref = _imports()
+    from hba._lib import HBA_ACT_QUICKGELU
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    bias, res = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    A, B = make_operand(ops, a, False), make_operand(ops, b, False)
+    tiles = -(-M // 256) * -(-N // 256)
+    assert tiles % 74 != 0 and tiles % (even_ctas // 2) == 0, "pick shapes with / without a partial round"
+    outs = []
+    for max_ctas in (0, even_ctas):
+        o32 = torch.full((M, N), float("nan"), device=DEV)
+        ob = ops.Operand.empty(M, N, False, DEV)
+        ops.gemm(A, B, M, bias=bias, act=HBA_ACT_QUICKGELU, residual=res, out_f32=o32, out=ob, max_ctas=max_ctas)
+        outs.append((o32, ob.buf.clone()))
+    assert torch.isfinite(outs[0][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    z = operand_value(A) @ operand_value(B).t() + bias.double()
+    assert rel_err(outs[0][0], z * torch.sigmoid(1.702 * z) + res.double()) < 3e-5
+
+
 def test_gemm_errors():
     hba, ops, ref = _imports()
     a = ops.Operand.empty(64, 96, False, DEV)

@@ -89,6 +89,9 @@ def main():
     ap.add_argument("--per-gpu", type=int, default=0, help="weak-scaling slice: N conditions per GPU")
     ap.add_argument("--max-start", type=int, default=0, help="only conditions whose start epoch is <= this")
     ap.add_argument("--chain", action="store_true")
+    ap.add_argument("--workers-per-gpu", type=int, default=1,
+                    help="worker processes per GPU (SURVEY N1: several conditions per GPU; they share the GPU by "
+                         "time slicing, or concurrently under an MPS daemon)")
     ap.add_argument("--backbone", default="ViT-L/14")
     ap.add_argument("--batch-size", type=int, default=32)
     ap.add_argument("--n-train", type=int, default=1806)
@@ -101,12 +104,13 @@ def main():
     os.environ.setdefault("HBA_SYNTHETIC_OK", "1")
     import multiprocessing as mp
     from hba import sweep
-    devices = [int(x) for x in a.gpus.split(",")]
+    gpus = [int(x) for x in a.gpus.split(",")]
+    devices = [g for g in gpus for _ in range(max(1, a.workers_per_gpu))]
     conds = sweep.length_grid_conditions() if a.kind == "grid" else sweep.single_epoch_conditions(1, 98)
     if a.max_start:
         conds = [c for c in conds if c["training_run"] <= a.max_start]
     conds = sweep.lpt_order(conds)
-    limit = a.per_gpu * len(devices) if a.per_gpu else a.limit
+    limit = a.per_gpu * len(gpus) if a.per_gpu else a.limit
     if limit:
         conds = conds[:limit]
     layout = "length" if a.kind == "grid" else "sweep"
@@ -170,10 +174,10 @@ def main():
                                                                                  c["perturb_length"]))).encode()
                                 ).hexdigest()[:16]
     out = {"metric": "perturbation sweep conditions/hour", "kind": a.kind, "layout": layout, "chain": bool(a.chain),
-           "n_gpus": len(devices), "conditions": len(conds), "ok": n_ok, "failed": len(conds) - n_ok,
+           "n_gpus": len(gpus), "workers_per_gpu": max(1, a.workers_per_gpu), "conditions": len(conds), "ok": n_ok, "failed": len(conds) - n_ok,
            "wall_s": wall, "conditions_per_hour": 3600.0 * n_ok / wall,
            "epochs_trained": epochs_total, "epochs_per_s": epochs_total / wall,
-           "sec_per_epoch_per_gpu": wall * len(devices) / max(1, epochs_total),
+           "sec_per_epoch_per_gpu": wall * len(gpus) / max(1, epochs_total),
            "worker_busy_s": {str(k): round(v, 2) for k, v in sorted(busy.items(), key=lambda kv: str(kv[0]))},
            "worker_startup_and_idle_s": round(wall - max(busy.values()), 2) if busy else None,
            "balance": (sum(busy.values()) / len(busy)) / max(busy.values()) if busy else None,

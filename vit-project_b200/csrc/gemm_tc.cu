@@ -83,6 +83,11 @@ struct GemmArgs {
   float* colsum;   // optional [ceil(M / 32), N]: column sums of the bf16 output per 32-row group
   int k_slices;    // split-K: work item = (tile, K slice); slice s writes out_f32 + s * slice_stride
   size_t slice_stride;
+  // tail splitting (k_slices == 1): tiles [tail_first, total) - the partial last round of the static schedule -
+  // are cut into tail_f column slabs of BN / tail_f columns, one work item each, so that the last round keeps
+  // ~all CTA pairs busy for 1 / tail_f of a tile time.  Every output element still accumulates its K products in
+  // the same order: results are bit-identical to the unsplit schedule.
+  int tail_first, tail_f;
   int debug;       // HBA_GEMM_DEBUG (measurement only): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA loads
 };
 
@@ -410,10 +415,30 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const GemmArgs& g, floa
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
+// work item -> (tile, K slice, first column inside the tile, width in columns)
+struct GemmItem {
+  int tile, slice, n_off, bn;
+};
+template <int BN>
+__device__ __forceinline__ GemmItem decode_item(const GemmArgs& g, int item, int total_tiles) {
+  GemmItem it;
+  if (g.tail_f > 1 && item >= g.tail_first) {
+    const int idx = item - g.tail_first;
+    it.bn = BN / g.tail_f;
+    it.tile = g.tail_first + idx / g.tail_f;
+    it.n_off = (idx % g.tail_f) * it.bn;
+    it.slice = 0;
+  } else {
+    it.tile = item % total_tiles, it.slice = item / total_tiles, it.n_off = 0, it.bn = BN;
+  }
+  return it;
+}
+
 template <int BN, int CG, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
-                   const __grid_constant__ CUtensorMap tma_b, const GemmArgs g) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_b4,
+                   const GemmArgs g) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BNC = BN / CG;   // rows of B this CTA stages per k-block
@@ -473,7 +498,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int total_tiles = num_m_tiles * num_n_tiles;
   const int kblocks = (g.K + BK - 1) / BK;  // a ragged last block is zero-filled by TMA
   // split-K: item = slice * total_tiles + tile; slice s covers k-blocks [s * kb_per, min(.., kblocks))
-  const int total_items = total_tiles * g.k_slices;
+  const int total_items = g.tail_f > 1 ? g.tail_first + (total_tiles - g.tail_first) * g.tail_f
+                                        : total_tiles * g.k_slices;
   const int kb_per = (kblocks + g.k_slices - 1) / g.k_slices;
 
   if (warp == 0) {
@@ -483,9 +509,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // where this CTA's TMA bytes are accounted: the pair leader's barriers
       const uint32_t full0 = (CG == 2) ? mapa_u32(&full_bar[0], 0) : smem_u32(&full_bar[0]);
       for (int item = worker; item < total_items; item += num_workers) {
-        const int tile = item % total_tiles, slice = item / total_tiles;
+        const GemmItem wi = decode_item<BN>(g, item, total_tiles);
+        const int tile = wi.tile, slice = wi.slice;
+        const int bnc = wi.bn / CG;   // rows of B this CTA stages for the item
         const int m0 = (tile / num_n_tiles) * TM + rank * BM;
-        const int n0 = (tile % num_n_tiles) * BN + rank * BNC;
+        const int n0 = (tile % num_n_tiles) * BN + wi.n_off + rank * bnc;
+        const CUtensorMap* tmb = wi.bn == BN ? &tma_b : (wi.bn * 2 == BN ? &tma_b2 : &tma_b4);
+        const uint32_t stage_bytes = (uint32_t)(CG * (Cfg::kABytes + bnc * BK * 2));
         const int kb_end = min(kblocks, (slice + 1) * kb_per);
         for (int kb = slice * kb_per; kb < kb_end; ++kb) {
           for (int s = 0; s < g.nsplit; ++s) {
@@ -503,7 +533,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const uint32_t fb = full0 + 8u * stage;
             if (elect_one()) {
             if (rank == 0)
-              mbar_arrive_expect_tx(&full_bar[stage], CG * (Cfg::kABytes + Cfg::kBBytes));
+              mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
             if (!g.a_mn) {
               tma_load<CG>(dA, &tma_a, fb, a_col, m0);
             } else {  // [K, M] storage: BM/64 boxes of 64 k-rows x 64 m-columns, 8 KB apart (LBO)
@@ -513,7 +543,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                              kb * BK);
             }
             if (!g.b_mn) {
-              tma_load<CG>(dB, &tma_b, fb, b_col, n0);
+              tma_load<CG>(dB, tmb, fb, b_col, n0);
             } else {
 #pragma unroll
               for (int j = 0; j < BNC / 64; ++j)
@@ -529,8 +559,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_bf16(TM, BN) | (g.a_mn ? (1u << 15) : 0u) |
-                             (g.b_mn ? (1u << 16) : 0u);
+      const uint32_t idesc_flags = (g.a_mn ? (1u << 15) : 0u) | (g.b_mn ? (1u << 16) : 0u);
       // K-major: +32 B per 16-element k-step inside the 128-byte swizzle row (start address += 2);
       // MN-major: 16 k-rows of 128 B further down (start address += 128)
       const uint32_t a_step = g.a_mn ? 128u : 2u, b_step = g.b_mn ? 128u : 2u;
@@ -540,7 +569,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = worker; item < total_items; item += num_workers) {
-        const int slice = item / total_tiles;
+        const GemmItem wi = decode_item<BN>(g, item, total_tiles);
+        const int slice = wi.slice;
+        const uint32_t idesc = make_idesc_bf16(TM, wi.bn) | idesc_flags;
         const int kiters = (min(kblocks, (slice + 1) * kb_per) - slice * kb_per) * g.nsplit;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -580,7 +611,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;  // which 1 / (kEpiWarps / 4) of the tile's columns this warp drains
     constexpr int kParts = kEpiWarps / 4;
-    constexpr int kChunksPerWarp = BN / kChunkCols / kParts;
     const uint32_t tempty_addr[2] = {
         (CG == 2) ? mapa_u32(&tempty_bar[0], 0) : smem_u32(&tempty_bar[0]),
         (CG == 2) ? mapa_u32(&tempty_bar[1], 0) : smem_u32(&tempty_bar[1])};
@@ -591,35 +621,37 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // waiting, and loads issued only then paid a full DRAM round trip per 32 x 32 chunk.
     auto prefetch_inputs = [&](int it) {
       if (it >= total_items || g.transpose_out || (!g.residual && !g.aux)) return;
-      const int tl = it % total_tiles;
+      const GemmItem pi = decode_item<BN>(g, it, total_tiles);
+      const int tl = pi.tile, pw = pi.bn / kParts;   // this warp's column share of the item
       const int prow = (tl / num_n_tiles) * TM + rank * BM + q * 32 + lane;
       if (prow >= g.M) return;
-      const int c0 = (tl % num_n_tiles) * BN + part * (BN / kParts);
+      const int c0 = (tl % num_n_tiles) * BN + pi.n_off + part * pw;
       if (g.residual) {
         const char* p = reinterpret_cast<const char*>(g.residual + (size_t)prow * g.ldr + c0);
-#pragma unroll
-        for (int b = 0; b < BN / kParts * 4; b += 128)
+        for (int b = 0; b < pw * 4; b += 128)
           if (c0 + b / 4 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
       }
       if (g.aux) {
         const int esz = g.aux_dtype == HBA_DT_F32 ? 4 : 2;
         const char* p = static_cast<const char*>(g.aux) + ((size_t)prow * g.ld_aux + c0) * esz;
-        for (int b = 0; b < BN / kParts * esz; b += 128)
+        for (int b = 0; b < pw * esz; b += 128)
           if (c0 + b / esz < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
       }
     };
     prefetch_inputs(worker);
     for (int item = worker; item < total_items; item += num_workers) {
-      const int tile = item % total_tiles, slice = item / total_tiles;
+      const GemmItem wi = decode_item<BN>(g, item, total_tiles);
+      const int tile = wi.tile, slice = wi.slice;
+      const int chunks_per_warp = wi.bn / kChunkCols / kParts;   // BN / tail_f >= 64 columns: at least one chunk
       const int m0 = (tile / num_n_tiles) * TM + rank * BM;
-      const int n0 = (tile % num_n_tiles) * BN;
+      const int n0 = (tile % num_n_tiles) * BN + wi.n_off;
       const int row = m0 + q * 32 + lane;
       float* const out_f32 = g.out_f32 ? g.out_f32 + (size_t)slice * g.slice_stride : nullptr;
       prefetch_inputs(item + num_workers);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = part * kChunksPerWarp; c < (part + 1) * kChunksPerWarp; ++c) {
+      for (int c = part * chunks_per_warp; c < (part + 1) * chunks_per_warp; ++c) {
         uint32_t r[kChunkCols];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * kChunkCols;
         tmem_ld_chunk(taddr, r);
@@ -770,6 +802,15 @@ static int cached_tma_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, 
   return HBA_OK;
 }
 
+static bool tail_split_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("HBA_GEMM_TAIL_SPLIT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 static bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -804,6 +845,26 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   int workers = num_sms() / CG;
   if (p->max_ctas > 0 && p->max_ctas / CG < workers) workers = p->max_ctas / CG > 0 ? p->max_ctas / CG : 1;
   if (tiles * g.k_slices < workers) workers = tiles * g.k_slices;
+  // tail splitting: cut the tiles of a partial last round into 2 or 4 column slabs when that shortens the round.
+  // Modelled slab times (the A tile is re-read per slab, so a slab costs more than its share): 0.6 / 0.4 of a tile.
+  GemmArgs ga = g;
+  ga.tail_first = tiles, ga.tail_f = 1;
+  CUtensorMap tb2 = tb, tb4 = tb;
+  if (BN == 256 && CG == 2 && g.k_slices == 1 && !p->a_mn_major && !p->b_mn_major && tail_split_enabled() &&
+      tiles > workers && tiles % workers != 0) {
+    const int rem = tiles % workers;
+    const double cost1 = 1.0;
+    const double cost2 = ((rem * 2 + workers - 1) / workers) * 0.6;
+    const double cost4 = ((rem * 4 + workers - 1) / workers) * 0.4;
+    int f = 1;
+    if (cost2 < cost1 - 0.05 && cost2 <= cost4) f = 2;
+    else if (cost4 < cost1 - 0.05) f = 4;
+    if (f > 1) {
+      ga.tail_first = tiles - rem, ga.tail_f = f;
+      HBA_CHECK(cached_tma_2d_bf16(&tb2, p->B, p->N, b_cols, p->ldb, BNC / 2, BK));
+      HBA_CHECK(cached_tma_2d_bf16(&tb4, p->B, p->N, b_cols, p->ldb, BNC / 4, BK));
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * CG));
   cfg.blockDim = dim3(kGemmThreads);
@@ -821,7 +882,7 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, ACT>, ta, tb, g);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CG, ACT>, ta, tb, tb2, tb4, ga);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("gemm_tc_kernel<%d,%d> launch: %s", BN, CG, cudaGetErrorString(e));
@@ -883,6 +944,7 @@ extern "C" int hba_gemm_bf16(const hba_gemm_params* p, void* stream) {
     HBA_REQUIRE(p->out_bf16 && !p->transpose_out && p->N % 4 == 0 && ((uintptr_t)p->colsum_partial & 15) == 0,
                 "hba_gemm_bf16: colsum_partial needs a bf16 output, N %% 4 == 0 and a 16-byte aligned buffer");
   g.k_slices = 1, g.slice_stride = 0;
+  g.tail_first = 0, g.tail_f = 1;
   const int kblocks_total = (p->K + BK - 1) / BK;
   int slices = p->k_slices > 1 ? p->k_slices : 1;
   if (slices > kblocks_total) slices = kblocks_total;

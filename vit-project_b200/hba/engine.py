@@ -392,6 +392,7 @@ class Engine:
                     cache_ctx["cache"].store(cache_ctx["ids"], x, a_f32)
             if keepP:
                 keepP["a_f32"] = a_f32
+                keepP["a_op"] = a
             self._live_part(tw, blkP, "v", a, x, x_mid, x_out, B, wP, bP, keep=keepP)
             if keepP:
                 keepP["x_mid"] = x_mid
@@ -581,12 +582,13 @@ class Engine:
         ops.layernorm_bwd(d_ln2, x_mid, R, d, blk.ln2_w, LN_EPS, dxo, accumulate=True)
         self.launches += 3
 
-    def _dw(self, tag, dY, a_f32, R, d_out, d_in):
+    def _dw(self, tag, dY, a_f32, R, d_out, d_in, a_op=None):
         """dW[out, in] = sum_r dY[r, out] a[r, in]: both operands are read MN-major (as [K = rows, M / N]
         matrices, no transposition pass; rows beyond R are zero-filled by TMA) and the K = R rows are split
         into slices when the 16 output tiles of a 1024 x 1024 gradient would leave 58 of 74 CTA pairs idle."""
         A = self._grad_operand(f"{tag}.dy{R}", dY, R, d_out)
-        Bo = self._grad_operand(f"{tag}.a{R}", a_f32, R, d_in)
+        # (a_op: the forward pass' own bf16 operand of the same activation - identical to restaging a_f32)
+        Bo = a_op if a_op is not None else self._grad_operand(f"{tag}.a{R}", a_f32, R, d_in)
         dW = torch.empty(d_out, d_in, device=self.device)
         s = ops.auto_k_slices(d_out, d_in, R)
         ws = self._buf("b.k_ws", (s * d_out * d_in,)) if s > 1 else None
@@ -663,7 +665,7 @@ class Engine:
                 ops.add_rows(dx, dxo, B, d, dst_row_step=T)  # residual path of the CLS rows
                 self.launches += 5
                 self._mlp_rows_bwd(blkP, "vbP", dx, M, d, kp["h_pre"], kp["x_mid"])  # dx = dY_P
-                grads[("v", L - 2)] = self._dw("vbP", dx, kp["a_f32"], M, d, d)
+                grads[("v", L - 2)] = self._dw("vbP", dx, kp["a_f32"], M, d, d, a_op=kp.get("a_op"))
         return grads
 
     def _frozen_wt(self, blk):
