@@ -165,3 +165,41 @@ def test_trunk_cache_bookkeeping_on_the_host():
     cache.store(cache.lookup(eng, [3, 7])["ids"], x, a)
     eng.precision = "fp32"                                            # precision mode changed
     assert cache.lookup(eng, [3, 7])["hit"] is False
+
+
+# ------------------------------------------------------------------------------- round 2 host pieces
+def test_find_dora_checkpoints_and_reference_rdm(tmp_path):
+    """hba.rsa_scale (RSA at scale over sweep checkpoints, BASELINE config 5): the checkpoint walk follows the
+    directory layouts of SWEEP:198-207 / LEN:128-137, sorted by run directory and epoch NUMBER (epoch10 after
+    epoch9), and the full-set reference RDM is 1 - corrcoef of the behavioural embedding with a zero diagonal."""
+    import numpy as np
+    from hba import rsa_scale
+    root = tmp_path
+    for rel in ("base/dora/epoch2_dora_params.pth", "base/dora/epoch10_dora_params.pth",
+                "base/dora/epoch9_dora_params.pth", "out/random_target_e1_l2/dora_params_1/epoch3_dora_params.pth",
+                "out/training_run7/dora_params_run7/epoch8_dora_params.pth", "out/training_run7/other.pth",
+                "base/rand/epoch2_random_states.pth"):
+        p = root / rel
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_bytes(b"x")
+    files = [str(p)[len(str(root)) + 1:] for p in map(str, rsa_scale.find_dora_checkpoints(str(root)))]
+    assert files == ["base/dora/epoch2_dora_params.pth", "base/dora/epoch9_dora_params.pth",
+                     "base/dora/epoch10_dora_params.pth",
+                     "out/random_target_e1_l2/dora_params_1/epoch3_dora_params.pth",
+                     "out/training_run7/dora_params_run7/epoch8_dora_params.pth"]
+    t = np.random.default_rng(0).standard_normal((7, 66))
+    rdm = rsa_scale.reference_rdm_from_targets(t)
+    assert rdm.shape == (7, 7) and np.allclose(np.diag(rdm), 0) and np.allclose(rdm, rdm.T)
+    assert np.allclose(rdm[0, 1], 1 - np.corrcoef(t[0], t[1])[0, 1])
+
+
+def test_auto_k_slices_for_row_gemms_and_weight_gradients():
+    """Split-K plans (hba.ops.auto_k_slices): a weight-gradient GEMM keeps >= 8 k-blocks per slice, a row GEMM
+    (CLS / EOT rows: one row tile) may go down to 4, and a problem that already fills the 74 CTA pairs is not split."""
+    from hba import ops
+    assert ops.auto_k_slices(1024, 1024, 8224) > 1            # dW of a 1024 x 1024 out_proj: 16 tiles
+    assert ops.auto_k_slices(9472, 512, 1024) == 1            # 74 tiles = one full round: nothing to gain
+    for (M, N, K) in [(32, 1024, 4096), (66, 768, 3072), (32, 768, 1024)]:
+        s8, s4 = ops.auto_k_slices(M, N, K), ops.auto_k_slices(M, N, K, min_kblocks=4)
+        assert 1 <= s8 <= s4 and s4 > 1
+        assert (K // 64) // s4 >= 4

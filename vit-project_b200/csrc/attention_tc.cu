@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // (secondary of the qkv GEMM: barriers and TMEM are set up before qkv exists)
   pdl_launch_dependents();   // the out_proj GEMM that follows may set itself up on SMs as this grid's CTAs retire
 
   // units of this CTA: u = blockIdx.x + n * gridDim.x, n = 0 .. my_units-1
@@ -573,7 +574,12 @@ int attention_tc_launch(const __nv_bfloat16* qkv, int64_t ld_qkv, int B, int T, 
   HBA_CHECK(make_tma_2d_bf16(&t16, qkv, rows, cols, ld_qkv, 16, 64));
   int ctas = num_sms();
   if (g.n_units < ctas) ctas = g.n_units;
-  attention_tc_kernel<<<ctas, kTcThreads, kTcSmemBytes, stream>>>(t128, t16, g);
+  cudaError_t e = launch_pdl(attention_tc_kernel, dim3(ctas), dim3(kTcThreads), kTcSmemBytes, stream, t128, t16, g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("attention_tc_kernel launch: %s", cudaGetErrorString(e));
+    return HBA_ERR_CUDA;
+  }
   return check_launch("attention_tc_kernel");
 }
 

@@ -711,30 +711,15 @@ extern "C" int hba_dora_merge_bwd(const float* G, int64_t ld_g, const float* D, 
   }
   // [in_f][8] dV tile, later reused for the [8 warps][64][8] partial sums of dA
   const size_t smem = (size_t)(in_f > 512 ? in_f : 512) * kDoraCols * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 - 4096 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(dora_merge_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("hba_dora_merge_bwd: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    configured = smem;
-  }
+  static SmemAttr attr_cols;
+  if (smem > 48 * 1024 - 4096)
+    HBA_CHECK(ensure_dyn_smem(dora_merge_bwd_cols_kernel, smem, attr_cols, "dora_merge_bwd_cols_kernel"));
   dora_merge_bwd_cols_kernel<<<out_f / kDoraCols, kDoraThreads, smem, s>>>(
       G, ld_g, D, A, Bm, m, in_f, out_f, r, scale, eps, dm, dA, workspace);
   HBA_CHECK(check_launch("dora_merge_bwd_cols_kernel"));
   const size_t smem_rows = (size_t)32 * (out_f + 1) * sizeof(float);
-  static size_t configured_rows = 0;
-  if (smem_rows > configured_rows) {
-    cudaError_t e = cudaFuncSetAttribute(dora_merge_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      set_error("hba_dora_merge_bwd: cannot reserve %zu bytes of shared memory: %s", smem_rows, cudaGetErrorString(e));
-      return HBA_ERR_CUDA;
-    }
-    configured_rows = smem_rows;
-  }
+  static SmemAttr attr_rows;
+  HBA_CHECK(ensure_dyn_smem(dora_merge_bwd_rows_kernel, smem_rows, attr_rows, "dora_merge_bwd_rows_kernel"));
   dora_merge_bwd_rows_kernel<<<(in_f + 7) / 8, 256, smem_rows, s>>>(workspace, A, in_f, out_f, r, scale, dB);
   return check_launch("dora_merge_bwd_rows_kernel");
 }

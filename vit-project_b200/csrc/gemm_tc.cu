@@ -488,10 +488,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   // Programmatic dependent launch (HBA_PDL): everything above - barrier init, TMEM allocation, descriptor
   // prefetch, the cluster rendezvous - touches no global memory and may run while the PRECEDING kernel of the
   // stream is still draining its last tiles; the wait returns once that kernel has completed and flushed.
-  // launch_dependents lets the NEXT kernel's CTAs do the same on SMs as this grid's CTAs retire.  Both are
-  // no-ops when the kernel was launched without the programmatic attribute.
-  pdl_launch_dependents();
+  // launch_dependents (AFTER the wait: whatever a dependent reads before its own wait was then written by
+  // kernels that have completed) lets the NEXT kernel's CTAs do the same on SMs as this grid's CTAs retire.
+  // Both are no-ops when the kernel was launched without the programmatic attribute.
   pdl_wait();
+  pdl_launch_dependents();
 
   const int num_m_tiles = (g.M + TM - 1) / TM;
   const int num_n_tiles = (g.N + BN - 1) / BN;
@@ -811,15 +812,6 @@ static bool tail_split_enabled() {
   return on == 1;
 }
 
-static bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("HBA_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
-  return on == 1;
-}
-
 template <int BN, int CG, int ACT>
 static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
@@ -846,7 +838,9 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
   if (p->max_ctas > 0 && p->max_ctas / CG < workers) workers = p->max_ctas / CG > 0 ? p->max_ctas / CG : 1;
   if (tiles * g.k_slices < workers) workers = tiles * g.k_slices;
   // tail splitting: cut the tiles of a partial last round into 2 or 4 column slabs when that shortens the round.
-  // Modelled slab times (the A tile is re-read per slab, so a slab costs more than its share): 0.6 / 0.4 of a tile.
+  // Slab times relative to a full tile (the kernel is bound by the bytes an SM takes in per k-block: its 16 KB of A
+  // are re-read per slab, only the B share shrinks: (16 + 16 / f) / 32 -> 0.75 / 0.625; measured: the qkv GEMM
+  // 8224 x 3072 x 1024 44.2 -> 42.7 us with f = 2, 5082 x 3072 x 768 36.4 -> 33.3 us with f = 4).
   GemmArgs ga = g;
   ga.tail_first = tiles, ga.tail_f = 1;
   CUtensorMap tb2 = tb, tb4 = tb;
@@ -854,8 +848,8 @@ static int launch_gemm(const hba_gemm_params* p, const GemmArgs& g, cudaStream_t
       tiles > workers && tiles % workers != 0) {
     const int rem = tiles % workers;
     const double cost1 = 1.0;
-    const double cost2 = ((rem * 2 + workers - 1) / workers) * 0.6;
-    const double cost4 = ((rem * 4 + workers - 1) / workers) * 0.4;
+    const double cost2 = ((rem * 2 + workers - 1) / workers) * 0.75;
+    const double cost4 = ((rem * 4 + workers - 1) / workers) * 0.65;
     int f = 1;
     if (cost2 < cost1 - 0.05 && cost2 <= cost4) f = 2;
     else if (cost4 < cost1 - 0.05) f = 4;

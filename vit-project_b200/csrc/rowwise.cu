@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(256)
 // grid has no second wave.  Warp w of the 8 consumer warps normalises row w of a stage out of shared memory;
 // the arithmetic (per-lane partial sums in the same order, xor-shuffle reductions, two-pass variance) is the
 // one of layernorm_fwd_kernel, so both kernels produce identical bits.
-constexpr int kLnsRows = 8;         // rows per stage = consumer warps
+// 24 consumer warps: with 8 the kernel was issue-latency bound (ncu: 2 warps per scheduler, 0.19 IPC per warp,
+// 39 % issue-active, DRAM at 26 % of peak, 16.2 us cold); a row costs ~830 warp instructions, i.e. 46 k per SM.
+constexpr int kLnsRows = 24;        // rows per stage = consumer warps
 constexpr int kLnsThreads = 32 * (kLnsRows + 1);
 constexpr int kLnsMaxStages = 8;
 
@@ -162,12 +164,13 @@ __global__ void __launch_bounds__(kLnsThreads, 1)
     }
     mbar_fence_init();
   }
+  pdl_wait();                // (secondary of the kernel that produces x: the barriers are set up before x exists)
+  pdl_launch_dependents();   // the GEMM that consumes y may run its prologue while the last rows are normalised
   for (int c = threadIdx.x * 4; c < cols; c += kLnsThreads * 4) {
     *reinterpret_cast<float4*>(s_gamma + c) = __ldg(reinterpret_cast<const float4*>(gamma + c));
     *reinterpret_cast<float4*>(s_beta + c) = __ldg(reinterpret_cast<const float4*>(beta + c));
   }
   __syncthreads();
-  pdl_launch_dependents();   // the GEMM that consumes y may run its prologue while the last rows are normalised
   const uint32_t row_bytes = (uint32_t)cols * 4u;
   if (warp == kLnsRows) {
     if (lane == 0) {
@@ -470,9 +473,14 @@ extern "C" int hba_layernorm_fwd(const float* x, int64_t rows, int32_t cols, int
     HBA_CHECK(ensure_dyn_smem(layernorm_fwd_stream_kernel, smem, attr, "layernorm_fwd_stream_kernel"));
     int grid = num_sms();
     if ((int64_t)grid * kLnsRows > rows) grid = (int)((rows + kLnsRows - 1) / kLnsRows);
-    layernorm_fwd_stream_kernel<<<grid, kLnsThreads, smem, s>>>(x, rows, cols, ldx, row_step, gamma, beta, eps,
-                                                                y_f32, ld_yf, static_cast<__nv_bfloat16*>(y_bf16),
-                                                                ld_yb, lo_off, stages);
+    cudaError_t e = launch_pdl(layernorm_fwd_stream_kernel, dim3(grid), dim3(kLnsThreads), smem, s, x, rows, cols, ldx,
+                               row_step, gamma, beta, eps, y_f32, ld_yf, static_cast<__nv_bfloat16*>(y_bf16), ld_yb,
+                               lo_off, stages);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("layernorm_fwd_stream_kernel launch: %s", cudaGetErrorString(e));
+      return HBA_ERR_CUDA;
+    }
     return check_launch("hba_layernorm_fwd (stream)");
   }
   layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(

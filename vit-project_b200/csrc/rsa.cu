@@ -39,14 +39,18 @@ __device__ __forceinline__ bool key_is_nan(unsigned long long k) { return k > kK
 // RDM: 32x32 pair tiles; each CTA centres its 64 rows in float64 (numpy.cov promotes to f64
 // before subtracting the mean) and forms cov/(sd_i sd_j) exactly in numpy's order of operations:
 // c = X X^T / (Dm - 1); c /= sd_i; c /= sd_j; clip to [-1, 1] (NaN kept, as numpy.clip does).
-// Every thread owns a 2 x 2 micro-tile (rows ty, ty+16 x columns tx, tx+16: 4 shared loads per 4 DFMA,
-// bank-conflict free with the 65-double row pitch).
-constexpr int kRdmTile = 32;
-constexpr int kRdmChunk = 64;
+// 64 x 64 pair tiles, every thread owns a 4 x 4 micro-tile (rows ty + 16 u x columns tx + 16 w: 8 shared loads
+// per 16 DFMA, bank-conflict free with the 33-double row pitch).  The 2 x 2 form on 32 x 32 tiles was bound by its
+// shared-memory loads (ncu: 76 us at N = 1854 for 0.23 GFLOP of DFMA, L1 at 51 %).
+// Small problems (N <= 256; the per-epoch RSA has N = 48) keep 32 x 32 tiles with 2 x 2 micro-tiles: one 64 x 64
+// tile would leave a single CTA with all the work.
+constexpr int kRdmChunk = 32;
 
+template <int kRdmTile>
 __global__ void __launch_bounds__(256)
     rdm_kernel(const float* __restrict__ E, int N, int Dm, double* __restrict__ rdm,
                double* __restrict__ tri, unsigned long long* __restrict__ keys) {
+  constexpr int kRdmMicro = kRdmTile / 16;
   __shared__ double sX[2][kRdmTile][kRdmChunk + 1];
   __shared__ double sMean[2][kRdmTile];
   __shared__ double sSd[2][kRdmTile];
@@ -71,7 +75,11 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) sMean[side][r] = mean, sSd[side][r] = sqrt(sq / (Dm - 1));
   }
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  double dot[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double dot[kRdmMicro][kRdmMicro];
+#pragma unroll
+  for (int u = 0; u < kRdmMicro; ++u)
+#pragma unroll
+    for (int w = 0; w < kRdmMicro; ++w) dot[u][w] = 0.0;
   for (int k0 = 0; k0 < Dm; k0 += kRdmChunk) {
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * kRdmTile * kRdmChunk; t += 256) {
@@ -85,16 +93,19 @@ __global__ void __launch_bounds__(256)
     const int kn = min(kRdmChunk, Dm - k0);
 #pragma unroll 4
     for (int k = 0; k < kn; ++k) {
-      const double a0 = sX[0][ty][k], a1 = sX[0][ty + 16][k];
-      const double b0 = sX[1][tx][k], b1 = sX[1][tx + 16][k];
-      dot[0][0] += a0 * b0, dot[0][1] += a0 * b1;
-      dot[1][0] += a1 * b0, dot[1][1] += a1 * b1;
+      double a[kRdmMicro], b[kRdmMicro];
+#pragma unroll
+      for (int u = 0; u < kRdmMicro; ++u) a[u] = sX[0][ty + 16 * u][k], b[u] = sX[1][tx + 16 * u][k];
+#pragma unroll
+      for (int u = 0; u < kRdmMicro; ++u)
+#pragma unroll
+        for (int w = 0; w < kRdmMicro; ++w) dot[u][w] += a[u] * b[w];
     }
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u)
+  for (int u = 0; u < kRdmMicro; ++u)
 #pragma unroll
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < kRdmMicro; ++w) {
       const int a = ty + 16 * u, b = tx + 16 * w;
       const int i = bi * kRdmTile + a, j = bj * kRdmTile + b;
       if (i >= N || j >= N || j < i) continue;
@@ -176,8 +187,10 @@ __global__ void __launch_bounds__(1024)
 //   the launch sequence is fixed (CUDA-graph friendly).
 constexpr int kRadixThreads = 256;
 constexpr int kRadixWarps = kRadixThreads / 32;
-constexpr int kRadixIters = 16;                                  // per warp
-constexpr int kRadixTile = kRadixWarps * kRadixIters * 32;       // 4096 elements per CTA
+// 8 elements per thread: with 16 the pass kernel needed 128 registers (2 CTAs = 16 warps per SM) and was bound by
+// the latency of its shared-memory / shuffle chain (ncu: 19 % issue-active, 38 us per pass at 1.7 M keys)
+constexpr int kRadixIters = 8;                                   // per warp
+constexpr int kRadixTile = kRadixWarps * kRadixIters * 32;       // 2048 elements per CTA
 constexpr int kDigits = 8;
 constexpr unsigned int kFlagAgg = 1u << 30, kFlagIncl = 2u << 30, kCountMask = (1u << 30) - 1u;
 
@@ -254,13 +267,13 @@ __device__ __forceinline__ unsigned int block_excl_scan_256(unsigned int v, unsi
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kRadixThreads, 2)
+__global__ void __launch_bounds__(kRadixThreads, 4)
     radix_pass_kernel(unsigned long long* __restrict__ kbuf0, unsigned long long* __restrict__ kbuf1,
                       unsigned int* __restrict__ vbuf0, unsigned int* __restrict__ vbuf1, int64_t n, int pass,
                       RadixCtl* __restrict__ ctl, unsigned int* __restrict__ status_all, int num_tiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);           // [4096]
-  unsigned int* s_vals = reinterpret_cast<unsigned int*>(s_keys + kRadixTile);            // [4096]
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);           // [kRadixTile]
+  unsigned int* s_vals = reinterpret_cast<unsigned int*>(s_keys + kRadixTile);            // [kRadixTile]
   unsigned int (*warp_hist)[256] = reinterpret_cast<unsigned int (*)[256]>(s_vals + kRadixTile);  // [8][256]
   unsigned int* s_local = &warp_hist[0][0] + kRadixWarps * 256;                           // [256] first local index of a bin
   int* s_gbase = reinterpret_cast<int*>(s_local + 256);                                   // [256] global pos - local idx
@@ -568,6 +581,17 @@ static int rank_large(const double* x, int64_t n, const RankWorkspace& w, double
   return check_launch("rank_final_kernel");
 }
 
+static void launch_rdm(const float* E, int N, int Dm, double* rdm, double* tri, unsigned long long* keys,
+                       cudaStream_t s) {
+  if (N <= 256) {
+    const int nb = (N + 31) / 32;
+    rdm_kernel<32><<<dim3(nb, nb), 256, 0, s>>>(E, N, Dm, rdm, tri, keys);
+  } else {
+    const int nb = (N + 63) / 64;
+    rdm_kernel<64><<<dim3(nb, nb), 256, 0, s>>>(E, N, Dm, rdm, tri, keys);
+  }
+}
+
 }  // namespace hba
 
 using namespace hba;
@@ -576,8 +600,7 @@ extern "C" int hba_rdm_f64(const float* E, int32_t N, int32_t Dm, double* rdm, d
                            void* stream) {
   HBA_REQUIRE(E && (rdm || tri) && N > 1, "hba_rdm_f64: bad arguments");
   HBA_REQUIRE(Dm > 1, "hba_rdm_f64: Dm=%d must be > 1", Dm);
-  const int nb = (N + kRdmTile - 1) / kRdmTile;
-  rdm_kernel<<<dim3(nb, nb), 256, 0, static_cast<cudaStream_t>(stream)>>>(E, N, Dm, rdm, tri, nullptr);
+  launch_rdm(E, N, Dm, rdm, tri, nullptr, static_cast<cudaStream_t>(stream));
   return check_launch("rdm_kernel");
 }
 
@@ -626,8 +649,7 @@ extern "C" int hba_rdm_spearman(const float* E, int32_t N, int32_t Dm, const dou
               (long long)hba_rank_workspace_bytes(P));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const RankWorkspace w = rank_workspace_layout(workspace, P);
-  const int nb = (N + kRdmTile - 1) / kRdmTile;
-  rdm_kernel<<<dim3(nb, nb), 256, 0, s>>>(E, N, Dm, rdm, nullptr, w.k0);
+  launch_rdm(E, N, Dm, rdm, nullptr, w.k0, s);
   HBA_CHECK(check_launch("rdm_kernel"));
   return rank_large(nullptr, P, w, ranks, ref_ranks, rho_out, s);
 }

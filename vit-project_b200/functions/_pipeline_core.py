@@ -269,14 +269,15 @@ class CheckpointWriter:
     `path` through a temporary file + `os.replace`, so that a reader never sees a partial checkpoint.  Files and
     formats are exactly those of the synchronous path.  `flush()` waits for everything submitted and re-raises
     the first write error; it runs at the end of every `train_model`, before any checkpoint is loaded, and at
-    interpreter exit.  Opt-in: `HBA_ASYNC_CKPT=1` (off by default until it has been timed on a GPU)."""
+    interpreter exit.  On by default (`HBA_ASYNC_CKPT=0` writes synchronously): 12 grid conditions on one B200 ran at
+    536 instead of 503 conditions/hour with identical result CSVs (profiles/r02_grid12_async_ckpt.json)."""
 
     def __init__(self):
         self._queue, self._thread, self._error = None, None, None
 
     @staticmethod
     def enabled():
-        return os.environ.get("HBA_ASYNC_CKPT", "0") == "1"
+        return os.environ.get("HBA_ASYNC_CKPT", "1") != "0"
 
     @classmethod
     def snapshot(cls, obj):

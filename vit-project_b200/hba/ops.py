@@ -22,6 +22,10 @@ _KERNELS_PER_CALL = {"hba_dora_merge_bwd": 2, "hba_pearson_f64": 3, "hba_softmax
 # When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and
 # (M, N, K, nsplit, start_event, end_event) is appended (bench.py's live roofline measurement).
 GEMM_PROFILE = None
+# Upper bound on the CTAs of every GEMM launched without an explicit `max_ctas` (0 = all SMs).  The data-parallel
+# ViT trainer lowers it during a multi-rank backward pass so that NCCL's all-reduce CTAs find free SMs beside the
+# persistent GEMM kernels instead of queueing behind them (HBA_DP_GEMM_CTAS).
+GEMM_MAX_CTAS = 0
 
 
 class EventProfile:
@@ -182,7 +186,7 @@ def gemm(a: Operand, b: Operand, M=None, *, bias=None, residual=None, act=HBA_AC
     if out is not None:
         p.out_bf16, p.ld_bf16, p.out_lo_off = out.buf.data_ptr(), out.ld, out.lo_off
     p.transpose_out = 1 if transpose_out else 0
-    p.max_ctas = max_ctas
+    p.max_ctas = max_ctas or GEMM_MAX_CTAS
     p.a_mn_major, p.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
     launches = 1
     if colsum_partial is not None:

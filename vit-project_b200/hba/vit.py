@@ -16,6 +16,7 @@ folded into the loss gradient; fused multi-tensor SGD afterwards.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -642,7 +643,14 @@ class DataParallelTrainer:
         hits = eng._buf("hits", (1,), torch.int32)
         ops.softmax_ce(logits, labels, loss, d_logits, hits, eng._buf("ce_ws", (2 * B,)))
         fold_world_size(d_logits, self.world)
-        eng.backward(d_logits, on_bucket_ready=self.reducer.on_bucket_ready)
+        # multi-rank: leave SMs to NCCL while gradient buckets are in flight (persistent 148-CTA GEMMs otherwise
+        # serialise with the all-reduce kernels: the exposed collective time of SURVEY 5 / round-1 SCALE)
+        reserve = int(os.environ.get("HBA_DP_GEMM_CTAS", "0")) if self.world > 1 else 0
+        ops.GEMM_MAX_CTAS = reserve
+        try:
+            eng.backward(d_logits, on_bucket_ready=self.reducer.on_bucket_ready)
+        finally:
+            ops.GEMM_MAX_CTAS = 0
         self.reducer.wait()
         self._sgd()
         return loss, hits
