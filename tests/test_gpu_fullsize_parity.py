@@ -30,12 +30,14 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
 
 # stated bf16-mode tolerances at full size (24 + 12 blocks of bf16 operands, fp32 accumulate)
-BF16_TOL = {"pred_rel_max": 6e-2,      # max |pred - oracle| / max |oracle|
-            "loss_rel": 2e-2,
-            "grad_rel_l2": 1.5e-1,     # ||g - g_oracle||_2 / ||g_oracle||_2 per DoRA tensor
-            "grad_cos": 0.99,          # cosine(g, g_oracle) per DoRA tensor
-            "traj_loss_rel": 3e-2,     # every step of the 24-step trajectory
-            "traj_rho_abs": 3e-2}      # behavioural-RSA rho along the trajectory
+# (set from the first B200 run, profiles/r02_parity_fullsize.json: 7.0e-3 / 2.6e-4 / 8.9e-3 / 0.99998 / 1.7e-4 / 7.9e-4,
+# with a margin of ~3x)
+BF16_TOL = {"pred_rel_max": 2.5e-2,    # max |pred - oracle| / max |oracle|
+            "loss_rel": 2e-3,
+            "grad_rel_l2": 3e-2,       # ||g - g_oracle||_2 / ||g_oracle||_2 per DoRA tensor
+            "grad_cos": 0.999,         # cosine(g, g_oracle) per DoRA tensor
+            "traj_loss_rel": 2e-3,     # every step of the 24-step trajectory
+            "traj_rho_abs": 5e-3}      # behavioural-RSA rho along the trajectory
 
 
 def _record(name, values):

@@ -2,6 +2,7 @@
 # its checkpoints sharded over 8 ranks, and the 8-rank bench (ViT-B/16 data parallel with / without SMs reserved for NCCL)
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
+timeout 300 python -m pytest tests/test_gpu_ops.py -m gpu -q -p no:cacheprovider -k "rdm or spearman or rsa_nan" 2>&1 | tail -2
 timeout 1500 python tools/grid_sweep_bench.py --kind grid --gpus 0,1,2,3,4,5,6,7 --keep --root /tmp/hba_grid_n8 --out gpurun_out/r02h_grid_full_n8.json > gpurun_out/r02h_grid_full_n8.log 2>&1
 echo "full grid N=8 rc=$?"; tail -1 gpurun_out/r02h_grid_full_n8.log | cut -c1-1500
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"

@@ -205,10 +205,41 @@ def _default_run_fn(config):
     return run_behavioral_training(config)
 
 
-def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn, chain=False):
+def cpu_threads_per_worker(n_workers):
+    """Intra-op CPU threads of one sweep worker: the host's cores split over the workers, at most 4 (the GPU does
+    the work; the host side of an epoch is Python), at least 1.
+    Without a cap every worker process sizes its OpenMP / MKL pools for ALL cores; eight of them on one host
+    (the full 136-condition grid on 8 B200s, profiles/r02_grid_full_136_n8.json) then spend their time spinning:
+    0.85 s per epoch per worker against 0.086 s for one worker alone.  (torchrun ranks never see this: torchrun
+    sets OMP_NUM_THREADS=1 itself.)"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    try:   # a container's CPU quota (cgroup v2) is invisible to the affinity mask
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            cores = min(cores, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(4, cores // max(1, n_workers)))
+
+
+_THREAD_ENV = ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS")
+
+
+def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn, chain=False, cpu_threads=0):
     # pin the GPU before anything initialises CUDA in this process
     if device_id is not None:
         os.environ["CUDA_VISIBLE_DEVICES"] = str(device_id)
+    if cpu_threads > 0:
+        # (the environment set by run_sweep already sized the OpenMP / MKL pools at library load; this also covers
+        # a parent that had the variables set to something else)
+        try:
+            import torch
+            torch.set_num_threads(cpu_threads)
+        except Exception:   # noqa: BLE001 - thread caps are an optimisation, never a reason to fail a condition
+            pass
     run_fn = run_fn or _default_run_fn
     while True:
         item = tasks.get()
@@ -254,11 +285,25 @@ def run_sweep(base_config, conditions, devices, layout="sweep", run_fn=None, cos
             tasks.put([(index_of[id(c)], c)])
     for _ in devices:
         tasks.put(None)
-    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn, chain),
+    n_threads = cpu_threads_per_worker(len(devices))
+    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn, chain, n_threads),
                          daemon=False) for w, dev in enumerate(devices)]
     t0 = time.time()
-    for p in procs:
-        p.start()
+    # the children read these when their OpenMP / MKL runtimes load (spawn: fresh interpreters inheriting os.environ);
+    # passive waiting keeps idle pool threads off the cores the other workers' Python threads need
+    saved_env = {k: os.environ.get(k) for k in _THREAD_ENV + ("OMP_WAIT_POLICY",)}
+    for k in _THREAD_ENV:
+        os.environ[k] = str(n_threads)
+    os.environ["OMP_WAIT_POLICY"] = "passive"
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        for k, v in saved_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     out = [None] * len(conditions)
     done = 0
     while done < len(conditions):
