@@ -269,15 +269,40 @@ class CheckpointWriter:
     `path` through a temporary file + `os.replace`, so that a reader never sees a partial checkpoint.  Files and
     formats are exactly those of the synchronous path.  `flush()` waits for everything submitted and re-raises
     the first write error; it runs at the end of every `train_model`, before any checkpoint is loaded, and at
-    interpreter exit.  On by default (`HBA_ASYNC_CKPT=0` writes synchronously): 12 grid conditions on one B200 ran at
-    536 instead of 503 conditions/hour with identical result CSVs (profiles/r02_grid12_async_ckpt.json)."""
+    interpreter exit.
+
+    When it is used: inside the epoch loops of `train_model` (the `deferred()` scope, which flushes on the way out)
+    unless `HBA_ASYNC_CKPT=0` - 12 grid conditions on one B200 ran at 536 instead of 503 conditions/hour with
+    identical result CSVs (profiles/r02_grid12_async_ckpt.json).  A direct call of `save_dora_parameters` /
+    `save_random_states` from user code stays synchronous, as in the reference (the file exists on return), unless
+    `HBA_ASYNC_CKPT=1` forces the background writer everywhere."""
 
     def __init__(self):
         self._queue, self._thread, self._error = None, None, None
+        self._scopes = 0
 
-    @staticmethod
-    def enabled():
-        return os.environ.get("HBA_ASYNC_CKPT", "1") != "0"
+    def enabled(self):
+        mode = os.environ.get("HBA_ASYNC_CKPT", "")
+        if mode == "1":
+            return True
+        if mode == "0":
+            return False
+        return self._scopes > 0
+
+    def deferred(self):
+        """Scope of an epoch loop: checkpoints submitted inside may be written in the background; every one of
+        them is on disk (or its error raised) when the scope is left."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            self._scopes += 1
+            try:
+                yield self
+            finally:
+                self._scopes -= 1
+                self.flush()
+        return scope()
 
     @classmethod
     def snapshot(cls, obj):

@@ -44,29 +44,31 @@ def train_model(model, train_loader, test_loader, inference_loader, device, opti
     with open(training_res_path, 'w', newline='') as f:
         f.write(",".join(BASE_HEADERS) + "\r\n")
     epochs_no_improve = 0
-    for epoch in range(epochs):
-        avg_train_loss = train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs,
-                                         None, log)
-        avg_test_loss = evaluate_model(model, test_loader, device, criterion)
-        log(f"Epoch {epoch+1}: Training Loss: {avg_train_loss:.4f}, Validation Loss: {avg_test_loss:.4f}")
-        rho, p_value, _ = behavioral_RSA(model, inference_loader, device)
-        log(f"Behavioral RSA Correlation & p-value: {rho:.4f}, {p_value:.4f}")
-        model.train()
-        append_csv_row(training_res_path, [epoch + 1, avg_train_loss, avg_test_loss, rho, p_value])
-        save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=logger)
-        save_dora_parameters(model, dora_parameters_path, epoch, vision_layers, transformer_layers,
-                             log_fn=log)
-        log(f"DoRA parameters saved for epoch {epoch+1}")
-        if avg_test_loss < best_test_loss:
-            best_test_loss, epochs_no_improve = avg_test_loss, 0
-        else:
-            epochs_no_improve += 1
-        if epochs_no_improve == early_stopping_patience:
-            log("\n\n*********************************")
-            log(f"Early stopping triggered at epoch {epoch+1}")
-            log("*********************************\n\n")
-            break
-    CHECKPOINTS.flush()   # (background checkpoint writer, HBA_ASYNC_CKPT=1: every file is on disk on return)
+    # (per-epoch checkpoints may be written by the background thread inside this scope; all of them are on
+    # disk - or their error raised - when it is left)
+    with CHECKPOINTS.deferred():
+        for epoch in range(epochs):
+            avg_train_loss = train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs,
+                                             None, log)
+            avg_test_loss = evaluate_model(model, test_loader, device, criterion)
+            log(f"Epoch {epoch+1}: Training Loss: {avg_train_loss:.4f}, Validation Loss: {avg_test_loss:.4f}")
+            rho, p_value, _ = behavioral_RSA(model, inference_loader, device)
+            log(f"Behavioral RSA Correlation & p-value: {rho:.4f}, {p_value:.4f}")
+            model.train()
+            append_csv_row(training_res_path, [epoch + 1, avg_train_loss, avg_test_loss, rho, p_value])
+            save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=logger)
+            save_dora_parameters(model, dora_parameters_path, epoch, vision_layers, transformer_layers,
+                                 log_fn=log)
+            log(f"DoRA parameters saved for epoch {epoch+1}")
+            if avg_test_loss < best_test_loss:
+                best_test_loss, epochs_no_improve = avg_test_loss, 0
+            else:
+                epochs_no_improve += 1
+            if epochs_no_improve == early_stopping_patience:
+                log("\n\n*********************************")
+                log(f"Early stopping triggered at epoch {epoch+1}")
+                log("*********************************\n\n")
+                break
 
 
 def run_behavioral_training(config):

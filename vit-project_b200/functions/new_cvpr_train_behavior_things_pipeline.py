@@ -79,41 +79,43 @@ def train_model(model, train_loader, test_loader, inference_loader, device, opti
             "used_shuffled_targets": "SHUFFLED TARGETS WERE USED IN THIS EPOCH",
             "used_uniform_images": "UNIFORM GRAYSCALE IMAGES WERE USED IN THIS EPOCH",
             "used_image_noise": "GAUSSIAN NOISE WAS APPLIED TO IMAGES IN THIS EPOCH"}
-    for epoch in range(resume_from_epoch, epochs):
-        flags = perturb.flags(epoch)
-        if perturb.active(epoch):
-            log("=" * 80)
-            log(f"\n*** {banner[perturb_type]} FOR EPOCH {epoch+1} (Perturbation window: epochs "
-                f"{perturb.first+1}-{perturb.last+1}) ***")
-            log("=" * 80)
-            log(f"Perturbation seed: {perturb_seed}")
-        avg_train_loss = train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs,
-                                         perturb, log)
-        avg_test_loss = evaluate_model(model, test_loader, device, criterion)
-        log(f"Epoch {epoch+1}: Training Loss: {avg_train_loss:.4f}, Validation Loss: {avg_test_loss:.4f}")
-        rho, p_value, _ = behavioral_RSA(model, inference_loader, device, logger=logger)
-        log(f"Behavioral RSA Correlation & p-value: {rho:.4f}, {p_value:.4f}")
-        model.train()
-        for key, msg in done.items():
-            if flags[key]:
-                log(f"*** {msg} ***")
-        append_csv_row(training_res_path, [epoch + 1, avg_train_loss, avg_test_loss, rho, p_value,
-                                           flags["used_random_targets"], flags["used_shuffled_targets"],
-                                           flags["used_uniform_images"], flags["used_image_noise"]])
-        save_dora_parameters(model, dora_parameters_path, epoch, logger=logger)
-        log(f"DoRA parameters saved for epoch {epoch+1}")
-        if dataloader_generator is not None:
-            save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=logger)
-        if avg_test_loss < best_test_loss:
-            best_test_loss, epochs_no_improve = avg_test_loss, 0
-        elif not perturb.in_window(epoch):
-            epochs_no_improve += 1
-        if epochs_no_improve == early_stopping_patience:
-            log("\n\n*********************************")
-            log(f"Early stopping triggered at epoch {epoch+1}")
-            log("*********************************\n\n")
-            break
-    CHECKPOINTS.flush()   # (background checkpoint writer, HBA_ASYNC_CKPT=1: every file is on disk on return)
+    # (per-epoch checkpoints may be written by the background thread inside this scope; all of them are on
+    # disk - or their error raised - when it is left)
+    with CHECKPOINTS.deferred():
+        for epoch in range(resume_from_epoch, epochs):
+            flags = perturb.flags(epoch)
+            if perturb.active(epoch):
+                log("=" * 80)
+                log(f"\n*** {banner[perturb_type]} FOR EPOCH {epoch+1} (Perturbation window: epochs "
+                    f"{perturb.first+1}-{perturb.last+1}) ***")
+                log("=" * 80)
+                log(f"Perturbation seed: {perturb_seed}")
+            avg_train_loss = train_one_epoch(model, train_loader, device, optimizer, criterion, epoch, epochs,
+                                             perturb, log)
+            avg_test_loss = evaluate_model(model, test_loader, device, criterion)
+            log(f"Epoch {epoch+1}: Training Loss: {avg_train_loss:.4f}, Validation Loss: {avg_test_loss:.4f}")
+            rho, p_value, _ = behavioral_RSA(model, inference_loader, device, logger=logger)
+            log(f"Behavioral RSA Correlation & p-value: {rho:.4f}, {p_value:.4f}")
+            model.train()
+            for key, msg in done.items():
+                if flags[key]:
+                    log(f"*** {msg} ***")
+            append_csv_row(training_res_path, [epoch + 1, avg_train_loss, avg_test_loss, rho, p_value,
+                                               flags["used_random_targets"], flags["used_shuffled_targets"],
+                                               flags["used_uniform_images"], flags["used_image_noise"]])
+            save_dora_parameters(model, dora_parameters_path, epoch, logger=logger)
+            log(f"DoRA parameters saved for epoch {epoch+1}")
+            if dataloader_generator is not None:
+                save_random_states(optimizer, epoch, random_state_path, dataloader_generator, logger=logger)
+            if avg_test_loss < best_test_loss:
+                best_test_loss, epochs_no_improve = avg_test_loss, 0
+            elif not perturb.in_window(epoch):
+                epochs_no_improve += 1
+            if epochs_no_improve == early_stopping_patience:
+                log("\n\n*********************************")
+                log(f"Early stopping triggered at epoch {epoch+1}")
+                log("*********************************\n\n")
+                break
 
 
 def run_behavioral_training(config):
