@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=0,
                     help="images per CPU-arm step (0 = the stated batch: same config as the GPU arm)")
     ap.add_argument("--sweep-per-gpu", type=int, default=4, help="grid conditions per GPU in the scheduler-run slice")
+    ap.add_argument("--sweep-timeout", type=float, default=600.0, help="limit of the scheduler-run sweep slice [s]")
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true")
     ap.add_argument("--roofline-seconds", type=float, default=2.6,
@@ -360,7 +361,18 @@ def measure_sweep_scheduler(args, world, rank, dist):
                "--max-start", "10", "--batch-size", str(args.batch), "--backbone", args.backbone,
                "--root", tempfile.mkdtemp(prefix="hba_grid_"), "--out", out_path]
         t0 = time.perf_counter()
-        proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+        # own session: on a timeout the tool AND the worker processes it spawned are killed together, so that no
+        # stray worker holds a GPU when the next section starts
+        proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                start_new_session=True)
+        try:
+            out_txt, err_txt = proc.communicate(timeout=args.sweep_timeout)
+        except subprocess.TimeoutExpired:
+            import signal
+            os.killpg(proc.pid, signal.SIGKILL)
+            out_txt, err_txt = proc.communicate()
+            err_txt = f"timed out after {args.sweep_timeout} s\n" + (err_txt or "")
+        proc.stdout_text, proc.stderr_text = out_txt, err_txt
         if os.path.exists(out_path):
             full = json.load(open(out_path))
             res = {k: v for k, v in full.items() if k != "per_condition"}
@@ -368,7 +380,7 @@ def measure_sweep_scheduler(args, world, rank, dist):
             res["epochs_per_condition"] = [c["epochs_trained"] for c in full["per_condition"]]
             res["tool_wall_s"] = time.perf_counter() - t0
         if proc.returncode != 0:
-            res["error"] = (proc.stderr or proc.stdout)[-400:]
+            res["error"] = (proc.stderr_text or proc.stdout_text or "")[-400:]
     except Exception as exc:
         res["error"] = f"{type(exc).__name__}: {exc}"[:300]
     if store is not None:

@@ -86,6 +86,35 @@ def test_two_worker_pool_runs_every_condition_and_survives_a_failure(tmp_path):
 
 
 # ------------------------------------------------------------------------------- gloo, world size 2
+def _report_threads(cfg):
+    import json
+    import torch
+    with open(os.path.join(cfg["output_base_directory"], f"threads_{cfg['training_run']}.json"), "w") as f:
+        json.dump({"torch": torch.get_num_threads(), "omp": os.environ.get("OMP_NUM_THREADS"),
+                   "wait": os.environ.get("OMP_WAIT_POLICY")}, f)
+
+
+def test_workers_start_with_capped_cpu_thread_pools(tmp_path, monkeypatch):
+    """Eight workers starting at once, each with OpenMP / MKL pools sized for all host cores, stalled 700 s in the
+    image pipeline of the full-grid run on 8 B200s (profiles/r02_grid_full_136_n8.json; reproduced on the CPU: 400
+    images decode in 2 s alone, 145 s in each of 8 concurrent default processes, 2.7 s with the caps).  run_sweep
+    hands every worker cores / workers threads (at most 4) through the environment of the spawn and restores its own."""
+    import json
+    from hba import sweep
+    monkeypatch.setenv("OMP_NUM_THREADS", "7")
+    monkeypatch.delenv("OMP_WAIT_POLICY", raising=False)
+    conds = [{"training_run": e, "perturb_length": 1} for e in (1, 2)]
+    res = sweep.run_sweep({"output_base_directory": str(tmp_path)}, conds, [None, None], run_fn=_report_threads,
+                          log=lambda *_: None)
+    assert all(r["ok"] for r in res), [r["error"] for r in res]
+    want = sweep.cpu_threads_per_worker(2)
+    assert 1 <= want <= 4 and sweep.cpu_threads_per_worker(10 ** 6) == 1
+    for e in (1, 2):
+        got = json.load(open(os.path.join(str(tmp_path), f"threads_{e}.json")))
+        assert got == {"torch": want, "omp": str(want), "wait": "passive"}
+    assert os.environ["OMP_NUM_THREADS"] == "7" and "OMP_WAIT_POLICY" not in os.environ   # the parent's own, restored
+
+
 def _dp_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     from hba import dp
