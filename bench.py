@@ -12,8 +12,11 @@ path shards as independent runs): weak scaling, no data-path collec
   value : images/s with inputs resident in HBM (device-timed, max over ranks)
   e2e   : same metric through the public API (functions.*: CLIPHBA + DoRALayer + FusedAdamW) with
           pinned HOST images/targets copied in and the loss read back every step
-  roofline : the tcgen05 GEMM kernel, algorithmic FLOPs / CUDA-event time of its launches, measured
-          live in the timed region, against MEASURED_PEAKS.json bf16_tflops_sustained
+  roofline : the tcgen05 GEMM kernel, algorithmic FLOPs / CUDA-event time of its launches over a >= 2 s
+          host-launched pass, against MEASURED_PEAKS.json: the burst figure when the pass kept the SM clock near
+          its maximum, the sustained one otherwise (both fractions are in the line)
+  fp32_mode / roofline_hbm / sweep / vit_b16 : the parity mode on the same workload, the HBM-bound kernels
+          against the measured HBM peak, a scheduler-run slice of the 136-condition grid, ViT-B/16 data parallel
   cpu_baseline : the oracle port (oracle/clip_ref.py + oracle/dora_ref.py, PyTorch fp32 on the host
           cores) on a bounded sample of the same workload
 
@@ -595,6 +598,15 @@ def main():
         peak, peak_burst = 1400.0, 1650.0
         peak_src = "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # which measured peak is the honest denominator is decided by the clocks of the pass itself: MEASURED_PEAKS'
+    # "sustained" figure was taken at a median 1,327 MHz (power-limited cuBLAS loop); a pass whose SM clock stays
+    # near its maximum is compared with the burst figure, however long it ran
+    peak_sustained = peak
+    mhz, mhz_max = roof_clocks.get("sm_mhz"), roof_clocks.get("sm_max_mhz")
+    if mhz and mhz_max and mhz >= 0.9 * mhz_max:
+        peak = peak_burst
+        peak_src = (f"measured (MEASURED_PEAKS.json bf16_tflops, the burst figure: the {ms_eager / 1e3:.1f} s roofline "
+                    f"pass kept the SM clock at a median {mhz:.0f} of {mhz_max:.0f} MHz)")
     shapes = {}
     for (M, N, K, ns, a, b) in prof:
         e = shapes.setdefault((M, N, K), [0, 0.0])
@@ -623,6 +635,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "peak_burst": peak_burst, "frac_of_burst_peak": achieved / peak_burst,
+                     "peak_sustained": peak_sustained, "frac_of_sustained_peak": achieved / peak_sustained,
                      "pass_seconds": ms_eager / 1e3, "pass_steps": roof_steps, "pass_clocks": roof_clocks,
                      "gemm_launches_per_step": len(prof) / roof_steps,
                      "gemm_flops_per_step": flops / roof_steps,
