@@ -53,6 +53,9 @@ int hba_device_check(void);
  *   out_f32 / out_bf16 (hi at column n, lo at column n + out_lo_off when out_lo_off > 0)
  *   transpose_out != 0 writes the outputs as [N, M] (ld* are then row strides of that layout);
  *     only alpha and bias apply in that mode (no act / residual / pre_out)
+ * Scheduling (no effect on results): persistent CTA pairs, 256 x 256 tiles; the tiles of a partial last round are
+ * cut into 2 or 4 column slabs (HBA_GEMM_TAIL_SPLIT=0 disables), every element still accumulates its K products
+ * in the same order, so the output bits do not depend on M, on max_ctas or on the split.
  */
 enum {
   HBA_ACT_NONE = 0,
@@ -90,9 +93,11 @@ typedef struct hba_gemm_params {
   int32_t max_ctas; /* 0 = one persistent CTA per SM */
   int32_t a_mn_major; /* A stored as [K, lda] (M contiguous): C = A^T-layout product, no transpose pass */
   int32_t b_mn_major; /* B stored as [K, ldb] (N contiguous), e.g. dX = dY . W with W [out, in] as is */
-  int32_t k_slices;   /* > 1: split-K for weight-gradient shapes (few output tiles, K = rows of the batch):
-                         every (tile, K slice) is a work item; the slices are summed in a fixed order
-                         (deterministic).  Needs k_workspace and a plain out_f32 epilogue, N % 4 == 0 */
+  int32_t k_slices;   /* > 1: split-K for problems with few output tiles (weight gradients: K = rows of the batch;
+                         the CLS / EOT row GEMMs, M = 32 / 66): every (tile, K slice) is a work item writing fp32
+                         partial sums into k_workspace; the slices are summed in a fixed order (deterministic) by a
+                         reduction that runs this struct's whole epilogue (bias, pre_out, act / aux, residual,
+                         out_f32, out_bf16 hi / lo).  Needs k_workspace, N % 4 == 0, no transpose_out / colsum */
   float* k_workspace; /* >= k_slices * M * N floats, 16-byte aligned */
   float* colsum_partial; /* or NULL: [ceil(M / 32), N] fp32 receiving, per 32-row group, the column sums
                             of the bf16 output (hi part) - the bias gradient of the previous Linear fused
