@@ -432,12 +432,40 @@ def measure_vit(args, device, world, dist):
     peak = json.load(open(peaks_path))["bf16_tflops_sustained"] if os.path.exists(peaks_path) else 1400.0
     tflops = value / world * 105.3e9 / 1e12   # 3 x 35.1 GFLOP per image
     loss_val, n_launch = float(loss), ops.COUNTERS["launches"] - c0
-    tr.close()
+    exposed = None
+    if dist is not None and world > 1:
+        # the same step with the gradient all-reduces left out (the ranks then drift apart - nothing is measured
+        # after this): what the collectives cost beyond what the backward pass hides
+        try:
+            tr.reducer.enabled = False
+            tr._graphs.clear()
+            # (rank-local on purpose: no collective inside this block, so a failure on one rank cannot strand the others)
+            for _ in range(3):
+                tr.step(images, labels)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(steps):
+                tr.step(images, labels)
+            f1.record()
+            torch.cuda.synchronize()
+            ms_local = f0.elapsed_time(f1)
+            exposed = {"ms_per_step_without_allreduce": ms_local / steps,
+                       "exposed_collective_ms_per_step": (ms - ms_local) / steps,
+                       "what": "same captured step with the bucket all-reduces left out, timed on this rank"}
+        except Exception as exc:   # reporting only
+            exposed = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+        finally:
+            tr.reducer.enabled = True
+    try:   # (never let the teardown cost the numbers above)
+        tr.close()
+    except Exception as exc:
+        exposed = dict(exposed or {}, close_error=f"{type(exc).__name__}: {exc}"[:200])
     del tr, model
     return {"metric": "ViT-B/16 train imgs/s", "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "ms_per_step": ms / steps, "scaling": "weak", "dtype": "bf16", "global_batch": batch * world,
             "parallelism": f"dp{world}: batch {batch}/GPU, NCCL gradient all-reduce per block bucket, CUDA-graph step",
-            "loss": loss_val, "gpu_launches": n_launch,
+            "loss": loss_val, "gpu_launches": n_launch, "collectives": exposed,
             "algorithmic_tflops_per_gpu": tflops, "frac_of_sustained_bf16_peak": tflops / peak}
 
 

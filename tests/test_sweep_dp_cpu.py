@@ -149,6 +149,35 @@ def test_gradient_buckets_all_reduce_on_gloo_world_2(tmp_path):
     assert all(off % 4 == 0 for off, _ in r0["offsets"])            # every gradient 16-byte aligned
 
 
+def test_bucket_reducer_can_be_switched_off_for_compute_only_timing():
+    """bench.py times the multi-rank ViT step once more with the all-reduces left out (`enabled = False`): buckets
+    are still announced in backward order, nothing is reduced, `wait()` has nothing to wait for."""
+    from hba.dp import BucketAllReducer
+
+    class _Dist:
+        calls = 0
+
+        def get_world_size(self, group=None):
+            return 2
+
+        def all_reduce(self, t, group=None, async_op=False):
+            _Dist.calls += 1
+
+            class _H:
+                def wait(self_inner):
+                    return None
+            return _H()
+    r = BucketAllReducer(_Dist())
+    r.on_bucket_ready("head", torch.zeros(4))
+    assert _Dist.calls == 1 and len(r.handles) == 1
+    r.wait()
+    r.enabled = False
+    r.on_bucket_ready("block1", torch.zeros(4))
+    assert _Dist.calls == 1 and r.handles == [] and r.launched == ["block1"]
+    r.wait()
+    assert r.launched == []
+
+
 def test_reference_arm_under_torchrun_two_ranks(tmp_path):
     """`bench.py --impl reference --gpus 2` launched the way the driver launches N > 1: rank 0 alone
     runs the CPU implementation and prints the JSON line, the other rank exits 0 without work."""

@@ -37,6 +37,7 @@ class BucketAllReducer:
         self.dist, self.group = dist, group
         self.handles = []
         self.launched = []
+        self.enabled = True   # False: buckets are announced but not reduced (compute-only timing of a multi-rank step)
 
     @property
     def world(self):
@@ -45,7 +46,7 @@ class BucketAllReducer:
     def on_bucket_ready(self, name, flat_slice):
         """Called by the backward pass as soon as every gradient of the bucket has been written."""
         self.launched.append(name)
-        if self.dist is not None and self.world > 1:
+        if self.enabled and self.dist is not None and self.world > 1:
             self.handles.append(self.dist.all_reduce(flat_slice, group=self.group, async_op=True))
 
     def wait(self):
