@@ -215,3 +215,25 @@ def test_model_construction_and_dora_surgery_match_reference_golden_on_the_host(
     assert not unexpected
     for k, t in gt["dora_epoch3"].items():
         assert torch.equal(dict(fresh.named_parameters())[k].detach(), t)
+
+
+def test_things_transform_equals_torchvision(tmp_path):
+    """The torchvision-free restatement of NEW:183-188 (Resize((224, 224)) -> ToTensor -> Normalize) is bit-identical
+    to the torchvision Compose the reference builds, for up- and down-scaled RGB images of odd sizes (JPEG and PNG
+    sources, as `Image.open(...).convert('RGB')` hands them over)."""
+    from PIL import Image
+    from torchvision import transforms
+    ref = transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
+                              transforms.Normalize(mean=core.THINGS_MEAN, std=core.THINGS_STD)])
+    mine = core._things_transform()
+    rng = np.random.default_rng(0)
+    for k, (h, w) in enumerate([(32, 32), (40, 52), (224, 224), (301, 257), (800, 600), (17, 1000)]):
+        arr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        path = os.path.join(str(tmp_path), f"img{k}." + ("jpg" if k % 2 else "png"))
+        Image.fromarray(arr).save(path)
+        img = Image.open(path).convert("RGB")
+        a, b = ref(img), mine(Image.open(path).convert("RGB"))
+        assert a.dtype == b.dtype == torch.float32 and a.shape == b.shape == (3, 224, 224)
+        assert torch.equal(a, b), (h, w, float((a - b).abs().max()))
+    gray = Image.fromarray(rng.integers(0, 256, (50, 60), dtype=np.uint8)).convert("RGB")
+    assert torch.equal(ref(gray), mine(gray))

@@ -29,7 +29,6 @@ import torch
 import torch.nn as nn
 from PIL import Image
 from torch.utils.data import DataLoader, Dataset
-from torchvision import transforms
 from tqdm import tqdm
 
 from hba import DoRALayer, ops, rsa
@@ -76,9 +75,29 @@ def _log_fn(logger):
 
 
 # ------------------------------------------------------------------------------- data
+class _ThingsTransform:
+    """Resize((224, 224)) -> ToTensor() -> Normalize(THINGS_MEAN, THINGS_STD) of NEW:183-188 on a PIL image, restated
+    without torchvision: `import torchvision` pulls in torch._dynamo (4 - 7 s per process, paid by every sweep
+    worker), and for a PIL input these three transforms are: PIL's own bilinear resize, uint8 HWC -> float32 CHW
+    / 255, (x - mean) / std.  Bit-identical to the torchvision Compose
+    (tests/test_pipeline_cpu.py::test_things_transform_equals_torchvision)."""
+
+    def __init__(self, size=(224, 224), mean=None, std=None):
+        self.size = size
+        self.mean = torch.tensor(THINGS_MEAN if mean is None else mean, dtype=torch.float32).view(-1, 1, 1)
+        self.std = torch.tensor(THINGS_STD if std is None else std, dtype=torch.float32).view(-1, 1, 1)
+
+    def __call__(self, img):
+        img = img.resize(self.size[::-1], Image.BILINEAR)          # torchvision F.resize on a PIL image (size = (h, w))
+        x = torch.from_numpy(np.array(img, np.uint8, copy=True))   # ToTensor: HWC uint8 ...
+        if x.ndim == 2:
+            x = x[:, :, None]
+        x = x.permute(2, 0, 1).contiguous().to(torch.float32).div(255)   # ... -> CHW float32 in [0, 1]
+        return x.sub_(self.mean).div_(self.std)                    # Normalize (on its own copy, like torchvision)
+
+
 def _things_transform():
-    return transforms.Compose([transforms.Resize((224, 224)), transforms.ToTensor(),
-                               transforms.Normalize(mean=THINGS_MEAN, std=THINGS_STD)])
+    return _ThingsTransform()
 
 
 class ThingsDataset(Dataset):

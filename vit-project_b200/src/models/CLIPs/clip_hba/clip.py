@@ -49,6 +49,24 @@ def available_models():
     return list(_MODELS.keys())
 
 
+# build_model() creates the module tree on the meta device and hands it the checkpoint's tensors; every random
+# initialisation would be thrown away, and on the meta device the first `normal_` / `randn` / scalar * tensor
+# pulls in ~900 Python modules of torch's decomposition machinery (6.5 s per process: every sweep worker pays it).
+# Inside `_uninitialised()` the constructors below allocate their parameters with torch.empty and skip the init.
+_SKIP_INIT = False
+
+
+class _uninitialised:
+    def __enter__(self):
+        global _SKIP_INIT
+        self._saved, _SKIP_INIT = _SKIP_INIT, True
+
+    def __exit__(self, *exc):
+        global _SKIP_INIT
+        _SKIP_INIT = self._saved
+        return False
+
+
 def _no_torch_path(name):
     raise NotImplementedError(
         f"{name}: this CLIP build computes only through CLIP.forward / encode_image / encode_text on "
@@ -92,13 +110,15 @@ class VisionTransformer(nn.Module):
         self.input_resolution, self.output_dim = input_resolution, output_dim
         self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
         scale = width ** -0.5
-        self.class_embedding = nn.Parameter(scale * torch.randn(width))
-        self.positional_embedding = nn.Parameter(
-            scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+
+        def rand(*shape):   # (same draws in the same order as before when the weights ARE initialised)
+            return nn.Parameter(torch.empty(*shape) if _SKIP_INIT else scale * torch.randn(*shape))
+        self.class_embedding = rand(width)
+        self.positional_embedding = rand((input_resolution // patch_size) ** 2 + 1, width)
         self.ln_pre = nn.LayerNorm(width)
         self.transformer = Transformer(width, layers, heads)
         self.ln_post = nn.LayerNorm(width)
-        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self.proj = rand(width, output_dim)
 
     def forward(self, x, pos_embedding=False):
         _no_torch_path("VisionTransformer")
@@ -113,12 +133,19 @@ class CLIP(nn.Module):
                                         vision_layers, vision_width // 64, embed_dim)
         self.transformer = Transformer(transformer_width, transformer_layers, transformer_heads,
                                        causal=True)
-        self.token_embedding = nn.Embedding(vocab_size, transformer_width)
+        if _SKIP_INIT:   # (a given weight tensor skips nn.Embedding's own normal_ initialisation)
+            self.token_embedding = nn.Embedding(vocab_size, transformer_width,
+                                                _weight=torch.empty(vocab_size, transformer_width))
+        else:
+            self.token_embedding = nn.Embedding(vocab_size, transformer_width)
         self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width))
         self.ln_final = nn.LayerNorm(transformer_width)
         self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
-        self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
-        self._init_weights()
+        if _SKIP_INIT:
+            self.logit_scale = nn.Parameter(torch.empty([]))
+        else:
+            self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
+            self._init_weights()
 
     def _init_weights(self):
         nn.init.normal_(self.token_embedding.weight, std=0.02)
@@ -165,7 +192,7 @@ def build_model(state_dict):
                                   "of scope: the reference drivers use ViT-L/14)")
     # modules are created on the meta device (no throw-away random init of 428 M parameters) and
     # take ownership of the checkpoint tensors
-    with torch.device("meta"):
+    with _uninitialised(), torch.device("meta"):
         model = CLIP(**_arch_from_state_dict(state_dict))
     sd = {k: (v.detach().clone().float() if torch.is_floating_point(v) else v.detach().clone())
           for k, v in state_dict.items() if k not in ("input_resolution", "context_length", "vocab_size")}
