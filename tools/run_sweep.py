@@ -24,8 +24,8 @@ def main():
     ap.add_argument("--end", type=int, default=98)
     ap.add_argument("--gpus", default="0")
     ap.add_argument("--workers-per-gpu", type=int, default=1,
-                    help="worker processes per GPU (they time-share it and fill each other's host phases; to be "
-                         "measured with tools/gpu_next_round.sh before changing the default)")
+                    help="worker processes per GPU - measured on a B200: 2 / 4 workers run 2.2x / 4.5x SLOWER than one "
+                         "(profiles/r02_grid12_workers*.json); keep 1")
     ap.add_argument("--plan", action="store_true")
     ap.add_argument("--chain", action="store_true",
                     help="grid only: LEN's shorter -> longer resume chain, one start epoch per worker at a time")
