@@ -178,6 +178,66 @@ def test_bucket_reducer_can_be_switched_off_for_compute_only_timing():
     assert r.launched == []
 
 
+def _rsa_scale_worker(rank, world, port, root):
+    """RSA at scale over DoRA checkpoints, sharded over 2 `gloo` ranks (hba.rsa_scale; the device pieces replaced by
+    CPU stand-ins: embeddings derived from the loaded checkpoint, numpy / scipy for the RSA tail)."""
+    import numpy as np
+    import torch.distributed as dist
+    from scipy.stats import spearmanr
+    from hba import rsa_scale
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    class _Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.m = torch.nn.Parameter(torch.zeros(3))
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((12, 66))
+    ref = rsa_scale.reference_rdm_from_targets(rng.standard_normal((12, 66)))
+    iu = np.triu_indices(12, k=1)
+
+    extra = rng.standard_normal((12, 66))
+
+    def embed(model, loaders, device):
+        with torch.no_grad():
+            return torch.from_numpy(base * float(model.m[0]) + extra * 30.0 * float(model.m[1]))
+
+    def evaluator(emb, want_rdm=False):
+        rdm = 1 - np.corrcoef(emb.numpy())
+        rho, p = spearmanr(ref[iu], rdm[iu])
+        return float(rho), float(p), None
+    files = rsa_scale.find_dora_checkpoints(root)
+    out = rsa_scale.clip_rsa_over_checkpoints(_Model(), [], ref, files, "cpu", rank=rank, world_size=world,
+                                              output_csv=os.path.join(root, "rsa.csv"), log=None, root=root,
+                                              evaluator=evaluator, embed_fn=embed)
+    torch.save({"out": out}, os.path.join(root, f"result{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_rsa_at_scale_shards_checkpoints_over_gloo_world_2(tmp_path):
+    import pandas as pd
+    import torch.multiprocessing as mp
+    root = str(tmp_path)
+    want = {}
+    for run, epochs in (("base/dora", (1, 2, 10)), ("out/random_target_e1_l2/dora_params_1", (3, 4))):
+        os.makedirs(os.path.join(root, run))
+        for e in epochs:
+            torch.save({"m": torch.tensor([1.0 + 0.1 * e, 0.01 * e, 0.0])}, os.path.join(root, run, f"epoch{e}_dora_params.pth"))
+            want[os.path.join(run, f"epoch{e}_dora_params.pth")] = e
+    port = 29750 + os.getpid() % 200
+    mp.spawn(_rsa_scale_worker, args=(2, port, root), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(root, f"result{r}.pt"), weights_only=False)["out"] for r in (0, 1))
+    assert r1 is None                                        # only rank 0 holds the gathered rows
+    rows, stats = r0
+    assert [r["checkpoint"] for r in rows] == sorted(want)   # every file exactly once, whatever rank evaluated it
+    assert [r["epoch"] for r in rows] == [want[r["checkpoint"]] for r in rows]
+    assert sorted(s["checkpoints"] for s in stats) == [2, 3] and {s["rank"] for s in stats} == {0, 1}
+    assert all(-1.0 <= r["behavioral_rsa_rho"] <= 1.0 for r in rows)
+    assert len({round(r["behavioral_rsa_rho"], 12) for r in rows}) == len(rows)   # each from its own checkpoint
+    df = pd.read_csv(os.path.join(root, "rsa.csv"))
+    assert list(df.columns) == list(__import__("hba.rsa_scale", fromlist=["x"]).RESULT_COLUMNS) and len(df) == 5
+
+
 def test_reference_arm_under_torchrun_two_ranks(tmp_path):
     """`bench.py --impl reference --gpus 2` launched the way the driver launches N > 1: rank 0 alone
     runs the CPU implementation and prints the JSON line, the other rank exits 0 without work."""

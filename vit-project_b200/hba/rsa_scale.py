@@ -64,12 +64,16 @@ def embeddings(model, loaders, device):
 
 
 def clip_rsa_over_checkpoints(model, loaders, reference_rdm, files, device, rank=0, world_size=1, output_csv=None,
-                              log=print, root=None):
-    """-> rows (rank 0) | None.  `model`: CLIPHBA with its adapters applied (weights of the checkpoints are loaded
-    with strict=False exactly as NEW:1159 does); `loaders`: ResidentLoaders whose concatenation is the image set in
-    the order of `reference_rdm`'s rows."""
-    from .rsa import RSAEvaluator
-    evaluator = RSAEvaluator(reference_rdm, device)
+                              log=print, root=None, evaluator=None, embed_fn=None):
+    """-> (rows, per-rank stats) on rank 0 | None.  `model`: CLIPHBA with its adapters applied (weights of the
+    checkpoints are loaded with strict=False exactly as NEW:1159 does); `loaders`: ResidentLoaders whose concatenation
+    is the image set in the order of `reference_rdm`'s rows.  `evaluator` / `embed_fn` default to the libhba ones
+    (hba.rsa.RSAEvaluator, `embeddings`); the world-2 `gloo` test of the sharding passes CPU stand-ins."""
+    if evaluator is None:
+        from .rsa import RSAEvaluator
+        evaluator = RSAEvaluator(reference_rdm, device)
+    embed_fn = embed_fn or embeddings
+    on_cuda = torch.device(device).type == "cuda"
     rows, t_emb, t_rsa = [], 0.0, 0.0
     for path in files[rank::world_size]:
         state = torch.load(path, map_location="cpu")
@@ -77,8 +81,9 @@ def clip_rsa_over_checkpoints(model, loaders, reference_rdm, files, device, rank
         if missing.unexpected_keys:
             raise RuntimeError(f"{path}: unexpected keys {missing.unexpected_keys[:3]} (adapter placement differs)")
         t0 = time.perf_counter()
-        emb = embeddings(model, loaders, device)
-        torch.cuda.synchronize(device)
+        emb = embed_fn(model, loaders, device)
+        if on_cuda:
+            torch.cuda.synchronize(device)
         t1 = time.perf_counter()
         rho, p, _ = evaluator(emb, want_rdm=False)
         t2 = time.perf_counter()
