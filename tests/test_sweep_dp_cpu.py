@@ -598,3 +598,92 @@ def test_pipelines_require_only_keys_the_reference_drivers_provide(tmp_path, mon
         missing = (new_needs | shared_needs) - set(cfg)
         assert not missing, (name, sorted(missing))
     assert not any(k.startswith("hba_") for k in base_needs | new_needs | shared_needs)      # our additions are .get() only
+
+
+# ------------------------------------------------------------------------------- bench.py: scheduler-run slice at N > 1
+_FAKE_GRID_TOOL = '''
+import argparse, json, os, subprocess, sys, time
+ap = argparse.ArgumentParser()
+for flag in ("--kind", "--gpus", "--per-gpu", "--max-start", "--batch-size", "--backbone", "--root", "--out"):
+    ap.add_argument(flag)
+a = ap.parse_args()
+assert "RANK" not in os.environ and "WORLD_SIZE" not in os.environ   # the tool must not look like a rank of the job
+if os.environ.get("FAKE_TOOL_MODE") == "hang":
+    child = subprocess.Popen([sys.executable, "-c", "import time; time.sleep(600)"])   # a sweep worker of its own
+    with open(os.environ["FAKE_TOOL_PIDS"], "w") as f:
+        f.write(f"{os.getpid()} {child.pid}")
+    time.sleep(600)
+time.sleep(1.5)
+gpus = a.gpus.split(",")
+json.dump({"conditions": len(gpus) * int(a.per_gpu), "conditions_per_hour": 123.0, "gpus": gpus, "wall_s": 1.5,
+           "per_condition": [{"epochs_trained": 7}] * (len(gpus) * int(a.per_gpu))}, open(a.out, "w"))
+'''
+
+
+def _fake_bench_root(tmp_path):
+    root = os.path.join(str(tmp_path), "fake_root")
+    os.makedirs(os.path.join(root, "tools"))
+    with open(os.path.join(root, "tools", "grid_sweep_bench.py"), "w") as f:
+        f.write(_FAKE_GRID_TOOL)
+    return root
+
+
+def _sched_worker(rank, world, port, fake_root, out_dir):
+    import argparse
+    import time
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    bench.ROOT = fake_root
+    args = argparse.Namespace(sweep_per_gpu=3, batch=32, backbone="ViT-tiny/14", sweep_timeout=120.0)
+    t0 = time.time()
+    res = bench.measure_sweep_scheduler(args, world, rank, dist)
+    torch.save({"res": res, "t0": t0, "t1": time.time()}, os.path.join(out_dir, f"sched{rank}.pt"))
+    dist.barrier()                 # the group is still usable by every rank afterwards (the ViT section follows)
+    dist.destroy_process_group()
+
+
+def test_bench_scheduler_slice_runs_on_rank0_while_other_ranks_wait_on_the_store(tmp_path):
+    """bench.py at N > 1 (the driver's 2 / 4 / 8-GPU runs): rank 0 alone launches the sweep tool over all N GPUs, the
+    other ranks block on the rendezvous store (no collective in flight) and return only once the slice is done."""
+    import torch.multiprocessing as mp
+    port = 29450 + os.getpid() % 200
+    mp.spawn(_sched_worker, args=(2, port, _fake_bench_root(tmp_path), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(str(tmp_path), f"sched{r}.pt"), weights_only=False) for r in (0, 1))
+    assert r1["res"] is None
+    res = r0["res"]
+    assert "error" not in res and res["conditions"] == 6 and res["gpus"] == ["0", "1"]
+    assert res["unit"] == "conditions/h" and res["epochs_per_condition"] == [7] * 6 and "per_condition" not in res
+    assert res["tool_wall_s"] >= 1.5
+    assert r1["t1"] >= r0["t0"] + 1.5      # rank 1 was released by rank 0's store key, not before the tool ended
+
+
+def test_bench_scheduler_slice_timeout_kills_the_tool_and_its_workers(tmp_path, monkeypatch):
+    """A slice that overruns --sweep-timeout is killed as a process group (tool + the workers it spawned) and
+    reported as an error; the bench line goes on."""
+    import argparse
+    import time
+    monkeypatch.syspath_prepend(ROOT)
+    import bench
+    monkeypatch.setattr(bench, "ROOT", _fake_bench_root(tmp_path))
+    pids_file = os.path.join(str(tmp_path), "pids")
+    monkeypatch.setenv("FAKE_TOOL_MODE", "hang")
+    monkeypatch.setenv("FAKE_TOOL_PIDS", pids_file)
+    for k in ("RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(sweep_per_gpu=1, batch=32, backbone="ViT-tiny/14", sweep_timeout=3.0)
+    t0 = time.time()
+    res = bench.measure_sweep_scheduler(args, 1, 0, None)
+    assert time.time() - t0 < 60
+    assert "timed out after 3.0 s" in res["error"]
+    tool_pid, child_pid = (int(x) for x in open(pids_file).read().split())
+    time.sleep(0.5)
+    for pid in (tool_pid, child_pid):
+        try:                       # (a zombie that init has not reaped yet still answers signal 0: read its state)
+            state = open(f"/proc/{pid}/stat").read().rsplit(")", 1)[1].split()[0]
+        except FileNotFoundError:
+            state = "gone"
+        assert state in ("gone", "Z"), f"pid {pid} survived the timeout in state {state}"
