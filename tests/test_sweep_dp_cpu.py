@@ -115,6 +115,39 @@ def test_workers_start_with_capped_cpu_thread_pools(tmp_path, monkeypatch):
     assert os.environ["OMP_NUM_THREADS"] == "7" and "OMP_WAIT_POLICY" not in os.environ   # the parent's own, restored
 
 
+def _report_visible_devices(cfg):
+    with open(os.path.join(cfg["output_base_directory"], f"visible_{cfg['training_run']}.txt"), "w") as f:
+        f.write(f"{os.environ.get('CUDA_VISIBLE_DEVICES')}|{cfg['cuda']}")
+    import time
+    time.sleep(1.0)    # (both workers get a condition)
+
+
+def test_workers_are_pinned_through_the_launchers_own_device_list(tmp_path, monkeypatch):
+    """`devices` of run_sweep are logical indices of the CALLING process: under a launcher that already restricted
+    the job (CUDA_VISIBLE_DEVICES="4,5", UUIDs, MIG slices) worker i gets the i-th entry of that list - never a
+    physical GPU outside it - and maps config['cuda'] onto the one device it then sees."""
+    from hba import sweep
+    assert sweep.pinned_device_env(1, "4,5") == "5" and sweep.pinned_device_env(0, " GPU-aa , GPU-bb ") == "GPU-aa"
+    assert sweep.pinned_device_env(0, "MIG-GPU-1/3/0") == "MIG-GPU-1/3/0"
+    for bad, cur in ((2, "4,5"), (0, ""), (-1, "0,1")):
+        with pytest.raises(ValueError):
+            sweep.pinned_device_env(bad, cur)
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "6,3")
+    conds = [{"training_run": e, "perturb_length": 1} for e in (1, 2)]
+    res = sweep.run_sweep({"output_base_directory": str(tmp_path), "cuda": 1}, conds, [0, 1],
+                          run_fn=_report_visible_devices, log=lambda *_: None)
+    assert all(r["ok"] for r in res), [r["error"] for r in res]
+    seen = {r["worker"]: open(os.path.join(str(tmp_path), f"visible_{r['condition']['training_run']}.txt")).read()
+            for r in res}
+    assert seen == {0: "6|0", 1: "3|0"}
+    assert os.environ["CUDA_VISIBLE_DEVICES"] == "6,3"           # the parent's own list is untouched
+    with pytest.raises(ValueError):                              # a device the job does not own: nothing is spawned
+        sweep.run_sweep({"output_base_directory": str(tmp_path)}, conds, [0, 2], run_fn=_report_visible_devices,
+                        log=lambda *_: None)
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES")
+    assert sweep.pinned_device_env(3) == "3"
+
+
 def _dp_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     from hba import dp

@@ -67,7 +67,8 @@ def write_dataset(root, n_train=1806, n_rsa=48, seed=0):
 def _baseline_worker(cfg):
     """Runs in a spawned process (so that the parent never initialises CUDA before the sweep workers pin their
     GPUs): the baseline run whose checkpoints the conditions resume from."""
-    os.environ["CUDA_VISIBLE_DEVICES"] = str(cfg.pop("_gpu"))
+    from hba import sweep
+    os.environ["CUDA_VISIBLE_DEVICES"] = sweep.pinned_device_env(cfg.pop("_gpu"))   # index into the launcher's own list
     import torch
     import functions.cvpr_train_behavior_things_pipeline_baseline as BASE
     cfg["criterion"] = torch.nn.MSELoss()

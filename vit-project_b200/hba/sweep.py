@@ -228,10 +228,27 @@ def cpu_threads_per_worker(n_workers):
 _THREAD_ENV = ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS")
 
 
-def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn, chain=False, cpu_threads=0):
+def pinned_device_env(device_id, current=None):
+    """The CUDA_VISIBLE_DEVICES value that pins a worker to the `device_id`-th device THIS process can see.
+    `devices` entries of `run_sweep` are logical indices (what torch.cuda.device(i) would address here): when the
+    launcher already restricted the job to some GPUs (CUDA_VISIBLE_DEVICES="4,5", a UUID list, a MIG slice), index i
+    means the i-th entry of that list, not physical GPU i - which may belong to another job."""
+    if current is None:
+        current = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if current is None:
+        return str(int(device_id))
+    entries = [e.strip() for e in current.split(",") if e.strip()]
+    if int(device_id) < 0 or int(device_id) >= len(entries):
+        raise ValueError(f"run_sweep: device {device_id} requested but CUDA_VISIBLE_DEVICES={current!r} exposes "
+                         f"{len(entries)} device(s)")
+    return entries[int(device_id)]
+
+
+def _worker(worker_id, device_id, tasks, results, base_config, layout, run_fn, chain=False, cpu_threads=0,
+            device_env=None):
     # pin the GPU before anything initialises CUDA in this process
     if device_id is not None:
-        os.environ["CUDA_VISIBLE_DEVICES"] = str(device_id)
+        os.environ["CUDA_VISIBLE_DEVICES"] = device_env if device_env is not None else pinned_device_env(device_id)
     if cpu_threads > 0:
         # (the environment set by run_sweep already sized the OpenMP / MKL pools at library load; this also covers
         # a parent that had the variables set to something else)
@@ -286,8 +303,10 @@ def run_sweep(base_config, conditions, devices, layout="sweep", run_fn=None, cos
     for _ in devices:
         tasks.put(None)
     n_threads = cpu_threads_per_worker(len(devices))
-    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn, chain, n_threads),
-                         daemon=False) for w, dev in enumerate(devices)]
+    # (resolved here, against the launcher's own CUDA_VISIBLE_DEVICES: a bad index fails before anything is spawned)
+    pins = [None if dev is None else pinned_device_env(dev) for dev in devices]
+    procs = [ctx.Process(target=_worker, args=(w, dev, tasks, results, base_config, layout, run_fn, chain, n_threads, pin),
+                         daemon=False) for w, (dev, pin) in enumerate(zip(devices, pins))]
     t0 = time.time()
     # the children read these when their OpenMP / MKL runtimes load (spawn: fresh interpreters inheriting os.environ);
     # passive waiting keeps idle pool threads off the cores the other workers' Python threads need
