@@ -7,7 +7,7 @@ file formats) in code that otherwise only executes on a B200.  NOT a test and NO
   * `hba.rsa.RSAEvaluator` by the NumPy / SciPy tail,
   * the `is_cuda` guards are stripped and "cuda" device strings mapped to the CPU.
 
-    python tools/emulate_vit_measure_tests.py [-k substring]
+    python tests/emulate_vit_measure_tests.py [-k substring]
 
 Numerical tolerances of the real tests are meaningless here (the emulation IS the oracle); a run that ends
 with "all emulated tests ran" only says the Python around the kernels is coherent.
