@@ -661,30 +661,36 @@ def _fake_bench_root(tmp_path):
     return root
 
 
-def _sched_worker(rank, world, port, fake_root, out_dir):
-    import argparse
-    import time
-    import torch.distributed as dist
-    sys.path.insert(0, ROOT)
-    import bench
-    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                      MASTER_PORT=str(port))
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    bench.ROOT = fake_root
-    args = argparse.Namespace(sweep_per_gpu=3, batch=32, backbone="ViT-tiny/14", sweep_timeout=120.0)
-    t0 = time.time()
-    res = bench.measure_sweep_scheduler(args, world, rank, dist)
-    torch.save({"res": res, "t0": t0, "t1": time.time()}, os.path.join(out_dir, f"sched{rank}.pt"))
-    dist.barrier()                 # the group is still usable by every rank afterwards (the ViT section follows)
-    dist.destroy_process_group()
+_SCHED_RANK_SCRIPT = '''
+import argparse, os, sys, time
+import torch
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+import bench
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")                      # env:// rendezvous through torchrun's agent store, as the driver's launch
+bench.ROOT = {fake_root!r}
+args = argparse.Namespace(sweep_per_gpu=3, batch=32, backbone="ViT-tiny/14", sweep_timeout=120.0)
+t0 = time.time()
+res = bench.measure_sweep_scheduler(args, world, rank, dist)
+torch.save({{"res": res, "t0": t0, "t1": time.time()}}, os.path.join({out_dir!r}, f"sched{{rank}}.pt"))
+dist.barrier()                 # the group is still usable by every rank afterwards (the ViT section follows)
+dist.destroy_process_group()
+'''
 
 
 def test_bench_scheduler_slice_runs_on_rank0_while_other_ranks_wait_on_the_store(tmp_path):
-    """bench.py at N > 1 (the driver's 2 / 4 / 8-GPU runs): rank 0 alone launches the sweep tool over all N GPUs, the
-    other ranks block on the rendezvous store (no collective in flight) and return only once the slice is done."""
-    import torch.multiprocessing as mp
-    port = 29450 + os.getpid() % 200
-    mp.spawn(_sched_worker, args=(2, port, _fake_bench_root(tmp_path), str(tmp_path)), nprocs=2, join=True)
+    """bench.py at N > 1 (the driver's 2 / 4 / 8-GPU runs, launched through torch.distributed.run): rank 0 alone
+    launches the sweep tool over all N GPUs, the other ranks block on the rendezvous store (no collective in flight)
+    and return only once the slice is done."""
+    script = os.path.join(str(tmp_path), "sched_rank.py")
+    with open(script, "w") as f:
+        f.write(_SCHED_RANK_SCRIPT.format(root=ROOT, fake_root=_fake_bench_root(tmp_path), out_dir=str(tmp_path)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29450 + os.getpid() % 200), script]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert p.returncode == 0, p.stderr[-3000:]
     r0, r1 = (torch.load(os.path.join(str(tmp_path), f"sched{r}.pt"), weights_only=False) for r in (0, 1))
     assert r1["res"] is None
     res = r0["res"]
