@@ -32,6 +32,9 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+T_START = time.perf_counter()   # process start, for --time-budget
+SWEEP_RESERVE_S = 150.0         # kept back from the budget for what follows the sweep slice (ViT section, CPU arm, teardown)
+SWEEP_MIN_S = 30.0              # ... but the slice always gets this much
 for _p in (ROOT, os.path.join(ROOT, "vit-project_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -53,7 +56,11 @@ def parse():
     ap.add_argument("--cpu-sample-images", type=int, default=0,
                     help="images per CPU-arm step (0 = the stated batch: same config as the GPU arm)")
     ap.add_argument("--sweep-per-gpu", type=int, default=4, help="grid conditions per GPU in the scheduler-run slice")
-    ap.add_argument("--sweep-timeout", type=float, default=600.0, help="limit of the scheduler-run sweep slice [s]")
+    ap.add_argument("--sweep-timeout", type=float, default=300.0, help="limit of the scheduler-run sweep slice [s]")
+    ap.add_argument("--time-budget", type=float, default=700.0,
+                    help="wall clock the whole run should stay within [s]: the scheduler-run sweep slice (the one section "
+                         "whose duration depends on the host: process start-up of N workers) gets what is left of it "
+                         "minus a reserve for the ViT section and the teardown, at most --sweep-timeout")
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true")
     ap.add_argument("--roofline-seconds", type=float, default=2.6,
@@ -364,17 +371,23 @@ def measure_sweep_scheduler(args, world, rank, dist):
                "--max-start", "10", "--batch-size", str(args.batch), "--backbone", args.backbone,
                "--root", tempfile.mkdtemp(prefix="hba_grid_"), "--out", out_path]
         t0 = time.perf_counter()
+        # the slice may use what is left of the run's time budget (minus a reserve for the ViT section and the
+        # teardown): a driver that limits the whole run must still get its JSON line, which is printed at the end
+        limit = float(args.sweep_timeout)
+        budget = getattr(args, "time_budget", None)
+        if budget:
+            limit = max(SWEEP_MIN_S, min(limit, budget - (t0 - T_START) - SWEEP_RESERVE_S))
         # own session: on a timeout the tool AND the worker processes it spawned are killed together, so that no
         # stray worker holds a GPU when the next section starts
         proc = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                 start_new_session=True)
         try:
-            out_txt, err_txt = proc.communicate(timeout=args.sweep_timeout)
+            out_txt, err_txt = proc.communicate(timeout=limit)
         except subprocess.TimeoutExpired:
             import signal
             os.killpg(proc.pid, signal.SIGKILL)
             out_txt, err_txt = proc.communicate()
-            err_txt = f"timed out after {args.sweep_timeout} s\n" + (err_txt or "")
+            err_txt = f"timed out after {limit:.1f} s\n" + (err_txt or "")
         proc.stdout_text, proc.stderr_text = out_txt, err_txt
         if os.path.exists(out_path):
             full = json.load(open(out_path))

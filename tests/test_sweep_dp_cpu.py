@@ -718,6 +718,17 @@ def test_bench_scheduler_slice_timeout_kills_the_tool_and_its_workers(tmp_path, 
     res = bench.measure_sweep_scheduler(args, 1, 0, None)
     assert time.time() - t0 < 60
     assert "timed out after 3.0 s" in res["error"]
+    # --time-budget: the slice gets what is left of the run's budget minus the reserve for the sections after it
+    monkeypatch.setattr(bench, "SWEEP_MIN_S", 1.0)
+    args.sweep_timeout = 300.0
+    args.time_budget = (time.perf_counter() - bench.T_START) + bench.SWEEP_RESERVE_S + 2.5
+    t0 = time.time()
+    res = bench.measure_sweep_scheduler(args, 1, 0, None)
+    assert 1.0 < time.time() - t0 < 30 and "timed out after 2." in res["error"]
+    args.time_budget = 1.0                                  # budget already spent: the floor applies
+    t0 = time.time()
+    res = bench.measure_sweep_scheduler(args, 1, 0, None)
+    assert time.time() - t0 < 30 and "timed out after 1.0 s" in res["error"]
     tool_pid, child_pid = (int(x) for x in open(pids_file).read().split())
     time.sleep(0.5)
     for pid in (tool_pid, child_pid):
