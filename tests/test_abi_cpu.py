@@ -160,3 +160,36 @@ def test_tokenize_refuses_made_up_ids_for_a_real_checkpoint(tmp_path, monkeypatc
     finally:
         clip._CHECKPOINT.update(saved)
         st.load.cache_clear()
+
+
+def _download_worker(root, out):
+    import time
+    import torch
+    from src.models.CLIPs.clip_hba import clip
+    t0 = time.time()
+    path = clip._download(clip._MODELS["ViT-tiny/14"], root)
+    sd = torch.load(path, map_location="cpu")          # must never be a half-written file
+    with open(out, "w") as f:
+        f.write(f"{os.getpid()} {os.path.getmtime(path)!r} {len(sd)} {float(sd['logit_scale'])!r} {t0!r}")
+
+
+def test_synthetic_checkpoint_is_materialised_once_under_concurrent_first_use(tmp_path):
+    """Eight sweep workers / torchrun ranks on a fresh machine all find no cached checkpoint at the same moment: one
+    generates it under a lock, the file appears atomically, nobody loads a partial file, and a completed file is
+    never replaced (its mtime keys the per-process frozen-model cache)."""
+    import multiprocessing as mp
+    root = str(tmp_path / "clip_cache")
+    ctx = mp.get_context("spawn")
+    outs = [str(tmp_path / f"w{i}.txt") for i in range(6)]
+    procs = [ctx.Process(target=_download_worker, args=(root, o)) for o in outs]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    rows = [open(o).read().split() for o in outs]
+    assert len({r[0] for r in rows}) == 6                      # six processes ...
+    assert len({r[1] for r in rows}) == 1                      # ... saw one and the same file (mtime unchanged)
+    assert len({(r[2], r[3]) for r in rows}) == 1
+    left = sorted(os.listdir(root))
+    assert left == ["ViT-tiny-14.pt", "ViT-tiny-14.pt.lock"], left      # no temporary files stay behind

@@ -240,9 +240,42 @@ def _download(url, root):
                               "using seeded random-init weights of the same architecture", RuntimeWarning)
                 target, synthetic = os.path.join(root, "synthetic-" + fname), True
             if not os.path.exists(target):
-                torch.save(synthetic_state_dict(fname), target)
+                _materialise_once(target, lambda: synthetic_state_dict(fname))
     _CHECKPOINT.update(synthetic=synthetic, path=target)
     return target
+
+
+def _materialise_once(target, make_state_dict):
+    """Writes `target` exactly once however many processes ask for it at the same time (the 8 workers of a sweep or
+    the 8 ranks of a torchrun launch on a fresh machine): one process generates under an advisory lock, the others
+    wait and then find the file; the file appears atomically (temporary file + hard link), so a concurrent reader
+    can never `torch.load` a half-written checkpoint, and a completed file is never replaced (its mtime keys the
+    per-process model cache of functions._pipeline_core.load_clip_to_cpu)."""
+    lock = None
+    try:
+        import fcntl
+        lock = open(target + ".lock", "w")
+        fcntl.flock(lock, fcntl.LOCK_EX)
+    except (ImportError, OSError):
+        lock = None          # (no advisory locks on this file system: the atomic publication below still holds)
+    try:
+        if os.path.exists(target):
+            return
+        tmp = f"{target}.tmp{os.getpid()}"
+        torch.save(make_state_dict(), tmp)
+        try:
+            os.link(tmp, target)             # atomic create-if-absent
+        except FileExistsError:
+            pass
+        except OSError:
+            os.replace(tmp, target)          # (no hard links here: atomic replace; same seeded content)
+            tmp = None
+        finally:
+            if tmp is not None and os.path.exists(tmp):
+                os.unlink(tmp)
+    finally:
+        if lock is not None:
+            lock.close()
 
 
 def _pseudo_ids(text, context_length):
