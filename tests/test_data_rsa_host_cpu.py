@@ -203,3 +203,28 @@ def test_auto_k_slices_for_row_gemms_and_weight_gradients():
         s8, s4 = ops.auto_k_slices(M, N, K), ops.auto_k_slices(M, N, K, min_kblocks=4)
         assert 1 <= s8 <= s4 and s4 > 1
         assert (K // 64) // s4 >= 4
+
+
+def test_trunk_cache_grows_when_a_later_run_brings_more_images(monkeypatch):
+    """The frozen CLIP (and its engine) is reused by every run of a process: a second run on another image directory
+    draws ids beyond the first cache's capacity.  `enable_trunk_cache` then installs a larger, empty cache and drops
+    the graphs captured on the model (they gather out of the old buffers) instead of failing the first lookup."""
+    import types
+    from functions import _pipeline_core as core
+    from hba import data
+    eng = types.SimpleNamespace(trunk_cache=None)
+    model = torch.nn.Module()
+    model.clip_model = types.SimpleNamespace(hba_engine=lambda: eng)
+    monkeypatch.setattr(data, "_NAME_IDS", {("a", f"img{i}"): i for i in range(100)})
+    core.enable_trunk_cache(model, 100)
+    first = eng.trunk_cache
+    assert first.capacity == 164
+    model.__dict__["_hba_train_step"] = object()
+    model.__dict__["_hba_forward_graphs"] = object()
+    core.enable_trunk_cache(model, 100)                          # same image set again: nothing changes
+    assert eng.trunk_cache is first and "_hba_train_step" in model.__dict__
+    data._NAME_IDS.update({("b", f"img{i}"): 100 + i for i in range(100)})
+    core.enable_trunk_cache(model, 100)                          # another directory: ids 100..199 > capacity 164
+    assert eng.trunk_cache is not first and eng.trunk_cache.capacity == 264 and not eng.trunk_cache.present
+    assert "_hba_train_step" not in model.__dict__ and "_hba_forward_graphs" not in model.__dict__
+    core.enable_trunk_cache(torch.nn.Module(), 10)               # a model without a libhba engine: no-op

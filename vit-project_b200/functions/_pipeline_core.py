@@ -437,10 +437,11 @@ def resident_loaders(config, dataset, train_dataset, test_dataset, inference_dat
                      dataloader_generator, train_indices=None, test_indices=None):
     """HBM-resident equivalents of the three DataLoaders of NEW:1123-1126 (same batch order and
     generator consumption; images decoded once per process instead of once per epoch)."""
-    key = (config['csv_file'], config['img_dir'], str(device))
+    # (keyed by the csv's mtime as well: a rewritten csv under the same path is decoded again)
+    key = (config['csv_file'], os.path.getmtime(config['csv_file']), config['img_dir'], str(device))
     if key not in _STORES:
         _STORES[key] = ResidentStore(dataset, device)
-    ikey = (config['inference_csv_file'], config['img_dir'], str(device))
+    ikey = (config['inference_csv_file'], os.path.getmtime(config['inference_csv_file']), config['img_dir'], str(device))
     if ikey not in _STORES:
         _STORES[ikey] = ResidentStore(inference_dataset, device)
     bs = config['batch_size']
@@ -453,11 +454,22 @@ def resident_loaders(config, dataset, train_dataset, test_dataset, inference_dat
 
 
 def enable_trunk_cache(model, n_images):
-    """Frozen-trunk activation cache (hba.engine.TrunkCache) sized for every distinct image."""
+    """Frozen-trunk activation cache (hba.engine.TrunkCache) sized for every distinct image.
+
+    The engine (and with it the cache) belongs to the frozen CLIP, which a process reuses from run to run
+    (`load_clip_to_cpu`): a later run on ANOTHER image set gets ids beyond the first run's capacity.  The cache is
+    then replaced by a larger, empty one - and the step / forward graphs captured on this model, which replay
+    gathers out of the old buffers, are dropped with it."""
     eng = _engine_of(model)
-    if eng is not None and eng.trunk_cache is None:
-        from hba.data import _NAME_IDS
-        eng.trunk_cache = TrunkCache(max(n_images, len(_NAME_IDS)) + 64)
+    if eng is None:
+        return
+    from hba.data import _NAME_IDS
+    need = max(n_images, len(_NAME_IDS))
+    if eng.trunk_cache is None or eng.trunk_cache.capacity < need:
+        if eng.trunk_cache is not None:
+            for holder in ("_hba_train_step", "_hba_forward_graphs"):
+                _unwrap(model).__dict__.pop(holder, None)
+        eng.trunk_cache = TrunkCache(need + 64)
 
 
 def _engine_of(model):
@@ -627,9 +639,10 @@ def behavioral_RSA(model, inference_loader, device, logger=None):
     emb = torch.cat(chunks, 0)
     log(f"First 10 image names: {names[:5]}")
     log(f"Embedding matrix shape: {tuple(emb.shape)}\n")
-    key = (inference_loader.dataset.RDM48_triplet_dir, str(emb.device))
+    path = inference_loader.dataset.RDM48_triplet_dir
+    key = (path, os.path.getmtime(path), str(emb.device))   # (a rewritten .mat is read again)
     if key not in _RSA_CACHE:
-        _RSA_CACHE[key] = rsa.RSAEvaluator(_reference_rdm(key[0]), emb.device)
+        _RSA_CACHE[key] = rsa.RSAEvaluator(_reference_rdm(path), emb.device)
     return _RSA_CACHE[key](emb)
 
 
