@@ -295,3 +295,34 @@ def test_epoch_loops_equal_the_reference_executed(tmp_path):
         live = json.load(open(tmp_path / "reference.json"))
         for name in gold["cases"]:
             assert live["cases"][name] == got["cases"][name], name           # every field identical, CSV text included
+
+
+def test_reusing_the_frozen_clip_under_a_live_model_warns(monkeypatch):
+    """A process shares ONE frozen CLIP between the CLIPHBA wrappers it builds one after another (sweep workers).
+    Building a second wrapper while the first is still referenced strips the first one's adapters: that is said
+    aloud; the sequential case (first wrapper gone, or only held by a reference cycle) stays silent."""
+    import gc
+    import warnings
+    monkeypatch.setenv("HBA_SYNTHETIC_OK", "1")
+    monkeypatch.setenv("HBA_REUSE_MODEL", "1")
+    names = ["a thing", "another thing"]
+    first = core.CLIPHBA(names, backbone_name="ViT-tiny/14", pos_embedding=True)
+    core.apply_dora_to_ViT(first, 2, 1, r=4)
+    shared = first.clip_model
+    first.__dict__["_cycle"] = [first]                    # a finished run's wrapper, alive only through a cycle
+    del first
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        second = core.CLIPHBA(names, backbone_name="ViT-tiny/14", pos_embedding=True)      # silent
+    assert second.clip_model is shared
+    assert all(isinstance(b.attn.out_proj, torch.nn.Linear) for b in shared.visual.transformer.resblocks)
+    core.apply_dora_to_ViT(second, 2, 1, r=4)
+    import pytest
+    with pytest.warns(RuntimeWarning, match="still alive and shares its frozen CLIP"):
+        third = core.CLIPHBA(names, backbone_name="ViT-tiny/14", pos_embedding=True)       # `second` is in use
+    assert third.clip_model is shared and not list(core.find_dora_paths(second))           # ... and lost its adapters
+    monkeypatch.setenv("HBA_REUSE_MODEL", "0")
+    fourth = core.CLIPHBA(names, backbone_name="ViT-tiny/14", pos_embedding=True)
+    assert fourth.clip_model is not shared
+    del second, third, fourth
+    gc.collect()

@@ -182,6 +182,7 @@ def load_clip_to_cpu(backbone_name):
     key = (backbone_name, path, os.path.getmtime(path))
     if reuse and key in _FROZEN_MODELS:
         model = _FROZEN_MODELS[key]
+        _warn_if_still_owned(model)
         for tower in (model.visual.transformer, model.transformer):
             for blk in tower.resblocks:
                 if isinstance(blk.attn.out_proj, DoRALayer):
@@ -198,6 +199,24 @@ def load_clip_to_cpu(backbone_name):
     return model
 
 
+_OWNERS = {}   # id(frozen clip model) -> weakref of the CLIPHBA built on it last
+
+
+def _warn_if_still_owned(clip_model):
+    """The shared frozen CLIP is about to be re-adapted for a new CLIPHBA: an earlier CLIPHBA on it that is still in
+    use loses its adapters.  Sequential runs (a sweep worker) never hit this - the finished run's wrapper is garbage,
+    at most held by a reference cycle - so this only speaks up for two models kept alive side by side."""
+    ref = _OWNERS.get(id(clip_model))
+    if ref is not None and ref() is not None:
+        gc.collect()
+        if ref() is not None:
+            import warnings
+            warnings.warn("a CLIPHBA built earlier in this process is still alive and shares its frozen CLIP with the "
+                          "one being built: its adapters are removed now and it must not be used any more. Set "
+                          "HBA_REUSE_MODEL=0 to give every CLIPHBA its own copy of the model.", RuntimeWarning,
+                          stacklevel=4)
+
+
 class CLIPHBA(nn.Module):
     """NEW:268-304: frozen CLIP scored against the fixed class prompts -> [B, n_prompts] fp32."""
 
@@ -205,6 +224,8 @@ class CLIPHBA(nn.Module):
         super().__init__()
         self.num_clip = len(classnames)
         self.clip_model = load_clip_to_cpu(backbone_name)
+        import weakref
+        _OWNERS[id(self.clip_model)] = weakref.ref(self)
         self.clip_model.float()
         self.pos_embedding = pos_embedding
         for p in self.clip_model.parameters():
