@@ -466,7 +466,9 @@ class Engine:
             a_op = self._opbuf("t.a_op", max(S, 128), d, zero=True)
             ops.split_bf16(a_eot, a_op)
             self.launches += 6
-            cache = {"key": key, "a_eot": a_eot, "x_eot": x_eot, "a_op": a_op}
+            # (the entry keeps the token tensor alive: the key holds its ADDRESS, and the caching allocator would hand
+            # the address of a freed prompt tensor to the next model's prompts - other class names, same key)
+            cache = {"key": key, "a_eot": a_eot, "x_eot": x_eot, "a_op": a_op, "tokens": tokens}
             if self.cache_text:
                 self._text_cache = cache
         blkZ = tw.blocks[L - 1]
