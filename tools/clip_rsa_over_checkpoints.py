@@ -53,6 +53,8 @@ def main(argv=None):
     logger.addHandler(logging.NullHandler())
     config = {"backbone": a.backbone, "vision_layers": a.vision_layers, "transformer_layers": a.transformer_layers,
               "rank": a.dora_rank}
+    # (every DoRA tensor comes from a checkpoint here: the random draws of the model construction decide nothing)
+    os.environ.setdefault("HBA_CONSTRUCTOR_RNG", "0")
     model = core.build_model(config, device, logger).to(device)
     train_set = core.ThingsDataset(csv_file=a.csv_file, img_dir=a.img_dir)
     rsa_set = core.ThingsInferenceDataset(inference_csv_file=a.inference_csv_file, img_dir=a.img_dir,

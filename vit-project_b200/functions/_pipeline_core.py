@@ -933,11 +933,35 @@ def open_logger(config):
     return logger
 
 
+def rng_state_will_be_restored(config):
+    """True when `run_behavioral_training` (NEW:1154-1199) is going to overwrite everything the global RNG decides
+    before training starts: the DoRA parameters come from a checkpoint AND the random states of that epoch are
+    loaded.  Only then may the draws of the model construction be skipped (see `build_model`)."""
+    resume = config.get("resume_from_epoch", 0)
+    if resume <= 0 or "training_run" not in config:
+        return False
+    if config.get("resume_dora_parameters_path"):
+        dora = os.path.join(config["resume_dora_parameters_path"], f"epoch{resume}_dora_params.pth")
+    else:
+        dora = os.path.join(config.get("baseline_dora_directory") or "", f"epoch{config['training_run'] - 1}_dora_params.pth")
+    prior = config.get("resume_random_state_path") or config.get("baseline_random_state_path")
+    return bool(prior) and os.path.exists(dora) and os.path.exists(os.path.join(prior, f"epoch{resume}_random_states.pth"))
+
+
 def build_model(config, device, logger):
+    """CLIPHBA + DoRA surgery of NEW:1128-1152 / BASE:760-778.  The reference's `CLIPHBA(...)` constructs the
+    published CLIP with its random initialisation before loading the checkpoint, which moves the global RNG; the
+    plug-in `clip.build_model` draws nothing, so for a run whose RNG state is not restored from a checkpoint
+    afterwards the same draws are replayed here (`clip.replay_constructor_draws`) - the DoRA matrices drawn next
+    are then the reference's.  HBA_CONSTRUCTOR_RNG=1 / 0 forces / forbids the replay."""
     from functions.spose_dimensions import classnames66
     pos_embedding = config["backbone"] != "RN50"
     logger.info(f"pos_embedding is {pos_embedding}")
     model = CLIPHBA(classnames=classnames66, backbone_name=config["backbone"], pos_embedding=pos_embedding)
+    mode = os.environ.get("HBA_CONSTRUCTOR_RNG", "")
+    if mode == "1" or (mode != "0" and not rng_state_will_be_restored(config)):
+        if hasattr(clip, "replay_constructor_draws"):
+            clip.replay_constructor_draws(model.clip_model)
     apply_dora_to_ViT(model, n_vision_layers=config["vision_layers"],
                       n_transformer_layers=config["transformer_layers"], r=config["rank"],
                       dora_dropout=0.1)
