@@ -11,6 +11,11 @@ C-ABI calls (which buffers feed which call, the graph pruning, the cache, the fu
 wiring), against the oracle model and against the reference's own pipeline executed on the CPU.  It says nothing about
 the CUDA kernels - those are compared with their formulas on a B200 by the `-m gpu` tests.
 
+Every entry point of the header is restated (CLIP path and ViT-B/16 path).  The restatement is pinned by the GPU op
+tests themselves: tests/emulate_clip_gpu_tests.py runs tests/test_gpu_ops.py on it, i.e. each restated entry point is
+compared with the same torch / fp64-autograd / numpy / scipy formulas that judge the CUDA kernels.  Not restated: the
+library's argument validation (HBA_ERR_ARG paths) and anything about scheduling (split-K, max_ctas, workspaces).
+
 Arithmetic notes: GEMMs accumulate hi.hi + lo.hi + hi.lo in fp32 like the kernel (nsplit = 3) or the plain bf16 product
 (nsplit = 1); attention keeps P in fp32 (the tensor-core kernel rounds P to bf16); everything else is the header's
 formula in fp32 / fp64.
@@ -384,6 +389,130 @@ class RefLib:
             v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
             p.addcdiv_(m, v.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
         return self._ok("hba_adamw_multi")
+
+    def hba_sgd_multi(self, ptrs, sizes, n, total, lr, momentum, weight_decay, first_step, skip_flag, stream):
+        """torch.optim.SGD(momentum, weight_decay, dampening 0, no nesterov), VIT:294-299."""
+        if _addr(skip_flag) and int(flat(skip_flag, 1, torch.int32)[0]) != 0:
+            return self._ok("hba_sgd_multi")
+        table = flat(ptrs, 3 * n, torch.int64).view(n, 3)
+        sz = flat(sizes, n, torch.int64)
+        for i in range(n):
+            k = int(sz[i])
+            p, g, buf = (flat(int(table[i, j]), k, torch.float32) for j in range(3))
+            d = g + weight_decay * p
+            if first_step:
+                buf.copy_(d)
+            else:
+                buf.mul_(momentum).add_(d)
+            p.add_(buf, alpha=-lr)
+        return self._ok("hba_sgd_multi")
+
+    def hba_sgd_staged(self, ptrs, prefix4, n, total4, lr, momentum, weight_decay, first_step, skip_flag, stream):
+        if _addr(skip_flag) and int(flat(skip_flag, 1, torch.int32)[0]) != 0:
+            return self._ok("hba_sgd_staged")
+        table = flat(ptrs, 4 * n, torch.int64).view(n, 4)
+        pre = flat(prefix4, n, torch.int64).tolist() + [int(total4)]
+        for i in range(n):
+            k = 4 * (pre[i + 1] - pre[i])
+            p, g, buf = (flat(int(table[i, j]), k, torch.float32) for j in range(3))
+            d = g + weight_decay * p
+            if first_step:
+                buf.copy_(d)
+            else:
+                buf.mul_(momentum).add_(d)
+            p.add_(buf, alpha=-lr)
+            if int(table[i, 3]):
+                flat(int(table[i, 3]), k, torch.bfloat16).copy_(p.to(torch.bfloat16))
+        return self._ok("hba_sgd_staged")
+
+    # ---------------------------------------------------------------- ViT-B/16 training step (VIT:125-165)
+    def hba_softmax_ce_fwd_bwd(self, logits, ld, labels, B, Cn, loss, d_logits, ld_d, correct, workspace, stream):
+        z = mat(logits, B, Cn, ld, torch.float32)
+        y = flat(labels, B, torch.int64)
+        logp = torch.log_softmax(z, 1)
+        flat(loss, 1, torch.float32)[0] = -logp[torch.arange(B), y].mean()
+        if _addr(d_logits):
+            d = torch.softmax(z, 1)
+            d[torch.arange(B), y] -= 1
+            mat(d_logits, B, Cn, ld_d, torch.float32).copy_(d / B)
+        if _addr(correct):
+            flat(correct, 1, torch.int32)[0] = int((z.argmax(1) == y).sum())
+        return self._ok("hba_softmax_ce_fwd_bwd")
+
+    def hba_colsum(self, x, dtype, rows, cols, ld, out, accumulate, workspace, stream):
+        s_ = mat(x, rows, cols, ld, DT[dtype]).float().sum(0)
+        o = flat(out, cols, torch.float32)
+        o.copy_(o + s_ if accumulate else s_)
+        return self._ok("hba_colsum")
+
+    def _ln_stats(self, x, rows, cols, ldx, row_step, eps):
+        xv = self._rows(x, rows, cols, ldx, row_step)
+        mu = xv.mean(1, keepdim=True)
+        rstd = 1.0 / torch.sqrt(((xv - mu) ** 2).mean(1, keepdim=True) + eps)
+        return (xv - mu) * rstd, rstd
+
+    def hba_layernorm_param_grad(self, dy, ld_dy, x, rows, cols, ldx, row_step, eps, dgamma_dbeta, accumulate,
+                                 workspace, stream):
+        xhat, _ = self._ln_stats(x, rows, cols, ldx, row_step, eps)
+        g = mat(dy, rows, cols, ld_dy, torch.float32)
+        new = torch.cat([(g * xhat).sum(0), g.sum(0)])
+        o = flat(dgamma_dbeta, 2 * cols, torch.float32)
+        o.copy_(o + new if accumulate else new)
+        return self._ok("hba_layernorm_param_grad")
+
+    def hba_layernorm_bwd_fused(self, dy, ld_dy, x, rows, cols, ldx, gamma, eps, dx, ld_dx, accumulate, dx_bf16, ld_b,
+                                lo_off, dgamma_dbeta, accumulate_params, dx_colsum, workspace, stream):
+        xhat, rstd = self._ln_stats(x, rows, cols, ldx, 1, eps)
+        g0 = mat(dy, rows, cols, ld_dy, torch.float32)
+        g = g0 * flat(gamma, cols, torch.float32)
+        d = rstd * (g - g.mean(1, keepdim=True) - xhat * (g * xhat).mean(1, keepdim=True))
+        out = mat(dx, rows, cols, ld_dx, torch.float32)
+        out.copy_(out + d if accumulate else d)
+        if _addr(dx_bf16):
+            write_operand(dx_bf16, out.clone(), ld_b, lo_off)
+        if _addr(dgamma_dbeta):
+            new = torch.cat([(g0 * xhat).sum(0), g0.sum(0)])
+            o = flat(dgamma_dbeta, 2 * cols, torch.float32)
+            o.copy_(o + new if accumulate_params else new)
+        if _addr(dx_colsum):
+            flat(dx_colsum, cols, torch.float32).copy_(out.sum(0))
+        return self._ok("hba_layernorm_bwd_fused")
+
+    def _attn_bwd(self, q, k, v, do, causal):
+        T = q.shape[2]
+        s_ = q @ k.transpose(-1, -2) / 8.0
+        if causal:
+            s_ = s_.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
+        p = torch.softmax(s_, -1)
+        dv = p.transpose(-1, -2) @ do
+        dp = do @ v.transpose(-1, -2)
+        ds = p * (dp - (dp * p).sum(-1, keepdim=True)) / 8.0
+        return ds @ k, ds.transpose(-1, -2) @ q, dv
+
+    def hba_attention_bwd(self, qkv, qkv_dtype, ld_qkv, B, T, H, causal, d_out, do_dtype, ld_do, d_qkv, dq_dtype,
+                          ld_dqkv, stream):
+        q, k, v = self._qkv(qkv, qkv_dtype, ld_qkv, B, T, H)
+        do = mat(d_out, B * T, H * 64, ld_do, DT[do_dtype]).float().reshape(B, T, H, 64).permute(0, 2, 1, 3)
+        full = torch.cat([t.permute(0, 2, 1, 3).reshape(B * T, H * 64) for t in self._attn_bwd(q, k, v, do, causal)], 1)
+        mat(d_qkv, B * T, 3 * H * 64, ld_dqkv, DT[dq_dtype]).copy_(full.to(DT[dq_dtype]))
+        return self._ok("hba_attention_bwd")
+
+    def hba_attention_fwd_lse(self, qkv, ld_qkv, B, T, H, causal, out, ld_out, lse, stream):
+        q, k, v = self._qkv(qkv, 1, ld_qkv, B, T, H)
+        s_ = q @ k.transpose(-1, -2) / 8.0
+        if causal:
+            s_ = s_.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1), float("-inf"))
+        o = (torch.softmax(s_, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, H * 64)
+        mat(out, B * T, H * 64, ld_out, torch.bfloat16).copy_(o.to(torch.bfloat16))
+        flat(lse, B * H * T, torch.float32).copy_((torch.logsumexp(s_, -1) / math.log(2.0)).reshape(-1))
+        return self._ok("hba_attention_fwd_lse")
+
+    def hba_attention_bwd_lse(self, qkv, ld_qkv, B, T, H, causal, out, ld_out, d_out, ld_do, lse, d_qkv, ld_dqkv, stream):
+        q, k, v = self._qkv(qkv, 1, ld_qkv, B, T, H)
+        do = mat(d_out, B * T, H * 64, ld_do, torch.bfloat16).float().reshape(B, T, H, 64).permute(0, 2, 1, 3)
+        full = torch.cat([t.permute(0, 2, 1, 3).reshape(B * T, H * 64) for t in self._attn_bwd(q, k, v, do, causal)], 1)
+        mat(d_qkv, B * T, 3 * H * 64, ld_dqkv, torch.bfloat16).copy_(full.to(torch.bfloat16))
+        return self._ok("hba_attention_bwd_lse")
 
     # ---------------------------------------------------------------- RSA tail (NEW:625-652)
     def hba_rdm_f64(self, E, N, Dm, rdm, tri, stream):

@@ -157,3 +157,25 @@ def test_run_behavioral_training_equals_the_reference_executed(tmp_path):
     assert got["c_abi_calls"]["hba_gemm_bf16"] > 500 and got["c_abi_calls"]["hba_adamw_multi"] == 27
     if have_reference:
         compare(json.load(open(tmp_path / "reference.json")), 2e-5, 1e-6)
+
+
+def test_gpu_test_files_dry_run_on_the_cpu_restatement():
+    """The GPU test files themselves - ops, model, pipeline, ViT - executed by pytest on the CPU with libhba served by
+    its restatement (tests/emulate_clip_gpu_tests.py; only the captured-graph tests and the C-ABI's argument
+    validation need the device).  Two things are pinned at once: the product's host side against every oracle /
+    golden those tests hold, and the restatement against the formulas that judge the CUDA kernels on the B200."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emulate_clip_gpu_tests as emu
+    tool = os.path.join(ROOT, "tests", "emulate_clip_gpu_tests.py")
+    procs = {f: subprocess.Popen([sys.executable, tool, os.path.join(ROOT, "tests", f)], stdout=subprocess.PIPE,
+                                 stderr=subprocess.STDOUT, text=True, env=dict(os.environ, OMP_NUM_THREADS="2"))
+             for f in emu.DRY_RUN_FILES}
+    counts = {}
+    for f, p in procs.items():
+        out, _ = p.communicate(timeout=800)
+        assert p.returncode == 0, f"{f}:\n{out[-3000:]}"
+        tail = [l for l in out.splitlines() if " passed" in l][-1]
+        assert "failed" not in tail and "error" not in tail, tail
+        counts[f] = int(tail.split(" passed")[0].split()[-1])
+    assert counts["test_gpu_ops.py"] >= 90 and counts["test_gpu_pipeline.py"] >= 10, counts
+    assert counts["test_gpu_model.py"] >= 6 and counts["test_gpu_vit.py"] >= 80, counts
