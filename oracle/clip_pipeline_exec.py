@@ -160,6 +160,22 @@ def run_arm(arm):
         if stack is not None:
             calls = ref_lib.calls
             out["c_abi_calls"] = {n: calls.count(n) for n in sorted(set(calls))}
+            # RSA at scale over the checkpoints the baseline left behind (hba.rsa_scale, BASELINE config 5), restricted
+            # to the inference set and its own reference RDM: must give back the rho train_model logged per epoch
+            import logging
+            import scipy.io
+            import functions._pipeline_core as core
+            from hba import rsa_scale
+            from hba.data import ResidentLoader, ResidentStore
+            os.environ["HBA_CONSTRUCTOR_RNG"] = "0"
+            model = core.build_model(dict(common), torch.device("cpu"), logging.getLogger("exec_rsa_scale"))
+            inf = core.ThingsInferenceDataset(common["inference_csv_file"], img_dir, common["RDM48_triplet_dir"])
+            loader = ResidentLoader(ResidentStore(inf, "cpu"), BATCH, shuffle=False, dataset=inf)
+            core.enable_trunk_cache(model, len(inf))
+            rows, stats = rsa_scale.clip_rsa_over_checkpoints(
+                model, [loader], scipy.io.loadmat(common["RDM48_triplet_dir"])["RDM48_triplet"],
+                rsa_scale.find_dora_checkpoints(f"{b}/dora"), "cpu", log=None, root=b)
+            out["rsa_over_checkpoints"] = rows
     finally:
         if stack is not None:
             stack.close()

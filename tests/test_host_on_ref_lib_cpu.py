@@ -157,6 +157,14 @@ def test_run_behavioral_training_equals_the_reference_executed(tmp_path):
     assert got["c_abi_calls"]["hba_gemm_bf16"] > 500 and got["c_abi_calls"]["hba_adamw_multi"] == 27
     if have_reference:
         compare(json.load(open(tmp_path / "reference.json")), 2e-5, 1e-6)
+    # hba.rsa_scale over the baseline's DoRA checkpoints, restricted to the inference set: the rho of every checkpoint
+    # is the one `train_model` wrote for that epoch (same embeddings through the cached forward, same RSA tail)
+    base_rows = list(csv.reader(got["runs"]["baseline"]["csv"].splitlines()))[1:]
+    scale = got["rsa_over_checkpoints"]
+    assert [r["epoch"] for r in scale] == [1, 2, 3] and [r["checkpoint"] for r in scale] == [
+        f"dora/epoch{e}_dora_params.pth" for e in (1, 2, 3)]
+    for r, row in zip(scale, base_rows):
+        assert abs(r["behavioral_rsa_rho"] - float(row[3])) < 1e-12 and abs(r["behavioral_rsa_p_value"] - float(row[4])) < 1e-12
 
 
 def test_gpu_test_files_dry_run_on_the_cpu_restatement():
