@@ -23,7 +23,7 @@ perturbation condition (NEW: random targets in epoch 3, resumed from the baselin
 epoch 4), a label-shuffle condition from the same checkpoints, and a condition that perturbs epoch 1 (uniform images;
 nothing to resume: its DoRA matrices are drawn after the model construction, like the baseline's).  Compared:
 every result CSV, the DoRA checkpoint of the last epoch, the optimizer step count and the RNG / generator state of the
-last random-state checkpoint.
+last random-state checkpoint.  Two more baseline runs adapt 2 + 2 and 3 + 2 blocks (the general placement path of hba.engine).
 
     python oracle/clip_pipeline_exec.py --arm reference --out tests/golden/clip_pipeline_exec.json
     python oracle/clip_pipeline_exec.py --arm product --out /tmp/product.json
@@ -157,6 +157,21 @@ def run_arm(arm):
                 resume_from_epoch=run - 1, perturb_type=kind, perturb_length=1, perturb_distribution=dist,
                 perturb_seed=42, previous_training_res_path=f"{b}/res.csv"))
             out["runs"][name] = summarise(d, f"{d}/res.csv", f"{d}/dora", f"{d}/rand")
+        # another adapter placement than the drivers' 2 + 1: every block of the miniature adapted (NEW:484-513 is general)
+        # (2 + 2 in the fp32 parity mode: the text tower's general path; 3 + 2 in the bf16 mode: at the pipeline's
+        # 224-pixel images the vision tower has T = 257 tokens, beyond the fp32 form of the full attention backward)
+        for name, nv, nt, mode in (("baseline_2p2", 2, 2, "fp32"), ("baseline_3p2", 3, 2, "bf16")):
+            if stack is not None:
+                hba.set_precision(mode)
+            g3 = f"{root}/{name}"
+            os.makedirs(g3)
+            BASE.run_behavioral_training(dict(common, vision_layers=nv, transformer_layers=nt, epochs=2, train_portion=0.8,
+                                              early_stopping_patience=100, checkpoint_path=f"{g3}/model.pth",
+                                              training_res_path=f"{g3}/res.csv", dora_parameters_path=f"{g3}/dora",
+                                              random_state_path=f"{g3}/rand"))
+            out["runs"][name] = summarise(g3, f"{g3}/res.csv", f"{g3}/dora", f"{g3}/rand")
+        if stack is not None:
+            hba.set_precision("fp32")
         if stack is not None:
             calls = ref_lib.calls
             out["c_abi_calls"] = {n: calls.count(n) for n in sorted(set(calls))}

@@ -119,7 +119,8 @@ def test_run_behavioral_training_equals_the_reference_executed(tmp_path):
     `run_behavioral_training` (BASE:707-823 and NEW:1066-1227, CPU branch) on the restated tiny CLIP against this
     repo's `run_behavioral_training` on the CPU restatement of libhba (fp32 mode, resident loaders, trunk cache,
     fused MSE, FusedAdamW), from the same image / csv / .mat / checkpoint files: a 3-epoch baseline, two conditions
-    resumed from its epoch-2 checkpoints (random targets, label shuffle) and one that perturbs epoch 1 from scratch.
+    resumed from its epoch-2 checkpoints (random targets, label shuffle), one that perturbs epoch 1 from scratch, and
+    two baselines with other adapter placements (2 + 2 in fp32 mode, 3 + 2 in bf16 mode: the general path).
     Losses within 2e-5 (fp32 re-association), RSA rho / p within 1e-6, and - exactly - epochs, perturbation flags,
     files, checkpoint keys, optimizer step counts and the torch / NumPy / DataLoader-generator states at the end
     (which also pins the RNG draws of the model construction, clip.replay_constructor_draws)."""
@@ -136,9 +137,11 @@ def test_run_behavioral_training_equals_the_reference_executed(tmp_path):
 
     def compare(want, loss_tol, rho_tol):
         assert list(got["runs"]) == list(want["runs"]) == ["baseline", "random_target", "label_shuffle",
-                                                            "uniform_images_from_scratch"]
+                                                            "uniform_images_from_scratch", "baseline_2p2", "baseline_3p2"]
         for name, w in want["runs"].items():
             g = got["runs"][name]
+            if name == "baseline_3p2":       # run in the bf16 mode (T = 257 is beyond the fp32 full attention backward)
+                loss_tol, rho_tol = max(loss_tol, 1e-2), max(rho_tol, 1e-1)
             for k in ("last_epoch", "dora_keys", "optimizer_steps", "n_optimizer_tensors", "torch_rng_sha", "generator_sha",
                       "numpy_rng_sha", "random_state_keys", "files"):
                 assert g[k] == w[k], (name, k, g[k], w[k])
@@ -149,12 +152,17 @@ def test_run_behavioral_training_equals_the_reference_executed(tmp_path):
                 for i, tol in ((1, loss_tol), (2, loss_tol), (3, rho_tol), (4, rho_tol)):
                     assert abs(float(a[i]) - float(b[i])) <= tol * max(1.0, abs(float(b[i]))), (name, a, b)
             for k, (s, m) in w["dora"].items():
-                assert abs(g["dora"][k][0] - s) <= 1e-3 * max(1.0, abs(s)) and abs(g["dora"][k][1] - m) <= 1e-3 * max(1.0, m)
+                if name == "baseline_3p2":   # (bf16 mode: the signed sum of a zero-mean matrix is no stable statistic)
+                    assert abs(g["dora"][k][1] - m) <= 2e-2 * max(1.0, m)
+                else:
+                    assert abs(g["dora"][k][0] - s) <= 1e-3 * max(1.0, abs(s)) and abs(g["dora"][k][1] - m) <= 1e-3 * max(1.0, m)
     # the committed reference-arm output may come from another CPU model: losses 1e-4, rho over 28 pairs 2e-2
     compare(gold, 1e-4, 2e-2)
     rows = list(csv.reader(gold["runs"]["uniform_images_from_scratch"]["csv"].splitlines()))
     assert [r[7] for r in rows[1:]] == ["True", "False"] and gold["runs"]["random_target"]["optimizer_steps"] == [12.0]
-    assert got["c_abi_calls"]["hba_gemm_bf16"] > 500 and got["c_abi_calls"]["hba_adamw_multi"] == 27
+    assert got["c_abi_calls"]["hba_gemm_bf16"] > 500 and got["c_abi_calls"]["hba_adamw_multi"] == 27 + 12
+    assert len(gold["runs"]["baseline_2p2"]["dora_keys"]) == 12 and len(gold["runs"]["baseline_3p2"]["dora_keys"]) == 15
+    assert got["c_abi_calls"]["hba_attention_bwd"] > 0
     if have_reference:
         compare(json.load(open(tmp_path / "reference.json")), 2e-5, 1e-6)
     # hba.rsa_scale over the baseline's DoRA checkpoints, restricted to the inference set: the rho of every checkpoint
@@ -187,3 +195,177 @@ def test_gpu_test_files_dry_run_on_the_cpu_restatement():
         counts[f] = int(tail.split(" passed")[0].split()[-1])
     assert counts["test_gpu_ops.py"] >= 90 and counts["test_gpu_pipeline.py"] >= 10, counts
     assert counts["test_gpu_model.py"] >= 6 and counts["test_gpu_vit.py"] >= 80, counts
+
+
+def _custom_state_dict(vision_layers, transformer_layers, seed=1):
+    from oracle import clip_ref
+    arch = dict(clip_ref.ARCH["ViT-tiny/14"], vision_layers=vision_layers, transformer_layers=transformer_layers)
+    torch.manual_seed(seed)
+    m = clip_ref.CLIP(**arch)
+    with torch.no_grad():
+        m.logit_scale.fill_(4.6052)
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.02)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("blocks,adapters,res,precision,tol", [
+    ((3, 2), (3, 2), 224, "bf16", 5e-2),      # every block of the miniature live; T = 257 like ViT-L/14
+    ((3, 2), (3, 2), 112, "fp32", 2e-4),      # resized positional table (T = 65): the fp32 form of the full backward
+    ((4, 3), (3, 2), 112, "fp32", 2e-4),      # a frozen block below the live ones in both towers
+    ((4, 3), (4, 3), 224, "bf16", 8e-2),
+    ((4, 3), (3, 1), 112, "fp32", 2e-4),      # vision general, text on the 2 + 1 path
+    ((4, 3), (2, 3), 112, "fp32", 2e-4),      # text general, vision on the 2 + 1 path
+])
+def test_general_adapter_placement_matches_the_oracle_model(blocks, adapters, res, precision, tol):
+    """apply_dora_to_ViT(n_vision_layers, n_transformer_layers) is general (NEW:484-513); the reference drivers use
+    2 + 1.  Any other placement runs the general path of hba.engine (every block from the first adapted one on all
+    rows, backward through MLP / out_proj / attention / in_proj / ln_1 of each) - here on the CPU restatement of libhba
+    against the oracle model with torch autograd: loss and the gradients of every adapter tensor."""
+    import hba
+    from oracle import clip_ref, dora_ref
+    from oracle.libhba_ref import emulated_device
+    from src.models.CLIPs.clip_hba import clip as pclip
+    try:
+        hba.set_precision(precision)
+        sd = _custom_state_dict(*blocks)
+        tokens = torch.stack([clip_ref.tokenize(p) for p in ("metallic; artificial", "food-related", "animal-related",
+                                                             "textile")])
+        g = torch.Generator().manual_seed(0)
+        images = torch.randn(3, 3, res, res, generator=g)
+        targets = torch.randn(3, 4, generator=g) * 9.5 + 5.75
+        oracle = dora_ref.CLIPHBARef(clip_ref.build_model(sd), tokens)
+        torch.manual_seed(123)
+        dora_ref.apply_dora_ref(oracle, *adapters, r=8)
+        dora_ref.switch_dora_ref(oracle)
+        product = dora_ref.CLIPHBARef(pclip.build_model(sd), tokens)
+        torch.manual_seed(123)
+        dora_ref.apply_dora_ref(product, *adapters, r=8, layer_cls=hba.DoRALayer)
+        dora_ref.switch_dora_ref(product, layer_cls=hba.DoRALayer)
+        crit = torch.nn.MSELoss()
+        lo = crit(oracle(images), targets)
+        lo.backward()
+        with emulated_device() as lib:
+            lp = crit(product(images), targets)
+            lp.backward()
+            with torch.no_grad():
+                again = product(images)              # the no-grad forward (evaluation) takes the same general path
+        assert abs(float(lp.detach()) - float(lo.detach())) <= tol * abs(float(lo.detach()))
+        assert abs(float(crit(again, targets)) - float(lp.detach())) <= 1e-6 * abs(float(lp.detach()))
+        named_p = [(n, p) for n, p in product.named_parameters() if p.requires_grad]
+        named_o = [(n, p) for n, p in oracle.named_parameters() if p.requires_grad]
+        assert [n for n, _ in named_p] == [n for n, _ in named_o] and len(named_p) == 3 * sum(adapters)
+        for (n, a), (_, b) in zip(named_p, named_o):
+            assert a.grad is not None and float((a.grad - b.grad).abs().max() / b.grad.abs().max()) <= tol, n
+        if max(adapters[0] - 2, adapters[1] - 1) > 0:
+            assert "hba_attention_bwd" in lib.calls       # the full attention backward of the general path
+    finally:
+        hba.set_precision("bf16")
+
+
+def test_fp32_mode_refuses_deep_vision_placement_at_257_tokens():
+    """The fp32 form of the full attention backward holds T <= 200 tokens: three adapted vision blocks at the native
+    224-pixel resolution (T = 257) are refused in the fp32 parity mode with a message, not with a kernel error."""
+    import hba
+    from oracle import clip_ref, dora_ref
+    from oracle.libhba_ref import emulated_device
+    from src.models.CLIPs.clip_hba import clip as pclip
+    try:
+        hba.set_precision("fp32")
+        tokens = torch.stack([clip_ref.tokenize(p) for p in ("a", "b")])
+        product = dora_ref.CLIPHBARef(pclip.build_model(_custom_state_dict(3, 2)), tokens)
+        torch.manual_seed(1)
+        dora_ref.apply_dora_ref(product, 3, 1, r=4, layer_cls=hba.DoRALayer)
+        dora_ref.switch_dora_ref(product, layer_cls=hba.DoRALayer)
+        with emulated_device(), pytest.raises(NotImplementedError, match="T <= 200"):
+            product(torch.zeros(1, 3, 224, 224))
+    finally:
+        hba.set_precision("bf16")
+
+
+def _abi_trace_of_default_placement():
+    """(names + every scalar argument + which pointers are null) of all C-ABI calls of: staging, three training
+    steps of the 2 + 1 placement (no cache / cache fill / cache hit) with FusedAdamW, one evaluation batch - in both
+    precision modes."""
+    import ctypes as C
+    import hba
+    from hba.engine import TrunkCache
+    from hba.optim import FusedAdamW
+    from oracle import clip_ref, dora_ref, libhba_ref
+    from src.models.CLIPs.clip_hba import clip as pclip
+    trace = []
+
+    class Tracing(libhba_ref.RefLib):
+        def __getattribute__(self, name):
+            fn = object.__getattribute__(self, name)
+            if not name.startswith("hba_") or name == "hba_last_error":
+                return fn
+
+            def wrapped(*args):
+                if name == "hba_gemm_bf16":
+                    p = args[0]._obj
+                    scal = ("M", "N", "K", "lda", "ldb", "nsplit", "a_lo_off", "b_lo_off", "ldr", "act", "ld_aux", "aux_dtype",
+                            "ld_pre", "pre_dtype", "ld_f32", "ld_bf16", "out_lo_off", "transpose_out", "max_ctas", "a_mn_major",
+                            "b_mn_major", "k_slices", "alpha")
+                    sig = tuple(getattr(p, f) if f in scal else bool(getattr(p, f)) for f, _ in p._fields_)
+                else:
+                    sig = tuple((a is not None and not (isinstance(a, C.c_void_p) and not a.value))
+                                if (a is None or isinstance(a, C.c_void_p) or (isinstance(a, int) and a >= 1 << 27)) else a
+                                for a in args)
+                rc = fn(*args)
+                trace.append((name, sig))
+                return rc
+            return wrapped
+    real = libhba_ref.RefLib
+    libhba_ref.RefLib = Tracing
+    try:
+        sd = clip_ref.synthetic_state_dict("ViT-tiny/14", seed=1)
+        tokens = torch.stack([clip_ref.tokenize(p) for p in ("metallic; artificial", "food-related", "animal-related",
+                                                             "textile")])
+        g = torch.Generator().manual_seed(0)
+        images = torch.randn(3, 3, 224, 224, generator=g)
+        targets = torch.randn(3, 4, generator=g)
+        for precision in ("bf16", "fp32"):
+            hba.set_precision(precision)
+            product = dora_ref.CLIPHBARef(pclip.build_model(sd), tokens)
+            torch.manual_seed(123)
+            dora_ref.apply_dora_ref(product, 2, 1, r=8, layer_cls=hba.DoRALayer)
+            dora_ref.switch_dora_ref(product, layer_cls=hba.DoRALayer)
+            with libhba_ref.emulated_device():
+                opt = FusedAdamW(product.parameters(), lr=3e-4)
+                eng = product.clip_model.hba_engine()
+                eng.trunk_cache = TrunkCache(16)
+                for ids in (None, [1, 2, 3], [1, 2, 3]):
+                    opt.zero_grad()
+                    eng.batch_ids = ids
+                    torch.nn.functional.mse_loss(product(images), targets).backward()
+                    opt.step()
+                with torch.no_grad():
+                    eng.batch_ids = [3, 1]
+                    product(images[:2])
+    finally:
+        libhba_ref.RefLib = real
+        hba.set_precision("bf16")
+    return trace
+
+
+def test_c_abi_call_trace_of_the_reference_placement_is_pinned():
+    """The kernel sequence of the reference drivers' placement (2 vision + 1 text adapters, BDRV:28-30) is what every
+    B200 measurement and GPU parity run of this repo exercised.  Its C-ABI call trace on the CPU restatement - entry
+    points, shapes, leading dimensions, flags, which optional pointers are given - is pinned by a digest: a change of
+    hba.engine / hba.dora / hba.optim that alters what is launched for this placement must be deliberate (regenerate:
+    HBA_WRITE_TRACE_GOLDEN=1)."""
+    import hashlib
+    trace = _abi_trace_of_default_placement()
+    digest = hashlib.sha256(repr(trace).encode()).hexdigest()
+    path = os.path.join(GOLD, "c_abi_trace_2p1.json")
+    counts = {}
+    for name, _ in trace:
+        counts[name] = counts.get(name, 0) + 1
+    if os.environ.get("HBA_WRITE_TRACE_GOLDEN") == "1":
+        with open(path, "w") as f:
+            json.dump({"calls": len(trace), "sha256": digest, "per_entry": counts}, f, indent=1, sort_keys=True)
+    gold = json.load(open(path))
+    assert len(trace) == gold["calls"] and counts == gold["per_entry"], (len(trace), counts)
+    assert digest == gold["sha256"]

@@ -13,7 +13,8 @@ fp32 re-association):
 Backward covers exactly the sub-graph that reaches trainable parameters in the reference setup
 (NEW:484-544: `out_proj` of the last <= 2 vision blocks and of the last text block): it returns
 dL/dW for those `out_proj.weight` tensors; the DoRA chain rule on top is hba.dora (fused) or plain
-autograd when the reference's own DoRALayer is used.
+autograd when the reference's own DoRALayer is used.  Deeper placements (apply_dora_to_ViT is general)
+take the general path further down: all rows of every block from the first adapted one, full backward.
 
 Precision modes (hba.set_precision):
   "bf16": bf16 operands, fp32 accumulate (tcgen05 kind::f16), fp32 residual stream / LN / softmax
@@ -51,11 +52,11 @@ def _roundup(v, m):
 class _Block:
     """Staged operands of one residual attention block."""
     __slots__ = ("ln1_w", "ln1_b", "ln2_w", "ln2_b", "w_in", "b_in", "w_out", "b_out", "w_fc",
-                 "b_fc", "w_proj", "b_proj", "w_in_t", "w_fc_t", "w_proj_t", "adapter")
+                 "b_fc", "w_proj", "b_proj", "w_in_t", "w_fc_t", "w_proj_t", "w_out_t", "adapter")
 
 
 class _Tower:
-    __slots__ = ("blocks", "d", "heads", "T", "causal")
+    __slots__ = ("blocks", "d", "heads", "T", "causal", "n_live")
 
 
 class LossRequest:
@@ -123,7 +124,16 @@ class Engine:
         ops.split_bf16(W, op, transpose=transpose)
         return op
 
-    def _stage_tower(self, resblocks, T, causal, n_live):
+    @staticmethod
+    def _live_blocks(resblocks, n_default):
+        """Blocks from the first adapted one to the end (at least the `n_default` of the reference drivers' placement,
+        BDRV:28-30: the staging - and with it every kernel launch - of that placement is unchanged)."""
+        first = next((i for i, blk in enumerate(resblocks) if not isinstance(blk.attn.out_proj, torch.nn.Linear)),
+                     len(resblocks))
+        return max(n_default, len(resblocks) - first)
+
+    def _stage_tower(self, resblocks, T, causal, n_default):
+        n_live = min(len(resblocks), self._live_blocks(resblocks, n_default))
         tw = _Tower()
         tw.blocks, tw.T, tw.causal = [], T, causal
         L = len(resblocks)
@@ -145,10 +155,14 @@ class Engine:
             b.w_fc, b.b_fc = self._operand(blk.mlp.c_fc.weight), blk.mlp.c_fc.bias.detach()
             b.w_proj, b.b_proj = self._operand(blk.mlp.c_proj.weight), blk.mlp.c_proj.bias.detach()
             live = i >= L - n_live
+            # (dX through a FROZEN out_proj is only ever needed when adapters sit below it: general placement)
+            b.w_out_t = (self._operand(op.weight, transpose=True)
+                         if live and not b.adapter and n_live > n_default else None)
             b.w_in_t = self._operand(attn.in_proj_weight, transpose=True) if live else None
             b.w_fc_t = self._operand(blk.mlp.c_fc.weight, transpose=True) if live else None
             b.w_proj_t = self._operand(blk.mlp.c_proj.weight, transpose=True) if live else None
             tw.blocks.append(b)
+        tw.n_live = n_live
         tw.d = resblocks[0].attn.embed_dim
         tw.heads = resblocks[0].attn.num_heads
         if tw.d // tw.heads != 64:
@@ -331,6 +345,7 @@ class Engine:
                                    "pos_embedding=False")
             tw = _Tower()
             tw.blocks, tw.d, tw.heads, tw.causal = self.vis.blocks, self.vis.d, self.vis.heads, False
+            tw.n_live = self.vis.n_live
             tw.T = grid * grid + 1
         npatch, d, T = grid * grid, tw.d, tw.T
         M = B * T
@@ -346,7 +361,7 @@ class Engine:
         for i in range(upto):
             blk = tw.blocks[i]
             if blk.adapter:
-                raise RuntimeError("libhba: adapters are supported on the last two vision blocks only")
+                raise RuntimeError("libhba: an adapter below the staged live blocks (restage: Engine.prepare)")
             self._block_full(tw, blk, "v", x, x, x, B, blk.w_out, blk.b_out)
         return x, tw
 
@@ -447,7 +462,7 @@ class Engine:
             for i in range(L - 1):
                 blk = tw.blocks[i]
                 if blk.adapter:
-                    raise RuntimeError("libhba: adapters are supported on the last text block only")
+                    raise RuntimeError("libhba: an adapter below the last text block on the 2 + 1 path (restage: Engine.prepare)")
                 self._block_full(tw, blk, "t", x, x, x, S, blk.w_out, blk.b_out)
             blkZ = tw.blocks[L - 1]
             h = self._opbuf("t.h", M, d)
@@ -493,6 +508,196 @@ class Engine:
         self.launches += 2
         return feat, {"S": S, "trainZ": trainZ, "keepZ": keepZ}
 
+    # ---------------------------------------------------------------- general adapter placement
+    # apply_dora_to_ViT(n_vision_layers, n_transformer_layers) is general (NEW:484-513); the reference drivers use 2 + 1
+    # (BDRV:28-30), which is what the pruned graph above serves.  More adapted blocks make more of each tower live: the
+    # methods below run every block from the first adapted one on ALL rows, keep what its backward needs, and walk the
+    # blocks back through MLP, out_proj, softmax attention (hba_attention_bwd, recomputed from the kept qkv), in_proj
+    # and ln_1.  Same kernels as the 2 + 1 path; only taken when the placement asks for it.
+    def _general_dtype(self):
+        return torch.float32 if self.split else torch.bfloat16
+
+    def _full_block_fwd(self, tw, blk, name, x_in, B, w_out, b_out, need_grad, keep_attention, a_cached=None):
+        """One live block on all rows with everything its backward needs kept under `name`.
+        -> (x_out, kept dict).  a_cached: the block's attention output from the trunk cache (first live block)."""
+        d, T, H = tw.d, tw.T, tw.heads
+        M = B * T
+        dt = self._general_dtype()
+        kept = {"x_in": x_in}
+        if a_cached is not None:
+            a_f32 = a_cached
+            a = self._opbuf(name + ".a", M, d)
+            ops.split_bf16(a_f32, a)
+            self.launches += 1
+        else:
+            h = self._opbuf(name + ".h", M, d)
+            ops.layernorm_fwd(x_in, M, d, blk.ln1_w, blk.ln1_b, LN_EPS, y=h)
+            qkv = self._keep(name + ".qkv", (M, 3 * d), dt) if (need_grad and keep_attention) \
+                else self._qkv_buffer(name, M, d)
+            self._gemm_qkv(h, blk.w_in, blk.b_in, qkv, M)
+            a = self._opbuf(name + ".a", M, d)
+            a_f32 = self._keep(name + ".a_f32", (M, d))
+            ops.attention_fwd(qkv, B, T, H, causal=tw.causal, out=a, out_f32=a_f32)
+            self.launches += 3
+            kept["qkv"] = qkv
+        kept["a_f32"], kept["a_op"] = a_f32, a
+        x_mid = self._keep(name + ".x_mid", (M, d))
+        x_out = self._keep(name + ".x_out", (M, d))
+        kept["x_mid"] = x_mid
+        kept["h_pre"] = self._keep(name + ".h_pre", (M, 4 * d), dt) if need_grad else None
+        self._live_part(tw, blk, name, a, x_in, x_mid, x_out, B, w_out, b_out,
+                        keep={"h_pre": kept["h_pre"]} if need_grad else None)
+        return x_out, kept
+
+    def _block_weights(self, blk, adapters, i, need_grad):
+        """(w [out,in], wt [in,out], bias, trainable) of block i's out_proj."""
+        if blk.adapter:
+            W, bias = adapters[i]
+            w, wt = self._adapter_operands(W)
+            return w, wt, bias.detach(), bool(need_grad and W.requires_grad)
+        return blk.w_out, blk.w_out_t, blk.b_out, False
+
+    def vision_head_general(self, x, tw, B, adapters, need_grad, cache_ctx=None):
+        """Blocks first..L-2 on all rows, block L-1 for the CLS query row, ln_post, proj - `first` = the first adapted
+        block.  Returns (img_feat, saved) like vision_head."""
+        L, T, d, H = len(tw.blocks), tw.T, tw.d, tw.heads
+        first = L - tw.n_live
+        M = B * T
+        if self.split and T > 200:
+            raise NotImplementedError("libhba fp32 mode: more than two adapted vision blocks need the full attention "
+                                      "backward, whose fp32 form holds T <= 200 tokens (use the bf16 mode)")
+        saved = {"B": B, "T": T, "tw": tw, "general": True, "first": first, "blocks": {}}
+        trains = {}
+        for i in range(first, L - 1):
+            blk = tw.blocks[i]
+            w, wt, bias, train = self._block_weights(blk, adapters, i, need_grad)
+            trains[i] = train
+            a_cached = None
+            if i == first and cache_ctx is not None and cache_ctx["hit"]:
+                a_cached = cache_ctx["a"]
+            x_out, kept = self._full_block_fwd(tw, blk, f"vg{i}", x, B, w, bias, need_grad, keep_attention=i > first,
+                                               a_cached=a_cached)
+            if i == first and cache_ctx is not None and not cache_ctx["hit"]:
+                cache_ctx["cache"].store(cache_ctx["ids"], x, kept["a_f32"])
+            kept.update(train=train, wt=wt)
+            saved["blocks"][i] = kept
+            x = x_out
+        # ---- block Z = L-1, CLS query rows only (as in vision_head)
+        blkZ = tw.blocks[L - 1]
+        wZ, wtZ, bZ, trainZ = self._block_weights(blkZ, adapters, L - 1, need_grad)
+        keepZ = None
+        if need_grad:
+            keepZ = {"x_mid": self._keep("xmidZ", (B, d)), "x_out": self._keep("xoutZ", (B, d)),
+                     "h_pre": self._keep("hpreZ", (B, 4 * d), self._general_dtype()),
+                     "a_f32": self._keep("aZ", (B, d)), "x_in": x, "wtZ": wtZ}
+        h = self._opbuf("v.h", M, d)
+        ops.layernorm_fwd(x, M, d, blkZ.ln1_w, blkZ.ln1_b, LN_EPS, y=h)
+        qkv = self._keep("qkvZ", (M, 3 * d), self._general_dtype()) if need_grad else self._qkv_buffer("v", M, d)
+        self._gemm_qkv(h, blkZ.w_in, blkZ.b_in, qkv, M)
+        a_cls = self._opbuf("v.acls", max(B, 128), d)
+        ops.attention_fwd(qkv, B, T, H, first_row_only=True, out=a_cls, out_f32=keepZ["a_f32"] if keepZ else None)
+        x_cls = x.view(B, T * d)[:, :d]
+        x_out = self._rows_tail(tw, blkZ, "v", a_cls, x_cls, B, wZ, bZ, keepZ)
+        hp = self._opbuf("v.lnpost", max(B, 128), d)
+        ops.layernorm_fwd(x_out, B, d, self.ln_post[0], self.ln_post[1], LN_EPS, y=hp)
+        feat = self._keep("imgfeat", (B, self.E))
+        ops.gemm(hp, self.proj_t, B, out_f32=feat, **self._skinny("v", B, self.E, d))
+        self.launches += 4
+        saved.update(trainZ=trainZ, keepZ=keepZ, qkvZ=qkv, trains=trains)
+        return feat, saved
+
+    def text_features_general(self, tokens, adapters, need_grad):
+        """Text tower with more than one adapted block: blocks below the first adapted one are cached per token tensor
+        (frozen), the rest runs on all S*T rows; after the last attention only the EOT rows are kept."""
+        tw = self.txt
+        S, T = tokens.shape
+        d, H, L = tw.d, tw.heads, len(tw.blocks)
+        first = L - tw.n_live
+        M = S * T
+        key = (tokens.data_ptr(), tokens._version, S, T, "general", first)
+        cache = self._text_cache if (self.cache_text and self._text_cache
+                                     and self._text_cache["key"] == key) else None
+        if cache is None:
+            x = self._buf("t.x", (M, d))
+            ops.embed_tokens(tokens, self.tok_table, self.tpos, x)
+            self.launches += 1
+            for i in range(first):
+                blk = tw.blocks[i]
+                self._block_full(tw, blk, "t", x, x, x, S, blk.w_out, blk.b_out)
+            eot = (tokens.argmax(dim=-1) + torch.arange(S, device=tokens.device) * T).contiguous()
+            cache = {"key": key, "x_first": x, "eot": eot, "tokens": tokens}
+            if self.cache_text:
+                self._text_cache = cache
+        x, eot = cache["x_first"], cache["eot"]
+        saved = {"S": S, "general": True, "first": first, "blocks": {}, "eot": eot}
+        trains = {}
+        for i in range(first, L - 1):
+            blk = tw.blocks[i]
+            w, wt, bias, train = self._block_weights(blk, adapters, i, need_grad)
+            trains[i] = train
+            x, kept = self._full_block_fwd(tw, blk, f"tg{i}", x, S, w, bias, need_grad, keep_attention=i > first)
+            kept.update(train=train, wt=wt)
+            saved["blocks"][i] = kept
+        blkZ = tw.blocks[L - 1]
+        wZ, wtZ, bZ, trainZ = self._block_weights(blkZ, adapters, L - 1, need_grad)
+        dt = self._general_dtype()
+        h = self._opbuf("t.h", M, d)
+        ops.layernorm_fwd(x, M, d, blkZ.ln1_w, blkZ.ln1_b, LN_EPS, y=h)
+        qkv = self._keep("t.qkvZ", (M, 3 * d), dt) if need_grad else self._qkv_buffer("t", M, d)
+        self._gemm_qkv(h, blkZ.w_in, blkZ.b_in, qkv, M)
+        a_all = self._buf("t.a_f32", (M, d))
+        ops.attention_fwd(qkv, S, T, H, causal=True, out_f32=a_all)
+        a_eot = self._keep("t.a_eot_g", (S, d))
+        x_eot = self._keep("t.x_eot_g", (S, d))
+        ops.gather_rows(a_all, eot, d, a_eot)
+        ops.gather_rows(x, eot, d, x_eot)
+        a_op = self._opbuf("t.a_op", max(S, 128), d, zero=True)
+        ops.split_bf16(a_eot, a_op)
+        self.launches += 6
+        keepZ = None
+        if need_grad:
+            keepZ = {"x_mid": self._keep("t.xmidZ", (S, d)), "x_out": self._keep("t.xoutZ", (S, d)),
+                     "h_pre": self._keep("t.hpreZ", (S, 4 * d), dt), "a_f32": a_eot, "x_in": x, "qkv": qkv, "wtZ": wtZ}
+        x_out = self._rows_tail(tw, blkZ, "t", a_op, x_eot, S, wZ, bZ, keepZ)
+        hp = self._opbuf("t.lnfinal", max(S, 128), d)
+        ops.layernorm_fwd(x_out, S, d, self.ln_final[0], self.ln_final[1], LN_EPS, y=hp)
+        feat = self._keep("txtfeat", (S, self.E))
+        ops.gemm(hp, self.tproj_t, S, out_f32=feat, **self._skinny("t", S, self.E, d))
+        self.launches += 2
+        saved.update(trainZ=trainZ, keepZ=keepZ, trains=trains)
+        return feat, saved
+
+    def _blocks_bwd_general(self, tw, side, saved, dx, B, grads):
+        """dx [M, d] = dL/d(output of block L-2) on entry.  Walks the live full blocks back to the first adapted one,
+        collecting dL/dW of every trainable out_proj; stops as soon as nothing trainable is left below."""
+        L, d, H = len(tw.blocks), tw.d, tw.heads
+        T = saved["T"] if side == "v" else tw.T
+        M = B * T
+        first, trains = saved["first"], saved["trains"]
+        dt = self._general_dtype()
+        for i in range(L - 2, first - 1, -1):
+            blk, kp = tw.blocks[i], saved["blocks"][i]
+            tag = f"{side}bg{i}"
+            self._mlp_rows_bwd(blk, tag, dx, M, d, kp["h_pre"], kp["x_mid"])       # dx := dL/d(out_proj output)
+            if trains[i]:
+                grads[(side, i)] = self._dw(tag, dx, kp["a_f32"], M, d, d, a_op=kp["a_op"])
+            if not any(trains[j] for j in range(first, i)):
+                break
+            g = self._grad_operand(tag + ".gy", dx, M, d)
+            d_a = self._buf(tag + ".da", (M, d), dt)       # (bf16 mode: the all-bf16 form of hba_attention_bwd)
+            if self.split:
+                ops.gemm(g, kp["wt"], M, out_f32=d_a)
+            else:
+                ops.gemm(g, kp["wt"], M, out=Operand(d_a, M, d, 0))
+            d_qkv = self._buf(tag + ".dqkv", (M, 3 * d), dt)
+            ops.attention_bwd(kp["qkv"], B, T, H, d_a, d_qkv, causal=tw.causal)
+            gq = self._grad_operand(tag + ".gq", d_qkv, M, 3 * d) if self.split else Operand(d_qkv, M, 3 * d, 0)
+            d_ln1 = self._buf(tag + ".dln1", (M, d))
+            ops.gemm(gq, blk.w_in_t, M, out_f32=d_ln1)
+            # residual: dL/dx_in = dL/d(out_proj output) + ln_1 backward of the attention branch
+            ops.layernorm_bwd(d_ln1, kp["x_in"], M, d, blk.ln1_w, LN_EPS, dx, accumulate=True)
+            self.launches += 4
+
     def _side_stream(self):
         st = self.__dict__.get("_side")
         if st is None or st.device != self.device:
@@ -532,20 +737,25 @@ class Engine:
         # fill the SMs the vision tower's kernel tails leave idle, and vice versa.  Same kernels, same
         # arguments: results are unchanged.  Fork / join are stream events, so the pair is captured into a
         # CUDA graph as two parallel branches.  HBA_TEXT_STREAM=0 keeps everything on one stream.
+        general_v, general_t = self.vis.n_live > 2, self.txt.n_live > 1
+        text_fn = self.text_features_general if general_t else self.text_features
         side = None
         if os.environ.get("HBA_TEXT_STREAM", "1") != "0":
             main = torch.cuda.current_stream(self.device)
             side = self._side_stream()
             side.wait_stream(main)    # fork: the adapters' merged weights were produced on the main stream
             with torch.cuda.stream(side):
-                txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
+                txt_feat, st = text_fn(tokens, t_adapters, need_grad)
         if cache_ctx is not None and cache_ctx["hit"]:
             x, tw = cache_ctx["x"], self.vis
         else:
-            x, tw = self.vision_trunk(images, max(L - 2, 0))
-        img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad, cache_ctx)
+            x, tw = self.vision_trunk(images, max(L - max(self.vis.n_live, 2), 0))
+        if general_v:
+            img_feat, sv = self.vision_head_general(x, tw, B, v_adapters, need_grad, cache_ctx)
+        else:
+            img_feat, sv = self.vision_head(x, tw, B, v_adapters, need_grad, cache_ctx)
         if side is None:
-            txt_feat, st = self.text_features(tokens, t_adapters, need_grad)
+            txt_feat, st = text_fn(tokens, t_adapters, need_grad)
         else:
             main.wait_stream(side)   # join: the cosine head needs both towers
         pred = torch.empty(B, txt_feat.shape[0], device=self.device)
@@ -623,7 +833,9 @@ class Engine:
         self.launches += 1
         # ------------------------------------------------ text: last block, EOT rows
         st = saved["t"]
-        if st["trainZ"]:
+        if st.get("general"):
+            self._text_backward_general(st, d_txt, grads)
+        elif st["trainZ"]:
             tw = self.txt
             d, L = tw.d, len(tw.blocks)
             blk, kz = tw.blocks[L - 1], st["keepZ"]
@@ -640,7 +852,9 @@ class Engine:
         tw = sv["tw"]
         L, d, T, H = len(tw.blocks), tw.d, sv["T"], tw.heads
         M = B * T
-        if sv["trainZ"] or sv.get("trainP"):
+        if sv.get("general"):
+            self._vision_backward_general(sv, d_img, B, grads)
+        elif sv["trainZ"] or sv.get("trainP"):
             blkZ, kz = tw.blocks[L - 1], sv["keepZ"]
             g = self._grad_operand("vb.g0", d_img, B, E)
             d_lnp = self._buf("vb.dlnp", (B, d))
@@ -670,9 +884,88 @@ class Engine:
                 grads[("v", L - 2)] = self._dw("vbP", dx, kp["a_f32"], M, d, d, a_op=kp.get("a_op"))
         return grads
 
+    def _text_backward_general(self, st, d_txt, grads):
+        tw = self.txt
+        S, d, L, T, H = st["S"], tw.d, len(tw.blocks), tw.T, tw.heads
+        M = S * T
+        E = self.E
+        trains, first = st["trains"], st["first"]
+        below = any(trains[j] for j in range(first, L - 1))
+        if not (st["trainZ"] or below):
+            return
+        blk, kz = tw.blocks[L - 1], st["keepZ"]
+        g = self._grad_operand("tb.g0", d_txt, S, E)
+        d_lnf = self._buf("tb.dlnf", (S, d))
+        ops.gemm(g, self.tproj_n, S, out_f32=d_lnf, **self._skinny("tb", S, d, E))
+        dxo = self._buf("tb.dxo", (S, d))
+        ops.layernorm_bwd(d_lnf, kz["x_out"], S, d, self.ln_final[0], LN_EPS, dxo)
+        self.launches += 2
+        self._mlp_rows_bwd(blk, "tb", dxo, S, d, kz["h_pre"], kz["x_mid"])          # dxo := dL/d(out_proj output), EOT rows
+        if st["trainZ"]:
+            grads[("t", L - 1)] = self._dw("tb", dxo, kz["a_f32"], S, d, d)
+        if not below:
+            return
+        # below the last block: its attention saw every row of the block input
+        wtZ = kz["wtZ"] if kz["wtZ"] is not None else self._frozen_wt(blk)
+        g2 = self._grad_operand("tb.g2", dxo, S, d)
+        d_a_eot = self._buf("tb.da_eot", (S, d))
+        ops.gemm(g2, wtZ, S, out_f32=d_a_eot, **self._skinny("tb", S, d, d))
+        dt = self._general_dtype()
+        d_a = self._buf("tb.da", (M, d), dt)
+        d_a.zero_()
+        d_a.index_copy_(0, st["eot"], d_a_eot.to(dt))
+        d_qkv = self._buf("tb.dqkv", (M, 3 * d), dt)
+        ops.attention_bwd(kz["qkv"], S, T, H, d_a, d_qkv, causal=True)
+        gq = self._grad_operand("tb.gq", d_qkv, M, 3 * d) if self.split else Operand(d_qkv, M, 3 * d, 0)
+        d_ln1 = self._buf("tb.dln1", (M, d))
+        ops.gemm(gq, blk.w_in_t, M, out_f32=d_ln1)
+        dx = self._buf("tb.dx", (M, d))
+        ops.layernorm_bwd(d_ln1, kz["x_in"], M, d, blk.ln1_w, LN_EPS, dx)
+        dx.index_add_(0, st["eot"], dxo)                                             # residual path of the EOT rows
+        self.launches += 4
+        self._blocks_bwd_general(tw, "t", st, dx, S, grads)
+
+    def _vision_backward_general(self, sv, d_img, B, grads):
+        tw = sv["tw"]
+        L, d, T, H = len(tw.blocks), tw.d, sv["T"], tw.heads
+        M = B * T
+        E = self.E
+        trains, first = sv["trains"], sv["first"]
+        below = any(trains[j] for j in range(first, L - 1))
+        if not (sv["trainZ"] or below):
+            return
+        blkZ, kz = tw.blocks[L - 1], sv["keepZ"]
+        g = self._grad_operand("vb.g0", d_img, B, E)
+        d_lnp = self._buf("vb.dlnp", (B, d))
+        ops.gemm(g, self.proj_n, B, out_f32=d_lnp, **self._skinny("vb", B, d, E))
+        dxo = self._buf("vb.dxo", (B, d))
+        ops.layernorm_bwd(d_lnp, kz["x_out"], B, d, self.ln_post[0], LN_EPS, dxo)
+        self.launches += 2
+        self._mlp_rows_bwd(blkZ, "vb", dxo, B, d, kz["h_pre"], kz["x_mid"])         # dxo := dL/d(out_proj output), CLS rows
+        if sv["trainZ"]:
+            grads[("v", L - 1)] = self._dw("vb", dxo, kz["a_f32"], B, d, d)
+        if not below:
+            return
+        wtZ = kz["wtZ"] if kz["wtZ"] is not None else self._frozen_wt(blkZ)
+        g2 = self._grad_operand("vb.g2", dxo, B, d)
+        d_a = self._buf("vb.da", (B, d))
+        ops.gemm(g2, wtZ, B, out_f32=d_a, **self._skinny("vb", B, d, d))
+        d_qkv = self._buf("vb.dqkv", (M, 3 * d))
+        ops.attention_bwd_row0(sv["qkvZ"], B, T, H, d_a, d_qkv)
+        gq = self._grad_operand("vb.gq", d_qkv, M, 3 * d)
+        d_ln1 = self._buf("vb.dln1", (M, d))
+        ops.gemm(gq, blkZ.w_in_t, M, out_f32=d_ln1)
+        dx = self._buf("vb.dx", (M, d))
+        ops.layernorm_bwd(d_ln1, kz["x_in"], M, d, blkZ.ln1_w, LN_EPS, dx)
+        ops.add_rows(dx, dxo, B, d, dst_row_step=T)                                   # residual path of the CLS rows
+        self.launches += 5
+        self._blocks_bwd_general(tw, "v", sv, dx, B, grads)
+
     def _frozen_wt(self, blk):
+        if getattr(blk, "w_out_t", None) is not None:
+            return blk.w_out_t
         raise RuntimeError("libhba: backward through a frozen out_proj of the last block is not "
-                           "staged (adapter expected on the last vision block)")
+                           "staged (adapter expected on the last block)")
 
 
 class TrunkCache:
