@@ -23,11 +23,13 @@ def _custom_state_dict(vision_layers, transformer_layers, seed=1):
     return {k: v.detach().clone() for k, v in m.state_dict().items()}
 
 
+# (native 224-pixel images only: T = 257 / 77 are the shapes every kernel involved has been run at on the B200; the
+# fp32 form of the vision tower's general path needs T <= 200 and is covered on the CPU restatement)
 @pytest.mark.parametrize("blocks,adapters,res,precision,tol_loss,tol_grad", [
     ((3, 2), (3, 2), 224, "bf16", 3e-2, 1.5e-1),    # every block live, T = 257 like ViT-L/14 (all-bf16 attention backward)
-    ((3, 2), (3, 2), 112, "fp32", 1e-3, 2e-3),      # T = 65: the fp32 form of the full attention backward
-    ((4, 3), (3, 2), 112, "fp32", 1e-3, 2e-3),      # a frozen block below the live ones in both towers
-    ((4, 3), (2, 3), 224, "bf16", 3e-2, 1.5e-1),    # text tower general, vision on the 2 + 1 path
+    ((4, 3), (3, 2), 224, "bf16", 3e-2, 1.5e-1),    # a frozen block below the live ones in both towers
+    ((4, 3), (2, 3), 224, "fp32", 1e-3, 2e-3),      # text tower general in the parity mode (causal fp32 attention backward)
+    ((3, 2), (2, 2), 224, "bf16", 3e-2, 1.5e-1),    # text tower general, vision on the 2 + 1 path
 ])
 def test_general_adapter_placement_matches_the_oracle_model_on_the_device(blocks, adapters, res, precision, tol_loss,
                                                                           tol_grad):
