@@ -264,6 +264,47 @@ def test_general_adapter_placement_matches_the_oracle_model(blocks, adapters, re
         hba.set_precision("bf16")
 
 
+@pytest.mark.parametrize("vis_idx,txt_idx", [([0], [0]), ([0, 2], []), ([1], [0, 1]), ([], [0]), ([1], [])])
+def test_adapters_placed_by_hand_match_the_oracle_model(vis_idx, txt_idx):
+    """Placements apply_dora_to_ViT cannot produce (module surgery by hand: a frozen block ABOVE an adapted one, gaps,
+    one tower only): the live range starts at the lowest adapter and the backward passes through frozen out_proj
+    weights on its way down."""
+    import hba
+    from oracle import clip_ref, dora_ref
+    from oracle.libhba_ref import emulated_device
+    from src.models.CLIPs.clip_hba import clip as pclip
+    try:
+        hba.set_precision("fp32")
+        sd = clip_ref.synthetic_state_dict("ViT-tiny/14", seed=1)
+        tokens = torch.stack([clip_ref.tokenize(p) for p in ("metallic; artificial", "food-related", "animal-related")])
+        g = torch.Generator().manual_seed(0)
+        images = torch.randn(2, 3, 112, 112, generator=g)
+        targets = torch.randn(2, 3, generator=g) * 9.5 + 5.75
+        models = []
+        for cls, builder in ((dora_ref.DoRALayerRef, clip_ref.build_model), (hba.DoRALayer, pclip.build_model)):
+            m = dora_ref.CLIPHBARef(builder(sd), tokens)
+            torch.manual_seed(5)
+            for tower, idx in ((m.clip_model.visual.transformer, vis_idx), (m.clip_model.transformer, txt_idx)):
+                for i in idx:
+                    tower.resblocks[i].attn.out_proj = cls(tower.resblocks[i].attn.out_proj, r=4)
+            dora_ref.switch_dora_ref(m, layer_cls=cls)
+            models.append(m)
+        oracle, product = models
+        lo = torch.nn.functional.mse_loss(oracle(images), targets)
+        lo.backward()
+        with emulated_device():
+            lp = torch.nn.functional.mse_loss(product(images), targets)
+            lp.backward()
+        assert abs(float(lp.detach()) - float(lo.detach())) <= 2e-5 * abs(float(lo.detach()))
+        pg = [p.grad for p in product.parameters() if p.requires_grad]
+        og = [p.grad for p in oracle.parameters() if p.requires_grad]
+        assert len(pg) == len(og) == 3 * (len(vis_idx) + len(txt_idx))
+        for a, b in zip(pg, og):
+            assert float((a - b).abs().max() / b.abs().max()) <= 2e-4
+    finally:
+        hba.set_precision("bf16")
+
+
 def test_fp32_mode_refuses_deep_vision_placement_at_257_tokens():
     """The fp32 form of the full attention backward holds T <= 200 tokens: three adapted vision blocks at the native
     224-pixel resolution (T = 257) are refused in the fp32 parity mode with a message, not with a kernel error."""

@@ -134,6 +134,8 @@ class Engine:
 
     def _stage_tower(self, resblocks, T, causal, n_default):
         n_live = min(len(resblocks), self._live_blocks(resblocks, n_default))
+        first_adapter = next((i for i, blk in enumerate(resblocks) if not isinstance(blk.attn.out_proj, torch.nn.Linear)),
+                             len(resblocks))
         tw = _Tower()
         tw.blocks, tw.T, tw.causal = [], T, causal
         L = len(resblocks)
@@ -155,9 +157,10 @@ class Engine:
             b.w_fc, b.b_fc = self._operand(blk.mlp.c_fc.weight), blk.mlp.c_fc.bias.detach()
             b.w_proj, b.b_proj = self._operand(blk.mlp.c_proj.weight), blk.mlp.c_proj.bias.detach()
             live = i >= L - n_live
-            # (dX through a FROZEN out_proj is only ever needed when adapters sit below it: general placement)
+            # (dX through a FROZEN out_proj is only ever needed when an adapter sits below it - never in the
+            # placements apply_dora_to_ViT produces for the drivers' 2 + 1)
             b.w_out_t = (self._operand(op.weight, transpose=True)
-                         if live and not b.adapter and n_live > n_default else None)
+                         if live and not b.adapter and i > first_adapter else None)
             b.w_in_t = self._operand(attn.in_proj_weight, transpose=True) if live else None
             b.w_fc_t = self._operand(blk.mlp.c_fc.weight, transpose=True) if live else None
             b.w_proj_t = self._operand(blk.mlp.c_proj.weight, transpose=True) if live else None
