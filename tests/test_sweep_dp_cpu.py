@@ -737,3 +737,61 @@ def test_bench_scheduler_slice_timeout_kills_the_tool_and_its_workers(tmp_path, 
         except FileNotFoundError:
             state = "gone"
         assert state in ("gone", "Z"), f"pid {pid} survived the timeout in state {state}"
+
+
+# ------------------------------------------------------------------------------- ViT data parallel, the real trainer
+def _vit_dp_worker(rank, world, port, out_dir):
+    """hba.vit.DataParallelTrainer itself (engine forward / backward, bucket all-reduces announced by the backward
+    pass, fused SGD) on a `gloo` group, libhba served by its CPU restatement."""
+    import torch.distributed as dist
+    import hba
+    from hba import vit
+    from oracle.libhba_ref import emulated_device
+    torch.set_num_threads(2)
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    hba.set_precision("fp32")
+    torch.manual_seed(100 + rank)                      # ranks start from DIFFERENT weights: the broadcast must fix that
+    model = vit.create_model("vit_tiny_test", num_classes=10)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randn(8, 3, 224, 224, generator=g)
+    labels = torch.randint(0, 10, (8,), generator=g)
+    share = slice(rank * 8 // world, (rank + 1) * 8 // world)
+    with emulated_device():
+        tr = vit.DataParallelTrainer(model, lr=0.05, momentum=0.9, weight_decay=1e-4, use_graph=False)
+        if world > 1:
+            tr.broadcast_parameters()
+        else:
+            torch.manual_seed(100)                    # (the single-rank arm: rank 0's initial weights)
+            ref0 = vit.create_model("vit_tiny_test", num_classes=10)
+            model.load_state_dict(ref0.state_dict())
+        losses = []
+        for _ in range(3):
+            loss, hits = tr.step(images[share], labels[share])
+            losses.append(float(loss))
+        launched = list(tr.reducer.launched)
+    torch.save({"params": {k: v.detach().clone() for k, v in model.state_dict().items()}, "losses": losses,
+                "world": tr.world}, os.path.join(out_dir, f"vit_w{world}_r{rank}.pt"))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_vit_data_parallel_trainer_world_2_equals_one_rank_on_the_full_batch(tmp_path):
+    """SURVEY 8e, ViT-B/16 row (VIT:287 DistributedDataParallel): two ranks with half the batch each end three SGD steps
+    with the parameters one rank reaches on the whole batch (mean over the GLOBAL batch: 1/world folded into
+    dL/dlogits, SUM all-reduce per block bucket), after a broadcast made their different initial weights equal."""
+    import torch.multiprocessing as mp
+    port = 29350 + os.getpid() % 200
+    mp.spawn(_vit_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    _vit_dp_worker(0, 1, 0, str(tmp_path))
+    r0, r1, one = (torch.load(os.path.join(str(tmp_path), f)) for f in ("vit_w2_r0.pt", "vit_w2_r1.pt", "vit_w1_r0.pt"))
+    assert r0["world"] == 2 and one["world"] == 1
+    worst = 0.0
+    for k, v in one["params"].items():
+        assert torch.equal(r0["params"][k], r1["params"][k]), k            # the ranks stay bit-identical to each other
+        scale = float(v.abs().max().clamp_min(1e-6))
+        worst = max(worst, float((r0["params"][k] - v).abs().max()) / scale)
+    assert worst < 2e-4, worst                                             # = one rank on the full batch (fp32 re-association)
+    # the global loss is the mean of the two half-batch losses
+    for a, b, c in zip(r0["losses"], r1["losses"], one["losses"]):
+        assert abs(0.5 * (a + b) - c) < 2e-4 * max(1.0, abs(c))
