@@ -2,7 +2,8 @@
 libhba served by its CPU restatement (oracle/libhba_ref.py) - the test functions themselves, through pytest, with
 `DEV` pointed at the CPU and CUDA-graph capture off.  NOT a test and NOT a product path: it catches host-side mistakes
 (names, shapes, state handling, file formats, cross-condition state) in code that otherwise only executes on a B200.
-Tests that need the device itself (captured graphs, CUDA generators, device-side timing) fail or are meaningless here.
+Tests that need the device itself (CUDA generators, device-side timing) fail or are meaningless here; captured
+graphs are replaced by call-by-call launches.
 
     python tests/emulate_clip_gpu_tests.py tests/test_gpu_pipeline.py [-k expr]
 
@@ -35,6 +36,13 @@ class _Plugin:
         self.ctx.__enter__()
         cpu = lambda flag: torch.device("cpu")
         core.select_device = BASE.select_device = NEW.select_device = cpu
+        # no CUDA-graph capture without a device: every step is launched call by call, whatever a test asks for
+        # (a "captured = eager" comparison then compares eager with eager; the tests AROUND the graphs - the fused
+        # MSE step against the criterion-called step, NaN batches, evaluation - keep their meaning)
+        from hba import vit
+        core.TrainStep._graphs_on = lambda self: False
+        core._CachedForwardGraphs.usable = lambda self, loader: False
+        vit.DataParallelTrainer.step = lambda self, images, labels: self._step_eager(images, labels)
 
     def pytest_sessionfinish(self, session, exitstatus):
         if self.ctx is not None:
@@ -48,8 +56,11 @@ class _Plugin:
                 item.module.DEV = torch.device("cpu")
 
 
-# what cannot run without the device itself: captured CUDA graphs, and the C-ABI's own argument validation
-NEEDS_DEVICE = "not cuda_graph and not captured_step_graphs and not fused_mse_step_equals and not gemm_errors"
+# what cannot run without the device itself: the C-ABI's own argument validation (captured CUDA graphs are replaced
+# by call-by-call launches, see the plugin)
+# ... and one comparison whose 1e-6 tolerance is about the summation order of two CUDA kernels (fused MSE head vs
+# head + torch MSE), which the restatement does not reproduce
+NEEDS_DEVICE = "not gemm_errors and not fused_mse_step_equals"
 DRY_RUN_FILES = ("test_gpu_ops.py", "test_gpu_model.py", "test_gpu_pipeline.py", "test_gpu_vit.py")
 
 
