@@ -13,8 +13,9 @@ the CUDA kernels - those are compared with their formulas on a B200 by the `-m g
 
 Every entry point of the header is restated (CLIP path and ViT-B/16 path).  The restatement is pinned by the GPU op
 tests themselves: tests/emulate_clip_gpu_tests.py runs tests/test_gpu_ops.py on it, i.e. each restated entry point is
-compared with the same torch / fp64-autograd / numpy / scipy formulas that judge the CUDA kernels.  Not restated: the
-library's argument validation (HBA_ERR_ARG paths) and anything about scheduling (split-K, max_ctas, workspaces).
+compared with the same torch / fp64-autograd / numpy / scipy formulas that judge the CUDA kernels.  The argument
+checks of the front ends (HBA_REQUIRE) are restated as well; not restated: anything about scheduling (split-K order,
+max_ctas, workspace use).
 
 Arithmetic notes: GEMMs accumulate hi.hi + lo.hi + hi.lo in fp32 like the kernel (nsplit = 3) or the plain bf16 product
 (nsplit = 1); attention keeps P in fp32 (the tensor-core kernel rounds P to bf16); everything else is the header's
@@ -98,12 +99,45 @@ def _act(v, act, aux):
     raise ValueError(act)
 
 
+class _ArgError(Exception):
+    pass
+
+
+def _require(cond, msg):
+    if not cond:
+        raise _ArgError(msg)
+
+
+def _al(p, n=16):
+    return _addr(p) % n == 0
+
+
+HBA_ERR_ARG = -22
+
+
 class RefLib:
-    """Method-for-method stand-in of libhba.so on host memory (see the module docstring)."""
+    """Method-for-method stand-in of libhba.so on host memory (see the module docstring).  The argument checks of the
+    library's front ends (HBA_REQUIRE: null pointers, shape limits, leading-dimension and 16-byte pointer alignment
+    rules of the vectorised / TMA accesses) are restated too and answer like the library: HBA_ERR_ARG and a message
+    in hba_last_error() - so a host-side call that the device would refuse is refused here as well."""
 
     def __init__(self):
         self.calls = []            # entry-point names in call order (tests assert on the sequencing)
         self._err = b""
+
+    def __getattribute__(self, name):
+        fn = object.__getattribute__(self, name)
+        if not name.startswith("hba_") or name in ("hba_last_error", "hba_abi_version", "hba_device_check",
+                                                   "hba_rank_workspace_bytes"):
+            return fn
+
+        def guarded(*args):
+            try:
+                return fn(*args)
+            except _ArgError as exc:
+                object.__setattr__(self, "_err", f"{name}: {exc}".encode())
+                return HBA_ERR_ARG
+        return guarded
 
     # ---------------------------------------------------------------- plumbing
     def hba_last_error(self):
@@ -123,6 +157,37 @@ class RefLib:
     def hba_gemm_bf16(self, pref, stream):
         p = pref._obj if hasattr(pref, "_obj") else pref
         M, N, K = p.M, p.N, p.K
+        _require(p.A and p.B, "null operand")
+        _require(M > 0 and N > 0 and K > 0, f"empty problem M={M} N={N} K={K}")
+        _require(p.lda % 8 == 0 and p.ldb % 8 == 0, "lda/ldb must be multiples of 8")
+        _require(_al(p.A) and _al(p.B), "TMA operand must be 16-byte aligned")
+        _require(p.nsplit in (1, 3), "nsplit must be 1 or 3")
+        kpad = (K + 63) // 64 * 64
+        if p.nsplit == 3:
+            _require(p.a_lo_off >= (M if p.a_mn_major else kpad) and p.b_lo_off >= (N if p.b_mn_major else kpad)
+                     and p.a_lo_off % 8 == 0 and p.b_lo_off % 8 == 0,
+                     "lo offsets must lie behind the hi part and be multiples of 8")
+        _require(p.out_f32 or p.out_bf16 or p.pre_out, "no output")
+        _require(0 <= p.act <= 4, "bad act")
+        if p.act in (3, 4):
+            _require(p.aux, "activation gradient needs aux")
+        if p.transpose_out:
+            _require(p.act == 0 and not p.residual and not p.pre_out, "transpose_out supports alpha and bias only")
+        else:
+            _require(not p.out_f32 or (p.ld_f32 % 4 == 0 and _al(p.out_f32)), "out_f32 must be 16-byte aligned with ld % 4 == 0")
+            _require(not p.out_bf16 or (p.ld_bf16 % 8 == 0 and p.out_lo_off % 8 == 0 and _al(p.out_bf16)),
+                     "out_bf16 must be 16-byte aligned with ld % 8 == 0")
+        _require(not p.residual or (p.ldr % 4 == 0 and _al(p.residual)), "residual must be 16-byte aligned with ld % 4 == 0")
+        _require(not p.bias or _al(p.bias), "bias must be 16-byte aligned")
+        if p.pre_out:
+            _require(_al(p.pre_out) and p.ld_pre % 8 == 0, "pre_out must be 16-byte aligned with ld % 8 == 0")
+        if p.colsum_partial:
+            _require(p.out_bf16 and not p.transpose_out and N % 4 == 0 and _al(p.colsum_partial),
+                     "colsum_partial needs a bf16 output, N % 4 == 0 and a 16-byte aligned buffer")
+        if min(p.k_slices, (K + 63) // 64) > 1:
+            _require(p.k_workspace and not p.transpose_out and not p.colsum_partial and N % 4 == 0,
+                     f"split-K (k_slices={p.k_slices}) needs k_workspace, N % 4 == 0 and no transposed / column-sum output")
+            _require(_al(p.k_workspace), "k_workspace must be 16-byte aligned")
         split = p.nsplit == 3
 
         def operand(ptr, ld, lo_off, rows, mn):
@@ -164,6 +229,10 @@ class RefLib:
         return self._ok("hba_gemm_bf16")
 
     def hba_split_bf16(self, x, rows, cols, ld_in, out, ld_out, lo_off, transpose, stream):
+        _require(_addr(x) and _addr(out) and rows > 0 and cols > 0, "bad arguments")
+        if not transpose:
+            _require(cols % 4 == 0 and ld_in % 4 == 0 and ld_out % 2 == 0 and lo_off % 2 == 0 and _al(x) and _al(out, 4),
+                     "cols/ld must be multiples of 4 and pointers aligned")
         v = mat(x, rows, cols, ld_in, torch.float32)
         write_operand(out, v.t().contiguous() if transpose else v, ld_out, lo_off)
         return self._ok("hba_split_bf16")
@@ -175,6 +244,11 @@ class RefLib:
 
     def hba_layernorm_fwd(self, x, rows, cols, ldx, row_step, gamma, beta, eps, y_f32, ld_yf, y_bf16, ld_yb, lo_off,
                           stream):
+        _require(_addr(x) and _addr(gamma) and _addr(beta) and (_addr(y_f32) or _addr(y_bf16)) and rows > 0, "bad arguments")
+        _require(cols % 128 == 0 and cols <= 1024, f"cols={cols} must be a multiple of 128 and <= 1024")
+        _require(ldx % 4 == 0 and ld_yf % 4 == 0 and ld_yb % 4 == 0 and lo_off % 4 == 0 and _al(y_bf16, 8),
+                 "leading dimensions must keep 16-byte (fp32) / 8-byte (bf16) row alignment")
+        row_step = max(1, row_step)
         xv = self._rows(x, rows, cols, ldx, row_step)
         mu = xv.mean(1, keepdim=True)
         var = ((xv - mu) ** 2).mean(1, keepdim=True)
@@ -186,6 +260,10 @@ class RefLib:
         return self._ok("hba_layernorm_fwd")
 
     def hba_layernorm_bwd(self, dy, ld_dy, x, rows, cols, ldx, row_step, gamma, eps, dx, ld_dx, accumulate, stream):
+        _require(_addr(dy) and _addr(x) and _addr(gamma) and _addr(dx) and rows > 0, "bad arguments")
+        _require(cols % 128 == 0 and cols <= 1024, f"cols={cols} must be a multiple of 128 and <= 1024")
+        _require(ldx % 4 == 0 and ld_dy % 4 == 0 and ld_dx % 4 == 0, "leading dimensions must be multiples of 4")
+        row_step = max(1, row_step)
         xv = self._rows(x, rows, cols, ldx, row_step)
         g = mat(dy, rows, cols, ld_dy, torch.float32) * flat(gamma, cols, torch.float32)
         mu = xv.mean(1, keepdim=True)
@@ -198,6 +276,8 @@ class RefLib:
 
     # ---------------------------------------------------------------- front ends of the towers
     def hba_im2col_patches(self, image, B, H, W, P, out, ld_out, lo_off, stream):
+        _require(_addr(image) and _addr(out) and B > 0 and P > 0 and H % P == 0 and W % P == 0, "bad arguments")
+        _require((ld_out if lo_off == 0 else lo_off) >= 3 * P * P, "row too short for 3*P*P columns")
         img = flat(image, B * 3 * H * W, torch.float32).view(B, 3, H, W)
         gh, gw = H // P, W // P
         cols = img.view(B, 3, gh, P, gw, P).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, 3 * P * P)
@@ -205,6 +285,9 @@ class RefLib:
         return self._ok("hba_im2col_patches")
 
     def hba_assemble_tokens_ln(self, conv, B, n_patches, width, cls, pos, gamma, beta, eps, x_out, stream):
+        _require(_addr(conv) and _addr(cls) and _addr(pos) and _addr(x_out) and B > 0 and (not _addr(gamma)) == (not _addr(beta)),
+                 "bad arguments")
+        _require(width % 128 == 0 and width <= 1024, f"width={width} unsupported")
         c = flat(conv, B * n_patches * width, torch.float32).view(B, n_patches, width)
         ps = flat(pos, (n_patches + 1) * width, torch.float32).view(n_patches + 1, width)
         x = torch.cat([flat(cls, width, torch.float32).expand(B, 1, width), c], 1) + ps
@@ -215,6 +298,8 @@ class RefLib:
         return self._ok("hba_assemble_tokens_ln")
 
     def hba_embed_tokens(self, tokens, S, T, width, table, pos, x_out, stream):
+        _require(_addr(tokens) and _addr(table) and _addr(pos) and _addr(x_out) and S > 0 and T > 0 and width % 4 == 0,
+                 "bad arguments")
         tok = flat(tokens, S * T, torch.int64).view(S, T)
         n_vocab = int(tok.max()) + 1
         tab = flat(table, n_vocab * width, torch.float32).view(n_vocab, width)
@@ -223,6 +308,7 @@ class RefLib:
         return self._ok("hba_embed_tokens")
 
     def hba_gather_rows(self, src, ld_in, idx, n, cols, out, ld_out, stream):
+        _require(_addr(src) and _addr(idx) and _addr(out) and n > 0 and cols > 0, "bad arguments")
         ix = flat(idx, n, torch.int64)
         rows = int(ix.max()) + 1
         mat(out, n, cols, ld_out, torch.float32).copy_(mat(src, rows, cols, ld_in, torch.float32)[ix])
@@ -237,6 +323,12 @@ class RefLib:
 
     def hba_attention_fwd(self, qkv, dtype, ld_qkv, B, T, H, causal, first_row_only, out, ld_out, lo_off, out_f32,
                           ld_of, stream):
+        _require(_addr(qkv) and (_addr(out) or _addr(out_f32)) and B > 0 and T > 0 and H > 0, "bad arguments")
+        _require(T <= 288, f"T={T} exceeds 288")
+        _require(not (first_row_only and causal), "first_row_only with causal is unsupported")
+        if first_row_only:
+            _require(ld_qkv % 8 == 0 and _al(qkv), "first_row_only needs 16-byte aligned qkv rows (ld % 8 == 0)")
+        _require(dtype in DT, f"unknown dtype {dtype}")
         q, k, v = self._qkv(qkv, dtype, ld_qkv, B, T, H)
         if first_row_only:
             q = q[:, :, :1]
@@ -252,6 +344,9 @@ class RefLib:
         return self._ok("hba_attention_fwd")
 
     def hba_attention_bwd_row0(self, qkv, dtype, ld_qkv, B, T, H, d_out, ld_do, d_qkv, ld_dqkv, stream):
+        _require(_addr(qkv) and _addr(d_out) and _addr(d_qkv) and B > 0 and T > 0 and H > 0, "bad arguments")
+        _require(T <= 288, f"T={T} exceeds 288")
+        _require(ld_qkv % 8 == 0 and _al(qkv) and ld_dqkv % 4 == 0 and _al(d_qkv), "qkv / d_qkv rows must be 16-byte aligned")
         q, k, v = self._qkv(qkv, dtype, ld_qkv, B, T, H)
         q0 = q[:, :, :1]                                                     # [B, H, 1, 64]
         p = torch.softmax(q0 @ k.transpose(-1, -2) / 8.0, -1)               # [B, H, 1, T]
@@ -270,6 +365,10 @@ class RefLib:
     # ---------------------------------------------------------------- DoRA (NEW:447-463 and its autograd)
     def hba_dora_merge_fwd(self, D, A, Bm, m, in_f, out_f, r, scale, eps, w_t_f32, w_bf16, ld_w, w_lo_off, wt_bf16,
                            ld_wt, wt_lo_off, norm_out, stream):
+        _require(_addr(D) and _addr(A) and _addr(Bm) and _addr(m), "null input")
+        _require(_addr(w_t_f32) or _addr(w_bf16) or _addr(wt_bf16), "no output requested")
+        self._dora_check(in_f, out_f, r)
+        _require(not _addr(wt_bf16) or (ld_wt % 8 == 0 and wt_lo_off % 8 == 0 and _al(wt_bf16)), "wt_bf16 alignment")
         Dv = flat(D, in_f * out_f, torch.float32).view(in_f, out_f)
         V = Dv + scale * (flat(Bm, in_f * r, torch.float32).view(in_f, r) @ flat(A, r * out_f, torch.float32).view(r, out_f))
         n = torch.norm(V, dim=0) + eps
@@ -284,7 +383,16 @@ class RefLib:
             flat(norm_out, out_f, torch.float32).copy_(n)
         return self._ok("hba_dora_merge_fwd")
 
+    @staticmethod
+    def _dora_check(in_f, out_f, r):
+        _require(0 < in_f <= 2048, f"in_features={in_f} unsupported (max 2048)")
+        _require(out_f > 0 and out_f % 8 == 0, f"out_features={out_f} must be a multiple of 8")
+        _require(0 < r <= 64 and r % 4 == 0, f"rank={r} must be a multiple of 4 and <= 64")
+
     def hba_dora_merge_bwd(self, G, ld_g, D, A, Bm, m, in_f, out_f, r, scale, eps, dm, dA, dB, workspace, stream):
+        _require(all(_addr(t) for t in (G, D, A, Bm, m, dm, dA, dB, workspace)), "null pointer")
+        self._dora_check(in_f, out_f, r)
+        _require(out_f <= 1792, f"out_features={out_f} exceeds the shared-memory staging (max 1792)")
         Gt = mat(G, out_f, in_f, ld_g, torch.float32).t()                   # dL/dWt [in, out]
         Dv = flat(D, in_f * out_f, torch.float32).view(in_f, out_f)
         Av = flat(A, r * out_f, torch.float32).view(r, out_f)
@@ -308,6 +416,9 @@ class RefLib:
         return s * (img / ni) @ (txt / nt).t(), ni, nt, s
 
     def hba_cos_head_fwd(self, img, txt, B, Cn, E, logit_scale, pred, target, loss, stream):
+        _require(_addr(img) and _addr(txt) and _addr(logit_scale) and _addr(pred) and B > 0 and Cn > 0, "bad arguments")
+        _require(E > 0 and E % 4 == 0, f"E={E} must be a multiple of 4")
+        _require(not _addr(loss) or _addr(target), "loss requested without target")
         pr, *_ = self._cos(flat(img, B * E, torch.float32).view(B, E), flat(txt, Cn * E, torch.float32).view(Cn, E),
                            flat(logit_scale, 1, torch.float32))
         flat(pred, B * Cn, torch.float32).copy_(pr.reshape(-1))
@@ -325,6 +436,11 @@ class RefLib:
         return d_img, d_txt
 
     def hba_cos_head_bwd(self, img, txt, B, Cn, E, logit_scale, d_pred, pred, target, d_img, d_txt, stream):
+        _require(_addr(img) and _addr(txt) and _addr(logit_scale) and (_addr(d_img) or _addr(d_txt)) and B > 0 and Cn > 0,
+                 "bad arguments")
+        _require(_addr(d_pred) or (_addr(pred) and _addr(target)), "need d_pred or (pred, target)")
+        _require(E % 4 == 0 and E <= 2048, f"E={E} unsupported")
+        _require(B <= 1024 and Cn <= 1024, "B, C must be <= 1024")
         iv, tv = flat(img, B * E, torch.float32).view(B, E), flat(txt, Cn * E, torch.float32).view(Cn, E)
         if _addr(d_pred):
             dp = flat(d_pred, B * Cn, torch.float32).view(B, Cn)
@@ -337,6 +453,15 @@ class RefLib:
 
     def hba_cos_mse_fwd(self, img, txt, B, Cn, E, groups, logit_scale, pred, target, tstride, loss, bad_step,
                         bad_total, total, workspace, stream):
+        _require(_addr(img) and _addr(txt) and _addr(logit_scale) and _addr(pred) and B > 0 and Cn > 0 and groups > 0,
+                 "bad arguments")
+        _require(E > 0 and E % 4 == 0, f"E={E} must be a multiple of 4")
+        _require(groups <= 65535, "too many groups")
+        if _addr(target):
+            _require(_addr(loss) and _addr(workspace), "target given without loss / workspace")
+        else:
+            _require(not (_addr(loss) or _addr(bad_step) or _addr(bad_total) or _addr(total)),
+                     "loss outputs requested without target")
         ls = flat(logit_scale, 1, torch.float32)
         for g in range(groups):
             iv = flat(_addr(img) + 4 * g * B * E, B * E, torch.float32).view(B, E)
@@ -359,6 +484,10 @@ class RefLib:
 
     def hba_cos_mse_bwd(self, img, txt, B, Cn, E, groups, logit_scale, pred, target, tstride, d_loss, d_img, d_txt,
                         stream):
+        _require(_addr(img) and _addr(txt) and _addr(logit_scale) and _addr(pred) and _addr(target)
+                 and (_addr(d_img) or _addr(d_txt)) and B > 0 and Cn > 0 and groups > 0, "bad arguments")
+        _require(E % 4 == 0 and E <= 2048, f"E={E} unsupported")
+        _require(B <= 1024 and Cn <= 1024 and groups <= 65535, "B, C must be <= 1024")
         ls = flat(logit_scale, 1, torch.float32)
         for g in range(groups):
             iv = flat(_addr(img) + 4 * g * B * E, B * E, torch.float32).view(B, E)
@@ -374,6 +503,8 @@ class RefLib:
     # ---------------------------------------------------------------- AdamW (torch.optim.AdamW arithmetic, NEW:1181)
     def hba_adamw_multi(self, ptrs, sizes, n, total, lr, beta1, beta2, eps, weight_decay, step, step_dev, skip_flag,
                         stream):
+        _require(_addr(ptrs) and _addr(sizes) and 0 < n <= 1024 and total > 0 and (step >= 1 or _addr(step_dev)),
+                 "bad arguments")
         if _addr(skip_flag) and int(flat(skip_flag, 1, torch.int32)[0]) != 0:
             return self._ok("hba_adamw_multi")
         if _addr(step_dev):
@@ -491,6 +622,12 @@ class RefLib:
 
     def hba_attention_bwd(self, qkv, qkv_dtype, ld_qkv, B, T, H, causal, d_out, do_dtype, ld_do, d_qkv, dq_dtype,
                           ld_dqkv, stream):
+        _require(_addr(qkv) and _addr(d_out) and _addr(d_qkv) and B > 0 and T > 0 and H > 0, "bad arguments")
+        _require(T <= 288, f"T={T} exceeds 288")
+        _require((qkv_dtype, do_dtype, dq_dtype) in ((1, 1, 1), (1, 0, 1), (0, 0, 0)),
+                 f"unsupported dtype combination ({qkv_dtype}, {do_dtype}, {dq_dtype})")
+        # (the fp32 form stages K / V / dK / dV of one head in shared memory: 4 * T * 64 floats + the per-warp rows)
+        _require(qkv_dtype == 1 or T <= 200, f"fp32 form: T={T} exceeds the shared-memory staging (T <= 200)")
         q, k, v = self._qkv(qkv, qkv_dtype, ld_qkv, B, T, H)
         do = mat(d_out, B * T, H * 64, ld_do, DT[do_dtype]).float().reshape(B, T, H, 64).permute(0, 2, 1, 3)
         full = torch.cat([t.permute(0, 2, 1, 3).reshape(B * T, H * 64) for t in self._attn_bwd(q, k, v, do, causal)], 1)
@@ -498,6 +635,8 @@ class RefLib:
         return self._ok("hba_attention_bwd")
 
     def hba_attention_fwd_lse(self, qkv, ld_qkv, B, T, H, causal, out, ld_out, lse, stream):
+        _require(_addr(qkv) and _addr(out) and _addr(lse) and B > 0 and T > 0 and H > 0, "bad arguments")
+        _require(T <= 257 and ld_qkv % 8 == 0 and ld_out % 8 == 0, f"T={T} (max 257) / leading dimensions unsupported")
         q, k, v = self._qkv(qkv, 1, ld_qkv, B, T, H)
         s_ = q @ k.transpose(-1, -2) / 8.0
         if causal:
@@ -508,6 +647,11 @@ class RefLib:
         return self._ok("hba_attention_fwd_lse")
 
     def hba_attention_bwd_lse(self, qkv, ld_qkv, B, T, H, causal, out, ld_out, d_out, ld_do, lse, d_qkv, ld_dqkv, stream):
+        _require(_addr(qkv) and _addr(out) and _addr(d_out) and _addr(lse) and _addr(d_qkv) and B > 0 and T > 0 and H > 0,
+                 "bad arguments")
+        _require(T <= 256, f"T={T} exceeds 256")
+        _require(ld_qkv % 8 == 0 and ld_out % 8 == 0 and ld_do % 8 == 0 and ld_dqkv % 8 == 0,
+                 "leading dimensions must be multiples of 8")
         q, k, v = self._qkv(qkv, 1, ld_qkv, B, T, H)
         do = mat(d_out, B * T, H * 64, ld_do, torch.bfloat16).float().reshape(B, T, H, 64).permute(0, 2, 1, 3)
         full = torch.cat([t.permute(0, 2, 1, 3).reshape(B * T, H * 64) for t in self._attn_bwd(q, k, v, do, causal)], 1)
@@ -556,6 +700,8 @@ class RefLib:
 
     # ---------------------------------------------------------------- helpers
     def hba_add_rows(self, dst, ld_dst, dst_row_step, src, ld_src, rows, cols, stream):
+        _require(_addr(dst) and _addr(src) and rows > 0 and cols > 0, "bad arguments")
+        dst_row_step = max(1, dst_row_step)
         d = flat(dst, ((rows - 1) * dst_row_step) * ld_dst + cols, torch.float32).as_strided(
             (rows, cols), (ld_dst * dst_row_step, 1))
         d.add_(mat(src, rows, cols, ld_src, torch.float32))
