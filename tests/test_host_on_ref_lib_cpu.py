@@ -332,6 +332,7 @@ def _abi_trace_of_default_placement():
     precision modes."""
     import ctypes as C
     import hba
+    from hba._lib import SIGNATURES
     from hba.engine import TrunkCache
     from hba.optim import FusedAdamW
     from oracle import clip_ref, dora_ref, libhba_ref
@@ -345,16 +346,14 @@ def _abi_trace_of_default_placement():
                 return fn
 
             def wrapped(*args):
+                # pointers (by the declared argument types of hba._lib, never by value) are recorded as given / null
                 if name == "hba_gemm_bf16":
                     p = args[0]._obj
-                    scal = ("M", "N", "K", "lda", "ldb", "nsplit", "a_lo_off", "b_lo_off", "ldr", "act", "ld_aux", "aux_dtype",
-                            "ld_pre", "pre_dtype", "ld_f32", "ld_bf16", "out_lo_off", "transpose_out", "max_ctas", "a_mn_major",
-                            "b_mn_major", "k_slices", "alpha")
-                    sig = tuple(getattr(p, f) if f in scal else bool(getattr(p, f)) for f, _ in p._fields_)
+                    sig = tuple(bool(getattr(p, f)) if t is C.c_void_p else getattr(p, f) for f, t in p._fields_)
                 else:
-                    sig = tuple((a is not None and not (isinstance(a, C.c_void_p) and not a.value))
-                                if (a is None or isinstance(a, C.c_void_p) or (isinstance(a, int) and a >= 1 << 27)) else a
-                                for a in args)
+                    types = SIGNATURES[name][1]
+                    assert len(types) == len(args), name
+                    sig = tuple(bool(libhba_ref._addr(a)) if t is C.c_void_p else a for a, t in zip(args, types))
                 rc = fn(*args)
                 trace.append((name, sig))
                 return rc
